@@ -1,0 +1,48 @@
+# Builds the CUDA library (product) and the CPU oracle (test infrastructure).
+#   make            -> rpt_b200/lib/librpt_b200.so + oracle/_build/liboracle.so
+#   make lib        -> product only
+#   make oracle     -> oracle only
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC,-fopenmp -Xptxas -v
+CSRC      := rpt_b200/csrc
+OBJDIR    := build/obj
+LIB       := rpt_b200/lib/librpt_b200.so
+ORACLE    := oracle/_build/liboracle.so
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/rpt_b200.h
+
+all: lib oracle
+lib: $(LIB)
+oracle: $(ORACLE)
+
+$(OBJDIR)/kernels_f32.o: $(CSRC)/kernels_f32.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/kernels_f32.ptxas.log || (cat $(OBJDIR)/kernels_f32.ptxas.log; false)
+# the parity gate keeps products and sums separately rounded, like the reference's f64 code
+$(OBJDIR)/kernels_f64.o: $(CSRC)/kernels_f64.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@ 2> $(OBJDIR)/kernels_f64.ptxas.log || (cat $(OBJDIR)/kernels_f64.ptxas.log; false)
+$(OBJDIR)/film.o: $(CSRC)/film.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/film.ptxas.log || (cat $(OBJDIR)/film.ptxas.log; false)
+$(OBJDIR)/api.o: $(CSRC)/api.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/api.ptxas.log || (cat $(OBJDIR)/api.ptxas.log; false)
+$(OBJDIR)/kdbuild.o: $(CSRC)/kdbuild.cpp include/rpt_b200.h
+	@mkdir -p $(OBJDIR)
+	$(CXX) -std=c++17 -O3 -fPIC -fopenmp -Wall -c $< -o $@
+
+$(LIB): $(OBJDIR)/kernels_f32.o $(OBJDIR)/kernels_f64.o $(OBJDIR)/film.o $(OBJDIR)/api.o $(OBJDIR)/kdbuild.o
+	@mkdir -p rpt_b200/lib
+	$(NVCC) -shared $(ARCH) -o $@ $^ -Xcompiler -fopenmp -lgomp -cudart shared
+
+# -march=x86-64-v3: AVX2 hosts (this container and the GPU boxes); no FMA contraction so
+# the f64 arithmetic rounds like the reference's
+$(ORACLE): oracle/oracle.cpp include/rpt_b200.h
+	@mkdir -p oracle/_build
+	$(CXX) -std=c++17 -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp -fPIC -shared -Wall -Wextra -o $@ $<
+
+clean:
+	rm -rf build $(LIB) $(ORACLE)
+.PHONY: all lib oracle clean

@@ -1,0 +1,273 @@
+/*
+ * rpt_b200.h -- C ABI of the B200-native path-tracing core that stands where
+ * rpt's private `Renderer::sample` stands today.
+ *
+ * Every entry point cites the reference interface it replaces.  Citations are
+ * relative to the reference checkout (ekzhang/rpt @ 815b21c):
+ *
+ *   Renderer::sample / get_color / trace_ray   src/renderer.rs:117-174
+ *   Renderer::sample_lights / get_closest_hit  src/renderer.rs:177-220
+ *   Scene / Object / Light / Environment       src/scene.rs:7-41, src/object.rs:10-32,
+ *                                              src/light.rs:7-19, src/environment.rs:4-14,55-63
+ *   Material                                   src/material.rs:7-26
+ *   Camera                                     src/camera.rs:8-26
+ *   KdTree<Triangle> (= Mesh)                  src/kdtree.rs:99-119,226-233, src/shape/mesh.rs:7-22,102
+ *   Buffer::image / variance, color_bytes      src/buffer.rs:43-93, src/color.rs:17-23
+ *
+ * All structs are plain-old-data; all pointers are caller-owned host memory
+ * unless the name says `_device`.  Values cross the boundary as `double`
+ * because every quantity in the reference is `f64` (src/color.rs:2); the
+ * library converts to its device layout (f32 SoA, or f64 for the parity gate)
+ * inside rptb_scene_create.
+ *
+ * Error model: every function returning `int` returns RPTB_OK (0) or a
+ * negative rptb_status; the message is available from rptb_last_error()
+ * (thread-local).  Nothing unwinds or aborts across the boundary.  NaN/inf in
+ * inputs are passed through -- the reference does not validate them either.
+ *
+ * Threading: a rptb_scene is immutable after creation (the reference shares
+ * `&Scene` read-only across rayon workers, src/shape.rs:18 `Send + Sync`).
+ * Render calls on one handle are serialised internally.
+ */
+#ifndef RPT_B200_H
+#define RPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPTB_VERSION 100
+
+typedef enum rptb_status {
+    RPTB_OK = 0,
+    RPTB_ERR_BAD_ARG = -1,   /* null pointer, out-of-range index, bad enum   */
+    RPTB_ERR_CUDA = -2,      /* a CUDA runtime call failed (message has it)  */
+    RPTB_ERR_NO_DEVICE = -3, /* no usable sm_100 device / extension missing  */
+    RPTB_ERR_OOM = -4,       /* host or device allocation failed             */
+    RPTB_ERR_UNSUPPORTED = -5
+} rptb_status;
+
+/* ---- Material: src/material.rs:7-26 (six fields, same meaning) ---------- */
+typedef struct rptb_material {
+    double color[3];
+    double index;
+    double roughness;
+    double metallic;
+    double emittance;
+    uint32_t transparent; /* bool */
+    uint32_t _pad;
+} rptb_material;
+
+/* ---- KdTree<Triangle>: src/kdtree.rs:99-104,226-233 ---------------------
+ * The reference's pointer tree is serialised in depth-first pre-order.
+ * kind 0/1/2 = SplitX/SplitY/SplitZ(split, left, right); kind 3 = Leaf whose
+ * triangle indices are refs[first_ref .. first_ref+num_refs) in the order of
+ * the reference's Vec<usize> (ascending triangle index, src/kdtree.rs:270-281).
+ */
+typedef struct rptb_kdnode {
+    double split;
+    uint32_t kind;
+    uint32_t left;      /* node index of the left child  (kind 0..2) */
+    uint32_t right;     /* node index of the right child (kind 0..2) */
+    uint32_t first_ref; /* kind 3 */
+    uint32_t num_refs;  /* kind 3 */
+    uint32_t _pad;
+} rptb_kdnode;
+
+/* Mesh = KdTree<Triangle>; a triangle is 18 doubles v1,v2,v3,n1,n2,n3
+ * (src/shape/mesh.rs:7-22).  If `nodes` is NULL the library builds the
+ * reference-shaped tree itself (rptb_build_kdtree, src/kdtree.rs:235-355). */
+typedef struct rptb_mesh {
+    const double* tris;
+    uint64_t ntris;
+    const rptb_kdnode* nodes;
+    uint64_t nnodes;
+    const uint32_t* refs;
+    uint64_t nrefs;
+} rptb_mesh;
+
+/* ---- Object { shape: Box<dyn Shape>, material }: src/object.rs:10-16 ----
+ * The type-erased shape is made explicit.  `has_transform` distinguishes a
+ * bare shape from Transformed<T> (src/shape.rs:99-137); `transform` is the
+ * composed column-major 4x4 `Transformed::transform`.                        */
+typedef enum rptb_shape_kind {
+    RPTB_SHAPE_SPHERE = 0, /* src/shape/sphere.rs:13-64 */
+    RPTB_SHAPE_PLANE = 1,  /* src/shape/plane.rs:17-32  */
+    RPTB_SHAPE_CUBE = 2,   /* src/shape/cube.rs:20-87   */
+    RPTB_SHAPE_MESH = 3    /* src/kdtree.rs:129-143 + src/shape/mesh.rs:49-98 */
+} rptb_shape_kind;
+
+typedef struct rptb_object {
+    uint32_t kind;          /* rptb_shape_kind */
+    uint32_t material;      /* index into rptb_scene_desc.materials */
+    uint32_t mesh;          /* index into rptb_scene_desc.meshes (MESH only) */
+    uint32_t has_transform; /* 0 = bare shape, 1 = Transformed<T> */
+    double transform[16];   /* column-major */
+    double plane_normal[3]; /* PLANE only: x . normal = value */
+    double plane_value;
+} rptb_object;
+
+/* ---- Light: src/light.rs:7-19 -------------------------------------------- */
+typedef enum rptb_light_kind {
+    RPTB_LIGHT_POINT = 0,       /* Point(color, location)        */
+    RPTB_LIGHT_AMBIENT = 1,     /* Ambient(color)                */
+    RPTB_LIGHT_DIRECTIONAL = 2, /* Directional(color, direction) */
+    RPTB_LIGHT_OBJECT = 3       /* Object(Object) -- invisible emitter */
+} rptb_light_kind;
+
+typedef struct rptb_light {
+    uint32_t kind;
+    uint32_t _pad;
+    double color[3];
+    double vec[3];      /* location (POINT) or direction (DIRECTIONAL) */
+    rptb_object object; /* OBJECT only; its material holds colour/emittance */
+} rptb_light;
+
+/* ---- Environment: src/environment.rs:4-14,55-63 --------------------------- */
+typedef enum rptb_env_kind { RPTB_ENV_COLOR = 0, RPTB_ENV_HDRI = 1 } rptb_env_kind;
+
+typedef struct rptb_env {
+    uint32_t kind;
+    uint32_t width, height; /* HDRI */
+    uint32_t _pad;
+    double color[3];        /* COLOR */
+    const double* texels;   /* HDRI: width*height*3, row-major, row 0 = +y pole */
+} rptb_env;
+
+/* ---- Scene: src/scene.rs:7-18 ---------------------------------------------- */
+typedef struct rptb_scene_desc {
+    const rptb_material* materials;
+    uint32_t nmaterials;
+    const rptb_mesh* meshes;
+    uint32_t nmeshes;
+    const rptb_object* objects; /* scene.objects, in order */
+    uint32_t nobjects;
+    const rptb_light* lights;   /* scene.lights, in order */
+    uint32_t nlights;
+    rptb_env environment;
+} rptb_scene_desc;
+
+/* ---- Camera: src/camera.rs:8-26 (same six fields) -------------------------- */
+typedef struct rptb_camera {
+    double eye[3];
+    double direction[3];
+    double up[3];
+    double fov;
+    double aperture;
+    double focal_distance;
+} rptb_camera;
+
+/* ---- Renderer parameters: src/renderer.rs:18-57 ----------------------------
+ * width/height/max_bounces/exposure_value are the builder fields; `iterations`
+ * is the argument of Renderer::sample.  The reference seeds every row from OS
+ * entropy (src/renderer.rs:121); here the stream is Philox4x32-10 keyed by
+ * (seed, pixel, first_sample + i), so iterative_render passes an advancing
+ * first_sample to get the disjoint streams fresh entropy gave it.            */
+typedef enum rptb_precision {
+    RPTB_PRECISION_F32 = 0, /* the product path */
+    RPTB_PRECISION_F64 = 1  /* parity gate: literal f64 semantics, no ray offsets */
+} rptb_precision;
+
+typedef struct rptb_render_params {
+    uint32_t width;
+    uint32_t height;
+    uint32_t iterations;
+    uint32_t max_bounces;
+    double exposure_value;
+    uint64_t seed;
+    uint64_t first_sample;
+    uint32_t shard_index; /* this process renders pixel tiles t with      */
+    uint32_t shard_count; /* t % shard_count == shard_index; others stay 0 */
+    uint32_t precision;   /* rptb_precision */
+    uint32_t collect_stats; /* 0 = segments only; 1 = + node visits / tri tests */
+} rptb_render_params;
+
+typedef struct rptb_stats {
+    uint64_t segments;    /* trace_ray invocations (src/renderer.rs:145)       */
+    uint64_t rays;        /* get_closest_hit calls incl. shadow rays (:211)    */
+    uint64_t node_visits; /* kd nodes visited (src/kdtree.rs:151), if collected */
+    uint64_t tri_tests;   /* Triangle::intersect calls (mesh.rs:49), if collected */
+    uint64_t mesh_hits;   /* closest hits that landed on a mesh                */
+    uint64_t env_lookups; /* escaped paths that sampled an HDRI                */
+    double gpu_ms;        /* device time of the render launch(es)              */
+    uint32_t launches;    /* kernels launched by the call                      */
+    uint32_t _pad;
+} rptb_stats;
+
+typedef struct rptb_scene rptb_scene; /* opaque */
+
+/* Thread-local message of the last failing call. */
+const char* rptb_last_error(void);
+
+/* Library/device info: returns the CUDA device count (>=0) or a negative status. */
+int rptb_device_count(void);
+
+/* Replaces: construction of the borrowed `&Scene` the renderer walks
+ * (src/renderer.rs:20, src/scene.rs:7-18).  Copies everything to `device`. */
+int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out);
+void rptb_scene_destroy(rptb_scene* scene);
+/* Bytes of flattened scene resident on the device (f32 layout). */
+uint64_t rptb_scene_device_bytes(const rptb_scene* scene);
+
+/* Replaces: Renderer::sample's `colors: Vec<Color>` (src/renderer.rs:117-129).
+ * Writes width*height*3 doubles, row-major y*width+x, y = 0 top row: the mean
+ * of `iterations` path samples per pixel times 2^exposure_value (:131-142).  */
+int rptb_render_samples(rptb_scene* scene, const rptb_camera* camera,
+                        const rptb_render_params* params, double* out_rgb,
+                        rptb_stats* stats /* nullable */);
+
+/* Same computation, result left in device memory as float[width*height*3] on
+ * CUDA stream `stream` (a cudaStream_t; NULL = the library's own stream, and
+ * the call then synchronises).  Used by multi-GPU hosts that all-reduce the
+ * buffer with NCCL, and by bench.py's device-resident timing.  Pixels of
+ * other shards are written as zero.                                          */
+int rptb_render_samples_device(rptb_scene* scene, const rptb_camera* camera,
+                               const rptb_render_params* params, float* out_rgb_device,
+                               void* stream, rptb_stats* stats /* nullable, forces sync */);
+
+/* Replaces: Renderer::get_closest_hit (src/renderer.rs:211-220) for `n` world
+ * rays (n x 6 doubles: origin, dir).  out_t[i] = +inf and out_object[i] = -1
+ * on a miss; out_normal is n x 3.  precision as in rptb_precision.           */
+int rptb_closest_hit(rptb_scene* scene, const double* rays, uint64_t n, double t_min,
+                     uint32_t precision, double* out_t, int32_t* out_object,
+                     double* out_normal /* nullable */, rptb_stats* stats /* nullable */);
+
+/* Point-wise Material::bsdf (src/material.rs:125-210) on the device:
+ * `dirs` is n x 9 doubles (n, wo, wi); out is n x 3.                         */
+int rptb_bsdf_eval(const rptb_material* material, const double* dirs, uint64_t n,
+                   uint32_t precision, int device, double* out);
+
+/* Material::sample_f (src/material.rs:224-313) on the device: `dirs` is n x 6
+ * (n, wo); draw i uses Philox key (seed, i).  out_wi n x 3, out_pdf n;
+ * pdf = -1 encodes `None`.                                                    */
+int rptb_sample_f(const rptb_material* material, const double* dirs, uint64_t n, uint64_t seed,
+                  uint32_t precision, int device, double* out_wi, double* out_pdf);
+
+/* Replaces: KdTree::new -> construct (src/kdtree.rs:108-119,235-355).  Host
+ * side; produces the reference-shaped tree for hosts that cannot hand theirs
+ * over.  Free with rptb_free_kdtree.                                          */
+typedef struct rptb_kdtree_out {
+    rptb_kdnode* nodes;
+    uint64_t nnodes;
+    uint32_t* refs;
+    uint64_t nrefs;
+    uint32_t depth;
+    uint32_t max_leaf;
+} rptb_kdtree_out;
+int rptb_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out);
+void rptb_free_kdtree(rptb_kdtree_out* out);
+
+/* Replaces: Buffer::image -> get_filtered_color -> color_bytes
+ * (src/buffer.rs:43-56,75-93, src/color.rs:17-23) for a buffer holding
+ * `nbatches` equally weighted entries per pixel (sums[] = per-pixel sum over
+ * the entries, width*height*3 doubles).  out_rgb8 = width*height*3 bytes.    */
+int rptb_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height,
+                      uint32_t box_radius, int device, uint8_t* out_rgb8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPT_B200_H */

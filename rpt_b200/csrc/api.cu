@@ -1,0 +1,887 @@
+// api.cu -- the extern "C" boundary of include/rpt_b200.h: flattens a
+// rptb_scene_desc into the device layout of scene_dev.cuh and drives the kernels.
+//
+// What it stands in for on the reference side (ekzhang/rpt @815b21c):
+//   rptb_scene_create          the borrowed &Scene of Renderer (src/renderer.rs:20) +
+//                              Transformed::new precomputation (src/shape.rs:111-124)
+//   rptb_render_samples[_device] Renderer::sample (src/renderer.rs:117-129)
+//   rptb_closest_hit           Renderer::get_closest_hit (src/renderer.rs:211-220)
+//   rptb_bsdf_eval / sample_f  Material::bsdf / sample_f (src/material.rs:125-313)
+//   rptb_build_kdtree          KdTree::new (src/kdtree.rs:108-119,235-355)
+//   rptb_film_resolve          Buffer::image (src/buffer.rs:43-56,75-93)
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rpt_b200.h"
+#include "launch.h"
+
+namespace rptb {
+int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
+                      uint32_t& depth, uint32_t& max_leaf);
+cudaError_t launch_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height,
+                                uint32_t radius, uint8_t* out, cudaStream_t stream);
+cudaError_t launch_convert_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t stream);
+}  // namespace rptb
+
+using namespace rptb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? RPTB_ERR_OOM : RPTB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// All device allocations of a scene, freed together.
+struct Arena {
+    std::vector<void*> ptrs;
+    uint64_t bytes = 0;
+    template <class T>
+    cudaError_t upload(const std::vector<T>& host, const T** dev) {
+        *dev = nullptr;
+        if (host.empty()) return cudaSuccess;
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, host.size() * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        bytes += host.size() * sizeof(T);
+        e = cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+        *dev = (const T*)p;
+        return e;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+// ---- small double-precision matrix helpers (column-major 4x4 in) -------------------
+struct Xf {
+    double fwd[12];  // rows of the 3x4
+    double inv[12];
+    double nrm[9];   // rows of (L^-1)^T
+    double det;
+};
+
+bool invert4(const double* m /*col-major*/, double* out /*col-major*/) {
+    double w[4][8];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            w[r][c] = m[c * 4 + r];
+            w[r][c + 4] = r == c ? 1.0 : 0.0;
+        }
+    for (int i = 0; i < 4; i++) {
+        int p = i;
+        for (int r = i + 1; r < 4; r++)
+            if (std::fabs(w[r][i]) > std::fabs(w[p][i])) p = r;
+        if (w[p][i] == 0.0) return false;
+        if (p != i)
+            for (int c = 0; c < 8; c++) std::swap(w[i][c], w[p][c]);
+        const double piv = w[i][i];
+        for (int c = 0; c < 8; c++) w[i][c] /= piv;
+        for (int r = 0; r < 4; r++)
+            if (r != i && w[r][i] != 0.0) {
+                const double f = w[r][i];
+                for (int c = 0; c < 8; c++) w[r][c] -= f * w[i][c];
+            }
+    }
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) out[c * 4 + r] = w[r][c + 4];
+    return true;
+}
+
+// Transformed::new (src/shape.rs:111-124)
+bool make_xf(const double* t /*col-major 4x4*/, Xf& x) {
+    double inv[16];
+    if (!invert4(t, inv)) return false;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) {
+            x.fwd[r * 4 + c] = t[c * 4 + r];
+            x.inv[r * 4 + c] = inv[c * 4 + r];
+        }
+    // linear = upper-left 3x3; L(r,c) = t[c*4+r]
+    auto L = [&](int r, int c) { return t[c * 4 + r]; };
+    const double det = L(0, 0) * (L(1, 1) * L(2, 2) - L(1, 2) * L(2, 1)) - L(0, 1) * (L(1, 0) * L(2, 2) - L(1, 2) * L(2, 0)) +
+                       L(0, 2) * (L(1, 0) * L(2, 1) - L(1, 1) * L(2, 0));
+    x.det = det;
+    // inverse transpose = cofactor matrix / det
+    double cof[3][3];
+    cof[0][0] = L(1, 1) * L(2, 2) - L(1, 2) * L(2, 1);
+    cof[0][1] = -(L(1, 0) * L(2, 2) - L(1, 2) * L(2, 0));
+    cof[0][2] = L(1, 0) * L(2, 1) - L(1, 1) * L(2, 0);
+    cof[1][0] = -(L(0, 1) * L(2, 2) - L(0, 2) * L(2, 1));
+    cof[1][1] = L(0, 0) * L(2, 2) - L(0, 2) * L(2, 0);
+    cof[1][2] = -(L(0, 0) * L(2, 1) - L(0, 1) * L(2, 0));
+    cof[2][0] = L(0, 1) * L(1, 2) - L(0, 2) * L(1, 1);
+    cof[2][1] = -(L(0, 0) * L(1, 2) - L(0, 2) * L(1, 0));
+    cof[2][2] = L(0, 0) * L(1, 1) - L(0, 1) * L(1, 0);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) x.nrm[r * 3 + c] = cof[r][c] / det;
+    return true;
+}
+
+template <class R>
+void fill_object(const rptb_object& o, ObjectRec<R>& rec) {
+    std::memset(&rec, 0, sizeof(rec));
+    rec.kind = o.kind;
+    rec.material = o.material;
+    rec.mesh = o.mesh;
+    rec.has_transform = o.has_transform ? 1u : 0u;
+    Xf x;
+    static const double ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    make_xf(o.has_transform ? o.transform : ident, x);
+    for (int i = 0; i < 12; i++) {
+        rec.inv[i] = (R)x.inv[i];
+        rec.fwd[i] = (R)x.fwd[i];
+    }
+    for (int i = 0; i < 9; i++) rec.nrm[i] = (R)x.nrm[i];
+    rec.det = (R)x.det;
+    const double len = std::sqrt(o.plane_normal[0] * o.plane_normal[0] + o.plane_normal[1] * o.plane_normal[1] +
+                                 o.plane_normal[2] * o.plane_normal[2]);
+    for (int i = 0; i < 3; i++) {
+        rec.plane_n[i] = (R)o.plane_normal[i];
+        rec.plane_unit[i] = (R)(len > 0 ? o.plane_normal[i] / len : 0.0);
+    }
+    rec.plane_v = (R)o.plane_value;
+}
+
+template <class R>
+void fill_material(const rptb_material& m, MaterialRec<R>& rec) {
+    for (int i = 0; i < 3; i++) rec.color[i] = (R)m.color[i];
+    rec.index = (R)m.index;
+    rec.roughness = (R)m.roughness;
+    rec.metallic = (R)m.metallic;
+    rec.emittance = (R)m.emittance;
+    rec.transparent = m.transparent ? 1u : 0u;
+}
+
+// One flattened mesh on the host, before upload.
+struct HostMesh {
+    std::vector<KdNodeDev> nodes32;
+    std::vector<KdNodeDev64> nodes64;
+    std::vector<uint32_t> refs;
+    std::vector<float4> tri48;
+    std::vector<float> verts32, norms32;
+    std::vector<double> verts64, norms64;
+    double bmin[3], bmax[3];
+    uint32_t ntris = 0, depth = 0;
+};
+
+// Re-serialise the boundary tree in DFS pre-order (left child = node + 1) into both node formats.
+int flatten_nodes(const rptb_kdnode* in, uint64_t nnodes, const uint32_t* in_refs, uint64_t nrefs, uint64_t ntris,
+                  HostMesh& hm) {
+    struct Item {
+        uint32_t src;
+        uint32_t depth;
+        int64_t parent;  // dst index of the parent waiting for its right-child index, -1 if none
+    };
+    std::vector<Item> stack;
+    stack.push_back({0, 0, -1});
+    hm.depth = 0;
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        if (it.src >= nnodes) return fail(RPTB_ERR_BAD_ARG, "kd node index %u out of range (%llu nodes)", it.src, (unsigned long long)nnodes);
+        if (hm.nodes32.size() > nnodes) return fail(RPTB_ERR_BAD_ARG, "kd tree is not a tree (cycle?)");
+        const rptb_kdnode& s = in[it.src];
+        const uint32_t dst = (uint32_t)hm.nodes32.size();
+        if (it.parent >= 0) {  // we are the right child of `parent`
+            hm.nodes32[it.parent].word |= dst << 2;
+            hm.nodes64[it.parent].word |= dst << 2;
+        }
+        hm.depth = std::max(hm.depth, it.depth);
+        KdNodeDev n32;
+        KdNodeDev64 n64;
+        if (s.kind == 3) {
+            if ((uint64_t)s.first_ref + s.num_refs > nrefs) return fail(RPTB_ERR_BAD_ARG, "kd leaf refs out of range");
+            if (s.num_refs >= (1u << 30)) return fail(RPTB_ERR_UNSUPPORTED, "kd leaf too large");
+            const uint32_t first = (uint32_t)hm.refs.size();
+            for (uint32_t i = 0; i < s.num_refs; i++) {
+                const uint32_t t = in_refs[s.first_ref + i];
+                if (t >= ntris) return fail(RPTB_ERR_BAD_ARG, "kd leaf references triangle %u of %llu", t, (unsigned long long)ntris);
+                hm.refs.push_back(t);
+            }
+            n32.first_ref = first;
+            n32.word = (s.num_refs << 2) | 3u;
+            n64.split = 0.0;
+            n64.first_ref = first;
+            n64.word = n32.word;
+            hm.nodes32.push_back(n32);
+            hm.nodes64.push_back(n64);
+        } else if (s.kind <= 2) {
+            n32.split = (float)s.split;
+            n32.word = s.kind;  // right child patched in when it is emitted
+            n64.split = s.split;
+            n64.first_ref = 0;
+            n64.word = s.kind;
+            hm.nodes32.push_back(n32);
+            hm.nodes64.push_back(n64);
+            // pre-order: left next (pushed last), right later with a back-pointer to us
+            stack.push_back({s.right, it.depth + 1, (int64_t)dst});
+            stack.push_back({s.left, it.depth + 1, -1});
+        } else {
+            return fail(RPTB_ERR_BAD_ARG, "kd node kind %u", s.kind);
+        }
+    }
+    if (hm.nodes32.size() >= (1u << 30)) return fail(RPTB_ERR_UNSUPPORTED, "kd tree has too many nodes");
+    return RPTB_OK;
+}
+
+int flatten_mesh(const rptb_mesh& m, HostMesh& hm) {
+    if (m.ntris == 0 || m.tris == nullptr) return fail(RPTB_ERR_BAD_ARG, "mesh without triangles");
+    if (m.ntris >= (1ull << 31)) return fail(RPTB_ERR_UNSUPPORTED, "mesh too large");
+    hm.ntris = (uint32_t)m.ntris;
+    int rc;
+    if (m.nodes == nullptr) {
+        std::vector<rptb_kdnode> nodes;
+        std::vector<uint32_t> refs;
+        uint32_t depth, max_leaf;
+        build_kdtree_host(m.tris, m.ntris, nodes, refs, depth, max_leaf);
+        rc = flatten_nodes(nodes.data(), nodes.size(), refs.data(), refs.size(), m.ntris, hm);
+    } else {
+        rc = flatten_nodes(m.nodes, m.nnodes, m.refs, m.nrefs, m.ntris, hm);
+    }
+    if (rc != RPTB_OK) return rc;
+    if (hm.depth >= (uint32_t)KD_STACK) return fail(RPTB_ERR_UNSUPPORTED, "kd tree depth %u exceeds the traversal stack (%d)", hm.depth, KD_STACK);
+
+    for (int a = 0; a < 3; a++) {
+        hm.bmin[a] = INFINITY;
+        hm.bmax[a] = -INFINITY;
+    }
+    hm.tri48.resize(3 * (size_t)m.ntris);
+    hm.verts32.resize(9 * (size_t)m.ntris);
+    hm.norms32.resize(9 * (size_t)m.ntris);
+    hm.verts64.resize(9 * (size_t)m.ntris);
+    hm.norms64.resize(9 * (size_t)m.ntris);
+    for (uint64_t i = 0; i < m.ntris; i++) {
+        const double* t = m.tris + 18 * i;
+        for (int k = 0; k < 9; k++) {
+            hm.verts64[9 * i + k] = t[k];
+            hm.verts32[9 * i + k] = (float)t[k];
+            hm.norms64[9 * i + k] = t[9 + k];
+            hm.norms32[9 * i + k] = (float)t[9 + k];
+        }
+        for (int a = 0; a < 3; a++) {  // KdTree::bounds = merge of Triangle::bounding_box
+            hm.bmin[a] = std::fmin(hm.bmin[a], std::fmin(std::fmin(t[a], t[3 + a]), t[6 + a]));
+            hm.bmax[a] = std::fmax(hm.bmax[a], std::fmax(std::fmax(t[a], t[3 + a]), t[6 + a]));
+        }
+        // the per-triangle invariants of Triangle::intersect (mesh.rs:50-72), folded in double
+        const double d0[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]};
+        const double d1[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
+        double pn[3] = {d0[1] * d1[2] - d0[2] * d1[1], d0[2] * d1[0] - d0[0] * d1[2], d0[0] * d1[1] - d0[1] * d1[0]};
+        const double len = std::sqrt(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);
+        for (int a = 0; a < 3; a++) pn[a] /= len;
+        const double d00 = d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2];
+        const double d01 = d0[0] * d1[0] + d0[1] * d1[1] + d0[2] * d1[2];
+        const double d11 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2];
+        const double denom = d00 * d11 - d01 * d01;
+        double A[3], B[3];
+        for (int a = 0; a < 3; a++) {
+            A[a] = (d11 * d0[a] - d01 * d1[a]) / denom;
+            B[a] = (d00 * d1[a] - d01 * d0[a]) / denom;
+        }
+        const double pnv1 = pn[0] * t[0] + pn[1] * t[1] + pn[2] * t[2];
+        const double a0 = -(A[0] * t[0] + A[1] * t[1] + A[2] * t[2]);
+        const double b0 = -(B[0] * t[0] + B[1] * t[1] + B[2] * t[2]);
+        hm.tri48[3 * i + 0] = make_float4((float)pn[0], (float)pn[1], (float)pn[2], (float)pnv1);
+        hm.tri48[3 * i + 1] = make_float4((float)A[0], (float)A[1], (float)A[2], (float)a0);
+        hm.tri48[3 * i + 2] = make_float4((float)B[0], (float)B[1], (float)B[2], (float)b0);
+    }
+    return RPTB_OK;
+}
+
+template <class R>
+struct Tables {
+    std::vector<ObjectRec<R>> objects;
+    std::vector<LightRec<R>> lights;
+    std::vector<MaterialRec<R>> materials;
+    std::vector<MeshRec<R>> meshes;
+};
+
+}  // namespace
+
+struct rptb_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Arena arena;
+    SceneView<float> view32;
+    SceneView<double> view64;
+    DeviceCounters* counters = nullptr;
+    // cached output buffers of rptb_render_samples
+    float* out32 = nullptr;
+    double* out64 = nullptr;
+    size_t out_vals = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex lock;
+    uint64_t f32_bytes = 0;
+};
+
+namespace {
+
+int validate_object(const rptb_scene_desc* d, const rptb_object& o, const char* what, uint32_t i) {
+    if (o.kind > RPTB_SHAPE_MESH) return fail(RPTB_ERR_BAD_ARG, "%s %u: bad shape kind %u", what, i, o.kind);
+    if (o.material >= d->nmaterials) return fail(RPTB_ERR_BAD_ARG, "%s %u: material %u out of range", what, i, o.material);
+    if (o.kind == RPTB_SHAPE_MESH && o.mesh >= d->nmeshes) return fail(RPTB_ERR_BAD_ARG, "%s %u: mesh %u out of range", what, i, o.mesh);
+    if (o.has_transform) {
+        Xf x;
+        if (!make_xf(o.transform, x)) return fail(RPTB_ERR_BAD_ARG, "%s %u: singular transform", what, i);
+    }
+    return RPTB_OK;
+}
+
+template <class R>
+void fill_tables(const rptb_scene_desc* d, Tables<R>& t) {
+    t.objects.resize(d->nobjects);
+    for (uint32_t i = 0; i < d->nobjects; i++) fill_object(d->objects[i], t.objects[i]);
+    t.materials.resize(d->nmaterials);
+    for (uint32_t i = 0; i < d->nmaterials; i++) fill_material(d->materials[i], t.materials[i]);
+    t.lights.resize(d->nlights);
+    for (uint32_t i = 0; i < d->nlights; i++) {
+        const rptb_light& l = d->lights[i];
+        LightRec<R>& r = t.lights[i];
+        std::memset(&r, 0, sizeof(r));
+        r.kind = l.kind;
+        for (int k = 0; k < 3; k++) {
+            r.color[k] = (R)l.color[k];
+            r.vec[k] = (R)l.vec[k];
+        }
+        if (l.kind == RPTB_LIGHT_OBJECT) {
+            fill_object(l.object, r.object);
+            const rptb_material& m = d->materials[l.object.material];
+            for (int k = 0; k < 3; k++) r.radiance[k] = (R)(m.color[k] * m.emittance);  // light.rs:42
+        }
+    }
+}
+
+template <class R>
+int upload_tables(rptb_scene* s, const Tables<R>& t, SceneView<R>& v) {
+    CU(s->arena.upload(t.objects, &v.objects));
+    CU(s->arena.upload(t.lights, &v.lights));
+    CU(s->arena.upload(t.materials, &v.materials));
+    CU(s->arena.upload(t.meshes, &v.meshes));
+    v.nobjects = (uint32_t)t.objects.size();
+    v.nlights = (uint32_t)t.lights.size();
+    v.nmaterials = (uint32_t)t.materials.size();
+    v.nmeshes = (uint32_t)t.meshes.size();
+    v.tables_in_const = 0;
+    return RPTB_OK;
+}
+
+int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
+    Tables<float> t32;
+    Tables<double> t64;
+    fill_tables(d, t32);
+    fill_tables(d, t64);
+    t32.meshes.resize(d->nmeshes);
+    t64.meshes.resize(d->nmeshes);
+    for (uint32_t i = 0; i < d->nmeshes; i++) {
+        HostMesh hm;
+        const int rc = flatten_mesh(d->meshes[i], hm);
+        if (rc != RPTB_OK) return rc;
+        MeshRec<float>& a = t32.meshes[i];
+        MeshRec<double>& b = t64.meshes[i];
+        std::memset(&a, 0, sizeof(a));
+        std::memset(&b, 0, sizeof(b));
+        const uint64_t before = s->arena.bytes;
+        CU(s->arena.upload(hm.nodes32, &a.nodes));
+        CU(s->arena.upload(hm.refs, &a.refs));
+        CU(s->arena.upload(hm.tri48, &a.tri48));
+        CU(s->arena.upload(hm.verts32, &a.verts));
+        CU(s->arena.upload(hm.norms32, &a.norms));
+        s->f32_bytes += s->arena.bytes - before;
+        CU(s->arena.upload(hm.nodes64, &b.nodes));
+        b.refs = a.refs;
+        b.tri48 = nullptr;
+        CU(s->arena.upload(hm.verts64, &b.verts));
+        CU(s->arena.upload(hm.norms64, &b.norms));
+        for (int k = 0; k < 3; k++) {
+            a.bmin[k] = (float)hm.bmin[k];
+            a.bmax[k] = (float)hm.bmax[k];
+            b.bmin[k] = hm.bmin[k];
+            b.bmax[k] = hm.bmax[k];
+        }
+        // f32 bounds must contain the f32 vertices: widen by one ulp outward
+        for (int k = 0; k < 3; k++) {
+            a.bmin[k] = std::nextafterf(a.bmin[k], -INFINITY);
+            a.bmax[k] = std::nextafterf(a.bmax[k], INFINITY);
+        }
+        a.ntris = b.ntris = hm.ntris;
+        a.root_is_leaf = b.root_is_leaf = (hm.nodes32[0].word & 3u) == 3u;
+    }
+    {
+        const uint64_t before = s->arena.bytes;
+        int rc = upload_tables(s, t32, s->view32);
+        if (rc != RPTB_OK) return rc;
+        s->f32_bytes += s->arena.bytes - before;
+        rc = upload_tables(s, t64, s->view64);
+        if (rc != RPTB_OK) return rc;
+    }
+    // environment
+    std::memset(&s->view32.env, 0, sizeof(s->view32.env));
+    std::memset(&s->view64.env, 0, sizeof(s->view64.env));
+    s->view32.env.kind = s->view64.env.kind = d->environment.kind;
+    for (int k = 0; k < 3; k++) {
+        s->view32.env.color[k] = (float)d->environment.color[k];
+        s->view64.env.color[k] = d->environment.color[k];
+    }
+    if (d->environment.kind == RPTB_ENV_HDRI) {
+        const uint32_t w = d->environment.width, h = d->environment.height;
+        if (w == 0 || h == 0 || d->environment.texels == nullptr) return fail(RPTB_ERR_BAD_ARG, "HDRI without texels");
+        const size_t n = (size_t)w * h;
+        std::vector<float4> tex(n);
+        for (size_t i = 0; i < n; i++)
+            tex[i] = make_float4((float)d->environment.texels[3 * i], (float)d->environment.texels[3 * i + 1],
+                                 (float)d->environment.texels[3 * i + 2], 0.0f);
+        std::vector<double> tex64(d->environment.texels, d->environment.texels + 3 * n);
+        const uint64_t before = s->arena.bytes;
+        CU(s->arena.upload(tex, &s->view32.env.texels_f4));
+        s->f32_bytes += s->arena.bytes - before;
+        CU(s->arena.upload(tex64, &s->view64.env.texels_f64));
+        s->view32.env.width = s->view64.env.width = w;
+        s->view32.env.height = s->view64.env.height = h;
+    }
+    CU(cudaMalloc(&s->counters, sizeof(DeviceCounters)));
+    CU(cudaMemset(s->counters, 0, sizeof(DeviceCounters)));
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    return RPTB_OK;
+}
+
+template <class R>
+void fill_args(const rptb_camera* cam, const rptb_render_params* p, RenderArgs<R>& a) {
+    std::memset(&a, 0, sizeof(a));
+    // Camera::cast_ray invariants (src/camera.rs:66-67)
+    const double d = 1.0 / std::tan(cam->fov / 2.0);
+    const double* di = cam->direction;
+    const double* up = cam->up;
+    double right[3] = {di[1] * up[2] - di[2] * up[1], di[2] * up[0] - di[0] * up[2], di[0] * up[1] - di[1] * up[0]};
+    const double len = std::sqrt(right[0] * right[0] + right[1] * right[1] + right[2] * right[2]);
+    for (int k = 0; k < 3; k++) {
+        a.cam.eye[k] = (R)cam->eye[k];
+        a.cam.direction[k] = (R)di[k];
+        a.cam.up[k] = (R)up[k];
+        a.cam.right[k] = (R)(right[k] / len);
+    }
+    a.cam.d = (R)d;
+    a.cam.aperture = (R)cam->aperture;
+    a.cam.focal_distance = (R)cam->focal_distance;
+    a.width = p->width;
+    a.height = p->height;
+    a.iterations = p->iterations;
+    a.max_bounces = p->max_bounces;
+    a.exposure_scale = (R)std::pow(2.0, p->exposure_value);
+    a.seed = p->seed;
+    a.first_sample = p->first_sample;
+    a.shard_count = p->shard_count ? p->shard_count : 1;
+    a.shard_index = p->shard_index;
+    a.tiles_x = (p->width + 15) / 16;
+    a.tiles_y = (p->height + 7) / 8;
+    const uint32_t ntiles = a.tiles_x * a.tiles_y;
+    a.ntiles_mine = ntiles > a.shard_index ? (ntiles - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
+}
+
+int check_params(const rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p) {
+    if (!s || !cam || !p) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    if (p->width == 0 || p->height == 0) return fail(RPTB_ERR_BAD_ARG, "empty image %ux%u", p->width, p->height);
+    if ((uint64_t)p->width * p->height > 0x7FFFFFFFull / 4) return fail(RPTB_ERR_UNSUPPORTED, "image too large");
+    if (p->iterations == 0) return fail(RPTB_ERR_BAD_ARG, "iterations must be > 0 (the reference divides by it)");
+    if (p->max_bounces > MAX_BOUNCES_SUPPORTED) return fail(RPTB_ERR_UNSUPPORTED, "max_bounces %u > %u", p->max_bounces, MAX_BOUNCES_SUPPORTED);
+    const uint32_t sc = p->shard_count ? p->shard_count : 1;
+    if (p->shard_index >= sc) return fail(RPTB_ERR_BAD_ARG, "shard_index %u >= shard_count %u", p->shard_index, sc);
+    if (p->precision > RPTB_PRECISION_F64) return fail(RPTB_ERR_BAD_ARG, "bad precision %u", p->precision);
+    return RPTB_OK;
+}
+
+void read_stats(const DeviceCounters& c, rptb_stats* st) {
+    st->segments = c.segments;
+    st->rays = c.rays;
+    st->node_visits = c.node_visits;
+    st->tri_tests = c.tri_tests;
+    st->mesh_hits = c.mesh_hits;
+    st->env_lookups = c.env_lookups;
+}
+
+// Launch the render on `stream` into a device buffer of the precision's type.
+int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p, float* out32, double* out64,
+                  cudaStream_t stream, bool want_counters, uint32_t* launches) {
+    if (want_counters) CU(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), stream));
+    if (p->precision == RPTB_PRECISION_F32) {
+        RenderArgs<float> a;
+        fill_args(cam, p, a);
+        a.out = out32;
+        a.counters = want_counters ? s->counters : nullptr;
+        CU(launch_render_f32(s->view32, a, p->collect_stats != 0, stream, launches));
+    } else {
+        RenderArgs<double> a;
+        fill_args(cam, p, a);
+        a.out = out64;
+        a.counters = want_counters ? s->counters : nullptr;
+        CU(launch_render_f64(s->view64, a, p->collect_stats != 0, stream, launches));
+    }
+    return RPTB_OK;
+}
+
+int ensure_out(rptb_scene* s, size_t nvals) {
+    if (s->out_vals >= nvals) return RPTB_OK;
+    if (s->out32) cudaFree(s->out32);
+    if (s->out64) cudaFree(s->out64);
+    s->out32 = nullptr;
+    s->out64 = nullptr;
+    s->out_vals = 0;
+    CU(cudaMalloc(&s->out32, nvals * sizeof(float)));
+    CU(cudaMalloc(&s->out64, nvals * sizeof(double)));
+    s->out_vals = nvals;
+    return RPTB_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI ======
+extern "C" {
+
+const char* rptb_last_error(void) { return g_error.c_str(); }
+
+int rptb_device_count(void) {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(RPTB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out) {
+    if (!desc || !out) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if ((desc->nmaterials && !desc->materials) || (desc->nobjects && !desc->objects) || (desc->nlights && !desc->lights) ||
+        (desc->nmeshes && !desc->meshes))
+        return fail(RPTB_ERR_BAD_ARG, "null table with non-zero count");
+    for (uint32_t i = 0; i < desc->nobjects; i++) {
+        const int rc = validate_object(desc, desc->objects[i], "object", i);
+        if (rc != RPTB_OK) return rc;
+    }
+    for (uint32_t i = 0; i < desc->nlights; i++) {
+        if (desc->lights[i].kind > RPTB_LIGHT_OBJECT) return fail(RPTB_ERR_BAD_ARG, "light %u: bad kind", i);
+        if (desc->lights[i].kind == RPTB_LIGHT_OBJECT) {
+            const int rc = validate_object(desc, desc->lights[i].object, "light", i);
+            if (rc != RPTB_OK) return rc;
+            if (desc->lights[i].object.kind == RPTB_SHAPE_PLANE)
+                return fail(RPTB_ERR_UNSUPPORTED, "light %u: a plane cannot be sampled (Plane::sample is unimplemented!() in the reference)", i);
+        }
+    }
+    if (desc->environment.kind > RPTB_ENV_HDRI) return fail(RPTB_ERR_BAD_ARG, "bad environment kind");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RPTB_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RPTB_ERR_BAD_ARG, "device %d of %d", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(RPTB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    rptb_scene* s = new (std::nothrow) rptb_scene();
+    if (!s) return fail(RPTB_ERR_OOM, "host allocation failed");
+    s->device = device;
+    std::memset(&s->view32, 0, sizeof(s->view32));
+    std::memset(&s->view64, 0, sizeof(s->view64));
+    int rc;
+    try {
+        rc = scene_create_impl(desc, s);
+    } catch (const std::bad_alloc&) {
+        rc = fail(RPTB_ERR_OOM, "host allocation failed while flattening the scene");
+    }
+    if (rc != RPTB_OK) {
+        const std::string keep = g_error;
+        rptb_scene_destroy(s);
+        g_error = keep;
+        return rc;
+    }
+    *out = s;
+    return RPTB_OK;
+}
+
+void rptb_scene_destroy(rptb_scene* s) {
+    if (!s) return;
+    DeviceGuard g(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    s->arena.release();
+    if (s->counters) cudaFree(s->counters);
+    if (s->out32) cudaFree(s->out32);
+    if (s->out64) cudaFree(s->out64);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+uint64_t rptb_scene_device_bytes(const rptb_scene* s) { return s ? s->f32_bytes : 0; }
+
+int rptb_render_samples_device(rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p, float* out_dev,
+                               void* stream_v, rptb_stats* stats) {
+    int rc = check_params(s, cam, p);
+    if (rc != RPTB_OK) return rc;
+    if (!out_dev) return fail(RPTB_ERR_BAD_ARG, "null output");
+    std::lock_guard<std::mutex> lk(s->lock);
+    DeviceGuard g(s->device);
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : s->stream;
+    const size_t nvals = (size_t)p->width * p->height * 3;
+    uint32_t launches = 0;
+    if (stats) CU(cudaEventRecord(s->ev0, stream));
+    if (p->precision == RPTB_PRECISION_F32) {
+        rc = render_launch(s, cam, p, out_dev, nullptr, stream, stats != nullptr, &launches);
+        if (rc != RPTB_OK) return rc;
+    } else {
+        rc = ensure_out(s, nvals);
+        if (rc != RPTB_OK) return rc;
+        rc = render_launch(s, cam, p, nullptr, s->out64, stream, stats != nullptr, &launches);
+        if (rc != RPTB_OK) return rc;
+        CU(launch_convert_f64_to_f32(s->out64, out_dev, nvals, stream));
+        launches++;
+    }
+    if (stats) {
+        CU(cudaEventRecord(s->ev1, stream));
+        DeviceCounters c;
+        CU(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        std::memset(stats, 0, sizeof(*stats));
+        read_stats(c, stats);
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->gpu_ms = ms;
+        stats->launches = launches;
+    } else if (!stream_v) {
+        CU(cudaStreamSynchronize(stream));
+    }
+    return RPTB_OK;
+}
+
+int rptb_render_samples(rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p, double* out_rgb,
+                        rptb_stats* stats) {
+    int rc = check_params(s, cam, p);
+    if (rc != RPTB_OK) return rc;
+    if (!out_rgb) return fail(RPTB_ERR_BAD_ARG, "null output");
+    std::lock_guard<std::mutex> lk(s->lock);
+    DeviceGuard g(s->device);
+    const size_t nvals = (size_t)p->width * p->height * 3;
+    rc = ensure_out(s, nvals);
+    if (rc != RPTB_OK) return rc;
+    uint32_t launches = 0;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    rc = render_launch(s, cam, p, s->out32, s->out64, s->stream, true, &launches);
+    if (rc != RPTB_OK) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    DeviceCounters c;
+    CU(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    if (p->precision == RPTB_PRECISION_F32) {
+        std::vector<float> tmp(nvals);
+        CU(cudaMemcpyAsync(tmp.data(), s->out32, nvals * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        for (size_t i = 0; i < nvals; i++) out_rgb[i] = (double)tmp[i];
+    } else {
+        CU(cudaMemcpyAsync(out_rgb, s->out64, nvals * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        read_stats(c, stats);
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->gpu_ms = ms;
+        stats->launches = launches;
+    }
+    return RPTB_OK;
+}
+
+int rptb_closest_hit(rptb_scene* s, const double* rays, uint64_t n, double t_min, uint32_t precision, double* out_t,
+                     int32_t* out_object, double* out_normal, rptb_stats* stats) {
+    if (!s || (n && (!rays || !out_t || !out_object))) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    if (precision > RPTB_PRECISION_F64) return fail(RPTB_ERR_BAD_ARG, "bad precision %u", precision);
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n == 0) return RPTB_OK;
+    std::lock_guard<std::mutex> lk(s->lock);
+    DeviceGuard g(s->device);
+    double *d_rays = nullptr, *d_t = nullptr, *d_n = nullptr;
+    int32_t* d_obj = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_rays);
+        cudaFree(d_t);
+        cudaFree(d_n);
+        cudaFree(d_obj);
+    };
+#define CUC(call)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            cleanup();                                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? RPTB_ERR_OOM : RPTB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+        }                                                                                                    \
+    } while (0)
+    CUC(cudaMalloc(&d_rays, n * 6 * sizeof(double)));
+    CUC(cudaMalloc(&d_t, n * sizeof(double)));
+    CUC(cudaMalloc(&d_obj, n * sizeof(int32_t)));
+    if (out_normal) CUC(cudaMalloc(&d_n, n * 3 * sizeof(double)));
+    CUC(cudaMemcpyAsync(d_rays, rays, n * 6 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUC(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), s->stream));
+    CUC(cudaEventRecord(s->ev0, s->stream));
+    if (precision == RPTB_PRECISION_F32)
+        CUC(launch_closest_hit_f32(s->view32, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->stream));
+    else
+        CUC(launch_closest_hit_f64(s->view64, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->stream));
+    CUC(cudaEventRecord(s->ev1, s->stream));
+    CUC(cudaMemcpyAsync(out_t, d_t, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUC(cudaMemcpyAsync(out_object, d_obj, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    if (out_normal) CUC(cudaMemcpyAsync(out_normal, d_n, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    DeviceCounters c;
+    CUC(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    CUC(cudaStreamSynchronize(s->stream));
+    if (stats) {
+        read_stats(c, stats);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+        stats->gpu_ms = ms;
+        stats->launches = 1;
+    }
+    cleanup();
+    return RPTB_OK;
+}
+
+static int point_eval(const rptb_material* m, const double* dirs, uint64_t n, uint32_t in_stride, uint64_t seed,
+                      uint32_t precision, int device, double* out_a, uint32_t a_stride, double* out_b, bool sample) {
+    if (!m || (n && (!dirs || !out_a))) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    if (precision > RPTB_PRECISION_F64) return fail(RPTB_ERR_BAD_ARG, "bad precision %u", precision);
+    if (n == 0) return RPTB_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RPTB_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RPTB_ERR_BAD_ARG, "device %d of %d", device, ndev);
+    DeviceGuard g(device);
+    double *d_in = nullptr, *d_a = nullptr, *d_b = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_in);
+        cudaFree(d_a);
+        cudaFree(d_b);
+    };
+    CUC(cudaMalloc(&d_in, n * in_stride * sizeof(double)));
+    CUC(cudaMalloc(&d_a, n * a_stride * sizeof(double)));
+    if (sample) CUC(cudaMalloc(&d_b, n * sizeof(double)));
+    CUC(cudaMemcpy(d_in, dirs, n * in_stride * sizeof(double), cudaMemcpyHostToDevice));
+    if (precision == RPTB_PRECISION_F32) {
+        MaterialRec<float> r;
+        fill_material(*m, r);
+        if (sample) CUC(launch_sample_f_f32(r, d_in, n, seed, d_a, d_b, 0));
+        else CUC(launch_bsdf_f32(r, d_in, n, d_a, 0));
+    } else {
+        MaterialRec<double> r;
+        fill_material(*m, r);
+        if (sample) CUC(launch_sample_f_f64(r, d_in, n, seed, d_a, d_b, 0));
+        else CUC(launch_bsdf_f64(r, d_in, n, d_a, 0));
+    }
+    CUC(cudaMemcpy(out_a, d_a, n * a_stride * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sample) CUC(cudaMemcpy(out_b, d_b, n * sizeof(double), cudaMemcpyDeviceToHost));
+    cleanup();
+    return RPTB_OK;
+}
+
+int rptb_bsdf_eval(const rptb_material* m, const double* dirs, uint64_t n, uint32_t precision, int device, double* out) {
+    return point_eval(m, dirs, n, 9, 0, precision, device, out, 3, nullptr, false);
+}
+
+int rptb_sample_f(const rptb_material* m, const double* dirs, uint64_t n, uint64_t seed, uint32_t precision, int device,
+                  double* out_wi, double* out_pdf) {
+    if (n && !out_pdf) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    return point_eval(m, dirs, n, 6, seed, precision, device, out_wi, 3, out_pdf, true);
+}
+
+int rptb_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out) {
+    if (!out) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    if (ntris == 0 || !tris) return fail(RPTB_ERR_BAD_ARG, "no triangles");
+    if (ntris >= (1ull << 31)) return fail(RPTB_ERR_UNSUPPORTED, "mesh too large");
+    try {
+        std::vector<rptb_kdnode> nodes;
+        std::vector<uint32_t> refs;
+        uint32_t depth = 0, max_leaf = 0;
+        build_kdtree_host(tris, ntris, nodes, refs, depth, max_leaf);
+        out->nodes = (rptb_kdnode*)std::malloc(sizeof(rptb_kdnode) * nodes.size());
+        out->refs = (uint32_t*)std::malloc(sizeof(uint32_t) * std::max<size_t>(refs.size(), 1));
+        if (!out->nodes || !out->refs) {
+            std::free(out->nodes);
+            std::free(out->refs);
+            std::memset(out, 0, sizeof(*out));
+            return fail(RPTB_ERR_OOM, "host allocation failed");
+        }
+        std::memcpy(out->nodes, nodes.data(), sizeof(rptb_kdnode) * nodes.size());
+        std::memcpy(out->refs, refs.data(), sizeof(uint32_t) * refs.size());
+        out->nnodes = nodes.size();
+        out->nrefs = refs.size();
+        out->depth = depth;
+        out->max_leaf = max_leaf;
+    } catch (const std::bad_alloc&) {
+        return fail(RPTB_ERR_OOM, "host allocation failed");
+    }
+    return RPTB_OK;
+}
+
+void rptb_free_kdtree(rptb_kdtree_out* out) {
+    if (!out) return;
+    std::free(out->nodes);
+    std::free(out->refs);
+    std::memset(out, 0, sizeof(*out));
+}
+
+int rptb_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height, uint32_t box_radius,
+                      int device, uint8_t* out_rgb8) {
+    if (!sums || !out_rgb8) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    if (nbatches == 0) return fail(RPTB_ERR_BAD_ARG, "Pixel found with no samples");  // buffer.rs:89
+    if (width == 0 || height == 0) return fail(RPTB_ERR_BAD_ARG, "empty image");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RPTB_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RPTB_ERR_BAD_ARG, "device %d of %d", device, ndev);
+    DeviceGuard g(device);
+    const size_t nvals = (size_t)width * height * 3;
+    double* d_in = nullptr;
+    uint8_t* d_out = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_in);
+        cudaFree(d_out);
+    };
+    CUC(cudaMalloc(&d_in, nvals * sizeof(double)));
+    CUC(cudaMalloc(&d_out, nvals));
+    CUC(cudaMemcpy(d_in, sums, nvals * sizeof(double), cudaMemcpyHostToDevice));
+    CUC(launch_film_resolve(d_in, nbatches, width, height, box_radius, d_out, 0));
+    CUC(cudaMemcpy(out_rgb8, d_out, nvals, cudaMemcpyDeviceToHost));
+    cleanup();
+    return RPTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// film.cu -- film resolve on the device ("next" row N1 of SURVEY section 8f).
+//
+// Replaces Buffer::image -> get_filtered_color -> color_bytes
+// (ekzhang/rpt src/buffer.rs:43-56,75-93, src/color.rs:17-23): box filter of radius r
+// over the per-pixel sample sums (every pixel holds `nbatches` equally weighted
+// entries), then clamp, gamma 1/2.2 and a truncating cast to u8.  Computed in f64 and
+// summed in the reference's order (x outer, y inner), so the bytes match the CPU
+// restatement exactly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rptb {
+
+__global__ void film_resolve_kernel(const double* __restrict__ sums, uint32_t nbatches, uint32_t width,
+                                    uint32_t height, uint32_t radius, uint8_t* __restrict__ out) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    unsigned long long count = 0;
+    const uint32_t i0 = x >= radius ? x - radius : 0u;  // saturating_sub
+    const uint32_t j0 = y >= radius ? y - radius : 0u;
+    const uint64_t i1 = (uint64_t)x + radius, j1 = (uint64_t)y + radius;
+    for (uint64_t i = i0; i <= i1 && i < width; i++)
+        for (uint64_t j = j0; j <= j1 && j < height; j++) {
+            const double* p = sums + 3 * (j * width + i);
+            c0 += p[0];
+            c1 += p[1];
+            c2 += p[2];
+            count += nbatches;
+        }
+    const double n = (double)count;
+    const double c[3] = {c0 / n, c1 / n, c2 / n};
+    uint8_t* o = out + 3 * ((size_t)y * width + x);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double v = fmin(fmax(c[k], 0.0), 1.0);
+        o[k] = (uint8_t)(pow(v, 1.0 / 2.2) * 255.0);  // `as u8` truncates
+    }
+}
+
+__global__ void convert_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+cudaError_t launch_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height,
+                                uint32_t radius, uint8_t* out, cudaStream_t stream) {
+    const dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+    film_resolve_kernel<<<grid, block, 0, stream>>>(sums, nbatches, width, height, radius, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convert_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    convert_f64_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in, out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace rptb

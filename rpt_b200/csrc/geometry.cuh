@@ -1,0 +1,388 @@
+// geometry.cuh -- ray/shape intersection on the device.
+//
+// Reference functions restated (file:line in ekzhang/rpt @815b21c):
+//   Ray::apply_transform             src/shape.rs:64-72
+//   Transformed<T>::intersect        src/shape.rs:128-137
+//   Sphere::intersect                src/shape/sphere.rs:13-45
+//   Plane::intersect                 src/shape/plane.rs:17-32
+//   Cube::intersect                  src/shape/cube.rs:20-72
+//   Triangle::intersect              src/shape/mesh.rs:49-82
+//   BoundingBox::intersect           src/kdtree.rs:54-68
+//   KdTree::intersect/_subtree       src/kdtree.rs:129-136,151-223
+//   Renderer::get_closest_hit        src/renderer.rs:211-220
+//
+// Design (not a port): the reference recurses through a pointer tree carrying a
+// child AABB per call and re-slabbing it at every node (6 divisions).  Here the
+// tree is a flat 8-byte-node array in DFS order and the traversal carries only the
+// ray's parametric interval [lo, hi] inside the current cell on a small per-thread
+// stack; the three pruning rules of kdtree.rs:207-222 are kept verbatim, so the
+// set of leaves visited -- and therefore the closest hit -- is the reference's
+// (SURVEY 8a a-TRAV).  Hit normals are *deferred*: the loop tracks (t, object,
+// triangle, barycentrics / face code) and the normal of the winner is computed
+// once, which is what the reference's repeated overwrites of `record.normal`
+// amount to.
+#pragma once
+#include "scene_dev.cuh"
+
+namespace rptb {
+
+template <class R>
+struct Hit {
+    R t;           // HitRecord::time
+    int obj;       // index into scene.objects, -1 = miss
+    uint32_t aux;  // MESH: triangle index; CUBE: axis*2 + (normal positive ? 1 : 0)
+    R bv, bw;      // MESH: barycentrics v, w
+};
+
+struct TravStats {
+    uint32_t node_visits, tri_tests;
+};
+
+template <class R>
+RPTB_D Vec3<R> xform_point(const R* m, Vec3<R> p) {  // rows of a 3x4
+    return {m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+            m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]};
+}
+template <class R>
+RPTB_D Vec3<R> xform_dir(const R* m, Vec3<R> d) {
+    return {m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z,
+            m[8] * d.x + m[9] * d.y + m[10] * d.z};
+}
+template <class R>
+RPTB_D Vec3<R> xform3(const R* m, Vec3<R> d) {  // rows of a 3x3
+    return {m[0] * d.x + m[1] * d.y + m[2] * d.z, m[3] * d.x + m[4] * d.y + m[5] * d.z,
+            m[6] * d.x + m[7] * d.y + m[8] * d.z};
+}
+
+// ---------------------------------------------------------------- sphere ------
+template <class R>
+RPTB_D bool sphere_intersect(Vec3<R> o, Vec3<R> d, R tmin, R& rec_t) {
+    const R a = length2(d);
+    const R b = dot(d, o);
+    R disc;
+    if (M<R>::literal) {
+        const R c = length2(o) - (R)1;
+        disc = b * b - a * c;
+    } else {
+        // same quantity, b^2 - a(|o|^2 - 1) = a (1 - |o - (b/a) d|^2), without the f32 cancellation
+        const R k = b / a;
+        const Vec3<R> q = o - k * d;
+        disc = a * ((R)1 - length2(q));
+    }
+    if (M<R>::signbit(disc)) return false;
+    const R sd = M<R>::sqrt(disc);
+    R t;
+    const R t_minus = (-b - sd) / a;
+    if (t_minus < tmin) {
+        const R t_plus = (-b + sd) / a;
+        if (t_plus < tmin) return false;
+        t = t_plus;
+    } else {
+        t = t_minus;
+    }
+    if (t < rec_t) {
+        rec_t = t;
+        return true;
+    }
+    return false;
+}
+
+// ----------------------------------------------------------------- plane ------
+template <class R>
+RPTB_D bool plane_intersect(const R* n, R value, Vec3<R> o, Vec3<R> d, R tmin, R& rec_t) {
+    const Vec3<R> nn = {n[0], n[1], n[2]};
+    const R cosine = dot(nn, d);
+    if (M<R>::abs(cosine) < (R)1e-8) return false;
+    const R time = (value - dot(nn, o)) / cosine;
+    if (time >= tmin && time < rec_t) {
+        rec_t = time;
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ cube ------
+template <class R>
+RPTB_D bool cube_intersect(Vec3<R> o, Vec3<R> d, R tmin, R& rec_t, uint32_t& code) {
+    R lo[3], hi[3];
+    bool swapped[3];
+#pragma unroll
+    for (int dim = 0; dim < 3; dim++) {
+        const R oo = comp(o, dim), dd = comp(d, dim);
+        R x1 = ((R)-0.5 - oo) / dd;
+        R x2 = ((R)0.5 - oo) / dd;
+        swapped[dim] = x1 > x2;
+        if (swapped[dim]) {
+            const R tmp = x1;
+            x1 = x2;
+            x2 = tmp;
+        }
+        lo[dim] = x1;
+        hi[dim] = x2;
+    }
+    // entry face normal is -1 along dim unless swapped; exit face normal is +1 unless swapped
+    R start, end;
+    uint32_t sc, ec;
+    if (lo[0] > lo[1] && lo[0] > lo[2]) { start = lo[0]; sc = 0u * 2u + (swapped[0] ? 1u : 0u); }
+    else if (lo[1] > lo[2]) { start = lo[1]; sc = 1u * 2u + (swapped[1] ? 1u : 0u); }
+    else { start = lo[2]; sc = 2u * 2u + (swapped[2] ? 1u : 0u); }
+    if (hi[0] < hi[1] && hi[0] < hi[2]) { end = hi[0]; ec = 0u * 2u + (swapped[0] ? 0u : 1u); }
+    else if (hi[1] < hi[2]) { end = hi[1]; ec = 1u * 2u + (swapped[1] ? 0u : 1u); }
+    else { end = hi[2]; ec = 2u * 2u + (swapped[2] ? 0u : 1u); }
+    if (start > end || end < tmin) return false;
+    R time;
+    uint32_t c;
+    if (start < tmin) { time = end; c = ec; }
+    else { time = start; c = sc; }
+    if (time < rec_t) {
+        rec_t = time;
+        code = c;
+        return true;
+    }
+    return false;
+}
+
+// -------------------------------------------------------------- triangle ------
+// f64: the reference's formulas verbatim from the three vertices.
+RPTB_D bool tri_intersect(const MeshRec<double>& m, uint32_t tri, Vec3<double> o, Vec3<double> d, double tmin,
+                          double& rec_t, double& bv, double& bw) {
+    const double* p = m.verts + 9 * (size_t)tri;
+    const Vec3<double> v1 = {p[0], p[1], p[2]}, v2 = {p[3], p[4], p[5]}, v3 = {p[6], p[7], p[8]};
+    const Vec3<double> d0 = v2 - v1, d1 = v3 - v1;
+    const Vec3<double> pn = M<double>::normalize(cross(d0, d1));
+    const double cosine = dot(pn, d);
+    if (fabs(cosine) < 1e-8) return false;
+    const double time = dot(pn, v1 - o) / cosine;
+    if (time < tmin || time >= rec_t) return false;
+    const Vec3<double> d2 = (o + time * d) - v1;
+    const double d00 = dot(d0, d0), d01 = dot(d0, d1), d11 = dot(d1, d1);
+    const double d20 = dot(d2, d0), d21 = dot(d2, d1);
+    const double denom = d00 * d11 - d01 * d01;
+    const double v = (d11 * d20 - d01 * d21) / denom;
+    const double w = (d00 * d21 - d01 * d20) / denom;
+    const double u = 1.0 - v - w;
+    if (u >= 0.0 && v >= 0.0 && w >= 0.0) {
+        rec_t = time;
+        bv = v;
+        bw = w;
+        return true;
+    }
+    return false;
+}
+// f32: the same plane-hit + dot-product barycentrics, with everything that depends
+// only on the triangle folded into 48 bytes on the host (in double):
+//   q0 = (pn, pn.v1)   q1 = (A, -A.v1)   q2 = (B, -B.v1)
+//   A = (d11 d0 - d01 d1)/denom, B = (d00 d1 - d01 d0)/denom  =>  v = A.(P - v1), w = B.(P - v1)
+RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, Vec3<float> d, float tmin,
+                          float& rec_t, float& bv, float& bw) {
+    const float4* q = m.tri48 + 3 * (size_t)tri;
+    const float4 q0 = __ldg(q);
+    const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+    if (fabsf(cosine) < 1e-8f) return false;
+    const float time = __fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+    if (time < tmin || time >= rec_t) return false;
+    const float4 q1 = __ldg(q + 1);
+    const float4 q2 = __ldg(q + 2);
+    const float px = fmaf(time, d.x, o.x), py = fmaf(time, d.y, o.y), pz = fmaf(time, d.z, o.z);
+    const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
+    const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
+    const float u = 1.0f - v - w;
+    if (u >= 0.0f && v >= 0.0f && w >= 0.0f) {
+        rec_t = time;
+        bv = v;
+        bw = w;
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------ kd traversal -----
+template <class R>
+RPTB_D void node_fields(const KdNodeDev& n, R& split, uint32_t& word, uint32_t& first_ref) {
+    split = n.split;
+    word = n.word;
+    first_ref = n.first_ref;
+}
+RPTB_D KdNodeDev load_node(const KdNodeDev* p) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    KdNodeDev n;
+    n.first_ref = v.x;
+    n.word = v.y;
+    return n;
+}
+RPTB_D KdNodeDev64 load_node(const KdNodeDev64* p) { return *p; }
+RPTB_D float node_split(const KdNodeDev& n) { return n.split; }
+RPTB_D double node_split(const KdNodeDev64& n) { return n.split; }
+RPTB_D uint32_t node_first_ref(const KdNodeDev& n) { return n.first_ref; }
+RPTB_D uint32_t node_first_ref(const KdNodeDev64& n) { return n.first_ref; }
+
+// KdTree::intersect.  `o`,`d` are in the mesh's local space (d not normalised, so
+// t is the world t).  Returns true if some triangle tightened h.t.
+template <class R, bool ANY, bool STATS>
+RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, Hit<R>& h, TravStats& ts) {
+    // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
+    R lo, hi;
+    Vec3<R> inv;
+    {
+        if (M<R>::literal) {
+            inv = {(R)0, (R)0, (R)0};
+            const R x1 = (m.bmin[0] - o.x) / d.x, x2 = (m.bmax[0] - o.x) / d.x;
+            const R y1 = (m.bmin[1] - o.y) / d.y, y2 = (m.bmax[1] - o.y) / d.y;
+            const R z1 = (m.bmin[2] - o.z) / d.z, z2 = (m.bmax[2] - o.z) / d.z;
+            lo = M<R>::max(M<R>::max(M<R>::min(x1, x2), M<R>::min(y1, y2)), M<R>::min(z1, z2));
+            hi = M<R>::min(M<R>::min(M<R>::max(x1, x2), M<R>::max(y1, y2)), M<R>::max(z1, z2));
+        } else {
+            inv = {M<R>::rcp(d.x), M<R>::rcp(d.y), M<R>::rcp(d.z)};
+            const R x1 = (m.bmin[0] - o.x) * inv.x, x2 = (m.bmax[0] - o.x) * inv.x;
+            const R y1 = (m.bmin[1] - o.y) * inv.y, y2 = (m.bmax[1] - o.y) * inv.y;
+            const R z1 = (m.bmin[2] - o.z) * inv.z, z2 = (m.bmax[2] - o.z) * inv.z;
+            lo = M<R>::max(M<R>::max(M<R>::min(x1, x2), M<R>::min(y1, y2)), M<R>::min(z1, z2));
+            hi = M<R>::min(M<R>::min(M<R>::max(x1, x2), M<R>::max(y1, y2)), M<R>::max(z1, z2));
+        }
+        if (M<R>::max(lo, tmin) > M<R>::min(hi, h.t)) return false;
+    }
+
+    uint32_t st_node[KD_STACK];
+    R st_lo[KD_STACK], st_hi[KD_STACK];
+    int sp = 0;
+    uint32_t node = 0;
+    bool any = false;
+
+    while (true) {
+        auto nd = load_node(m.nodes + node);
+        while ((nd.word & 3u) != 3u) {
+            if (STATS) ts.node_visits++;
+            const uint32_t axis = nd.word & 3u;
+            const uint32_t right = nd.word >> 2;
+            const R split = node_split(nd);
+            const R oa = comp(o, (int)axis), da = comp(d, (int)axis);
+            R t_split;
+            if (M<R>::literal) t_split = (split - oa) / da;
+            else t_split = (split - oa) * comp(inv, (int)axis);
+            const bool left_first = (oa < split) || (oa == split && da <= (R)0);
+            const uint32_t first = left_first ? node + 1u : right;
+            const uint32_t second = left_first ? right : node + 1u;
+            if (t_split > M<R>::min(hi, h.t) || t_split <= (R)0) {
+                node = first;  // (i) near only
+            } else if (t_split < M<R>::max(lo, tmin)) {
+                node = second;  // (ii) far only
+            } else {  // (iii) near, then far with the cell clipped at t_split
+                st_node[sp] = second;
+                st_lo[sp] = t_split;
+                st_hi[sp] = hi;
+                sp++;
+                node = first;
+                hi = t_split;
+            }
+            nd = load_node(m.nodes + node);
+        }
+        // leaf: every referenced triangle, no early out (kdtree.rs:162-171)
+        if (STATS) ts.node_visits++;
+        {
+            const uint32_t first_ref = node_first_ref(nd);
+            const uint32_t count = nd.word >> 2;
+            for (uint32_t i = 0; i < count; i++) {
+                const uint32_t tri = __ldg(m.refs + first_ref + i);
+                if (STATS) ts.tri_tests++;
+                if (tri_intersect(m, tri, o, d, tmin, h.t, h.bv, h.bw)) {
+                    h.aux = tri;
+                    any = true;
+                }
+            }
+        }
+        if (ANY && any) return true;
+        // pop; skip far cells that start beyond the hit found so far (kdtree.rs:212-213)
+        while (true) {
+            if (sp == 0) return any;
+            sp--;
+            node = st_node[sp];
+            lo = st_lo[sp];
+            hi = st_hi[sp];
+            if (!(h.t < lo)) break;
+        }
+    }
+}
+
+// ------------------------------------------------------- object dispatch ------
+template <class R, bool ANY, bool STATS>
+RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> o, Vec3<R> d, R tmin, Hit<R>& h,
+                             TravStats& ts) {
+    if (ob.has_transform) {  // Ray::apply_transform(inverse_transform)
+        const Vec3<R> lo = xform_point(ob.inv, o);
+        const Vec3<R> ld = xform_dir(ob.inv, d);
+        o = lo;
+        d = ld;
+    }
+    switch (ob.kind) {
+        case SHAPE_SPHERE: return sphere_intersect(o, d, tmin, h.t);
+        case SHAPE_PLANE: return plane_intersect(ob.plane_n, ob.plane_v, o, d, tmin, h.t);
+        case SHAPE_CUBE: return cube_intersect(o, d, tmin, h.t, h.aux);
+        default: return kd_intersect<R, ANY, STATS>(sv.meshes[ob.mesh], o, d, tmin, h, ts);
+    }
+}
+
+// Surface data of the winning hit, computed once.
+template <class R>
+struct Surface {
+    Vec3<R> n;   // shading normal == HitRecord::normal
+    Vec3<R> ng;  // geometric normal (f32 ray-offset policy only)
+    bool on_mesh;
+};
+
+template <class R>
+RPTB_D Surface<R> finalize_hit(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> o, Vec3<R> d, const Hit<R>& h) {
+    Surface<R> s;
+    if (ob.has_transform) {
+        const Vec3<R> lo = xform_point(ob.inv, o);
+        const Vec3<R> ld = xform_dir(ob.inv, d);
+        o = lo;
+        d = ld;
+    }
+    Vec3<R> n, ng;
+    s.on_mesh = false;
+    switch (ob.kind) {
+        case SHAPE_SPHERE:
+            n = M<R>::normalize(o + h.t * d);  // sphere.rs:40
+            ng = n;
+            break;
+        case SHAPE_PLANE: {
+            const Vec3<R> pn = {ob.plane_n[0], ob.plane_n[1], ob.plane_n[2]};
+            const R cosine = dot(pn, d);
+            if (M<R>::literal) n = -M<R>::normalize(pn) * signum(cosine);  // plane.rs:27
+            else n = -mk(ob.plane_unit[0], ob.plane_unit[1], ob.plane_unit[2]) * signum(cosine);
+            ng = n;
+            break;
+        }
+        case SHAPE_CUBE: {
+            const uint32_t axis = h.aux >> 1;
+            const R sgn = (h.aux & 1u) ? (R)1 : (R)-1;
+            n = mk(axis == 0 ? sgn : (R)0, axis == 1 ? sgn : (R)0, axis == 2 ? sgn : (R)0);
+            ng = n;
+            break;
+        }
+        default: {
+            const MeshRec<R>& m = sv.meshes[ob.mesh];
+            const R* p = m.norms + 9 * (size_t)h.aux;
+            const R u = (R)1 - h.bv - h.bw;
+            const Vec3<R> n1 = {p[0], p[1], p[2]}, n2 = {p[3], p[4], p[5]}, n3 = {p[6], p[7], p[8]};
+            n = M<R>::normalize(u * n1 + h.bv * n2 + h.bw * n3);  // mesh.rs:77
+            if (!M<R>::literal) {
+                const float4 q0 = __ldg(m.tri48 + 3 * (size_t)h.aux);
+                ng = mk((R)q0.x, (R)q0.y, (R)q0.z);
+            } else {
+                ng = n;
+            }
+            s.on_mesh = true;
+        }
+    }
+    if (ob.has_transform) {  // shape.rs:132
+        n = M<R>::normalize(xform3(ob.nrm, n));
+        if (!M<R>::literal) ng = M<R>::normalize(xform3(ob.nrm, ng));
+        else ng = n;
+    }
+    s.n = n;
+    s.ng = ng;
+    return s;
+}
+
+}  // namespace rptb

@@ -1,0 +1,326 @@
+// integrator.cuh -- the path-tracing megakernel and the diagnostic kernels.
+//
+// Reference loop being replaced (ekzhang/rpt @815b21c):
+//   Renderer::sample        src/renderer.rs:117-129   rayon over rows, one StdRng per row
+//   Renderer::get_color     src/renderer.rs:131-142   for _ in 0..iterations { jitter; cast_ray; trace_ray }
+//   Camera::cast_ray        src/camera.rs:64-81
+//   Renderer::trace_ray     src/renderer.rs:145-174   recursive, per-level firefly clamp
+//   Renderer::sample_lights src/renderer.rs:177-204
+//   Renderer::get_closest_hit src/renderer.rs:211-220
+//
+// B200 design: one thread owns one pixel for all `iterations` samples and sums them
+// in sample order, so the image is bit-reproducible and independent of how pixel
+// tiles are sharded over GPUs (no atomics on the film).  A warp covers an 8x4 pixel
+// block, a CTA a 16x8 tile; tiles are dealt round-robin to shards.  The recursion
+// of trace_ray is flattened into ONE loop whose body is one path segment: a lane
+// whose path ended regenerates its next camera ray at the top of the same loop
+// instead of idling until the longest path of the warp finishes (persistent-lane
+// path regeneration).  The per-level clamp `min(indirect, 100)` makes the estimator
+// non-linear, so each level's (local radiance, throughput) is kept on a small
+// per-thread stack and unwound when the path ends -- exactly the reference's value.
+#pragma once
+#include "shading.cuh"
+
+namespace rptb {
+
+constexpr int RENDER_THREADS = 128;  // 4 warps: a 16x8 pixel tile
+constexpr int TILE_W = 16, TILE_H = 8;
+
+template <class R>
+struct Level;
+template <>
+struct Level<float> {  // throughput pre-multiplied: w = f * (|cos| / pdf)
+    float local[3], w[3];
+};
+template <>
+struct Level<double> {  // literal: indirect = 1/pdf * (f (.) L) * |cos|
+    double local[3], f[3], inv_pdf, abscos;
+};
+
+RPTB_D Vec3<float> unwind(const Level<float>& l, Vec3<float> L) {
+    return {l.local[0] + fminf(l.w[0] * L.x, 100.0f), l.local[1] + fminf(l.w[1] * L.y, 100.0f),
+            l.local[2] + fminf(l.w[2] * L.z, 100.0f)};
+}
+RPTB_D Vec3<double> unwind(const Level<double>& l, Vec3<double> L) {
+    const double ix = l.inv_pdf * (l.f[0] * L.x) * l.abscos;
+    const double iy = l.inv_pdf * (l.f[1] * L.y) * l.abscos;
+    const double iz = l.inv_pdf * (l.f[2] * L.z) * l.abscos;
+    return {l.local[0] + fmin(ix, 100.0), l.local[1] + fmin(iy, 100.0), l.local[2] + fmin(iz, 100.0)};
+}
+
+struct PathCounters {
+    uint32_t segments, rays, mesh_hits, env_lookups;
+    TravStats ts;
+};
+
+// get_closest_hit: linear scan of scene.objects.  ANY = shadow query (first hit with
+// t < h.t ends the scan; the caller preloads h.t with the light distance).
+template <class R, bool ANY, bool STATS>
+RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, Hit<R>& h, TravStats& ts) {
+    h.obj = -1;
+    h.aux = 0;
+    h.bv = h.bw = (R)0;
+    const uint32_t n = sv.nobjects;
+    for (uint32_t i = 0; i < n; i++) {
+        if (object_intersect<R, ANY, STATS>(sv, sv.objects[i], o, d, tmin, h, ts)) {
+            h.obj = (int)i;
+            if (ANY) return;
+        }
+    }
+}
+
+// f32 only: start the next ray a few ulps off the surface, on the side it leaves from.
+// The reference restarts exactly at the hit point with t_min = 1e-12, which only works
+// in f64 ("f64 -> f32").
+RPTB_D Vec3<float> offset_origin(Vec3<float> p, Vec3<float> ng, Vec3<float> dir, float scale) {
+    const float delta = 1.9073486e-6f * scale;  // 32 * 2^-24 * max |coordinate| involved
+    const float s = dot(dir, ng) >= 0.0f ? delta : -delta;
+    return {fmaf(s, ng.x, p.x), fmaf(s, ng.y, p.y), fmaf(s, ng.z, p.z)};
+}
+RPTB_D Vec3<double> offset_origin(Vec3<double> p, Vec3<double>, Vec3<double>, double) { return p; }
+
+template <class R>
+RPTB_D R max_abs3(Vec3<R> a) { return M<R>::max(M<R>::max(M<R>::abs(a.x), M<R>::abs(a.y)), M<R>::abs(a.z)); }
+
+template <class R, int MAXD, bool STATS>
+__global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
+    const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
+    const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t x = tx * TILE_W + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t y = ty * TILE_H + (warp >> 1) * 4u + (lane >> 3);
+    if (x >= a.width || y >= a.height) return;
+    const uint32_t pix = y * a.width + x;
+
+    const R tmin = (R)1e-12;  // EPSILON, renderer.rs:14
+    const R dim = (R)max(a.width, a.height);
+    const R xn = ((R)(2u * x + 1u) - (R)a.width) / dim;
+    const R yn = ((R)(2u * (a.height - y) - 1u) - (R)a.height) / dim;
+    const Vec3<R> eye = {a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]};
+    const Vec3<R> cdir = {a.cam.direction[0], a.cam.direction[1], a.cam.direction[2]};
+    const Vec3<R> cup = {a.cam.up[0], a.cam.up[1], a.cam.up[2]};
+    const Vec3<R> cright = {a.cam.right[0], a.cam.right[1], a.cam.right[2]};
+
+    PathCounters pc = {0, 0, 0, 0, {0, 0}};
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    Level<R> stack[MAXD];
+    Rng<R> rng;
+    Vec3<R> ro = eye, rd = cdir;
+    uint32_t s = 0;
+    int depth = 0;
+    bool fresh = true;
+
+    while (true) {
+        if (fresh) {
+            if (s >= a.iterations) break;
+            rng.p.init(a.seed, pix, a.first_sample + s);
+            const R dx = gen_range(rng, (R)-1 / dim, (R)1 / dim);
+            const R dy = gen_range(rng, (R)-1 / dim, (R)1 / dim);
+            // Camera::cast_ray
+            const R cx = xn + dx, cy = yn + dy;
+            Vec3<R> origin = eye;
+            Vec3<R> new_dir = a.cam.d * cdir + cx * cright + cy * cup;
+            if (a.cam.aperture > (R)0) {
+                const Vec3<R> focal_point = origin + M<R>::normalize(new_dir) * a.cam.focal_distance;
+                R ax, ay;
+                unit_disc(rng, ax, ay);
+                origin = origin + (ax * cright + ay * cup) * a.cam.aperture;
+                new_dir = focal_point - origin;
+            }
+            ro = origin;
+            rd = M<R>::normalize(new_dir);
+            depth = 0;
+            fresh = false;
+        }
+
+        // ---- one trace_ray invocation ------------------------------------------
+        pc.segments++;
+        pc.rays++;
+        Hit<R> h;
+        h.t = M<R>::inf();
+        closest_hit<R, false, STATS>(sv, ro, rd, tmin, h, pc.ts);
+
+        Vec3<R> L;
+        bool done;
+        if (h.obj < 0) {
+            if (sv.env.kind != 0) pc.env_lookups++;
+            L = env_color(sv.env, rd);
+            done = true;
+        } else {
+            const ObjectRec<R>& ob = sv.objects[h.obj];
+            const Surface<R> sf = finalize_hit(sv, ob, ro, rd, h);
+            if (sf.on_mesh) pc.mesh_hits++;
+            const Vec3<R> pos = ro + h.t * rd;
+            const MaterialRec<R> mat = sv.materials[ob.material];
+            const Vec3<R> wo = -M<R>::normalize(rd);
+            const Vec3<R> n = sf.n;
+            const R err_scale = M<R>::literal ? (R)0 : M<R>::max(max_abs3(pos), max_abs3(ro));
+            Vec3<R> color = mat.emittance * mat_color(mat);
+            // opaque surface seen from its back: bsdf == 0 for every wi (material.rs:130-133),
+            // so neither the lights nor the bounce can contribute.
+            const bool dead = !M<R>::literal && !mat.transparent && M<R>::signbit(dot(n, wo));
+
+            // sample_lights
+            for (uint32_t li = 0; li < sv.nlights; li++) {
+                const LightRec<R>& l = sv.lights[li];
+                if (l.kind == LIGHT_AMBIENT) {
+                    color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
+                    continue;
+                }
+                if (dead) continue;
+                Vec3<R> intensity, wi;
+                R dist;
+                illuminate(sv, l, pos, rng, intensity, wi, dist);
+                if (!M<R>::literal) {
+                    // provably zero contribution: skip the shadow ray (the draws above are still consumed)
+                    const bool zero_i = intensity.x == (R)0 && intensity.y == (R)0 && intensity.z == (R)0;
+                    if (zero_i || (!mat.transparent && M<R>::signbit(dot(n, wi)))) continue;
+                }
+                pc.rays++;
+                Hit<R> sh;
+                sh.t = M<R>::next_up(dist);  // occluded iff some hit has t <= dist (renderer.rs:197)
+                closest_hit<R, true, STATS>(sv, offset_origin(pos, sf.ng, wi, err_scale), wi, tmin, sh, pc.ts);
+                if (sh.obj < 0) {
+                    const Vec3<R> f = bsdf(mat, n, wo, wi);
+                    color = color + cmul(f, intensity) * dot(wi, n);
+                }
+            }
+
+            done = true;
+            L = color;
+            if ((uint32_t)depth < a.max_bounces && !dead) {
+                Vec3<R> wi;
+                R pdf;
+                if (sample_f(mat, n, wo, rng, wi, pdf)) {
+                    const Vec3<R> f = bsdf(mat, n, wo, wi);
+                    const R abscos = M<R>::abs(dot(wi, n));
+                    Level<R>& lv = stack[depth];
+                    lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
+                    if constexpr (M<R>::literal) {
+                        lv.f[0] = f.x; lv.f[1] = f.y; lv.f[2] = f.z;
+                        lv.inv_pdf = (R)1 / pdf;
+                        lv.abscos = abscos;
+                    } else {
+                        const R k = abscos / pdf;
+                        lv.w[0] = f.x * k; lv.w[1] = f.y * k; lv.w[2] = f.z * k;
+                    }
+                    ro = offset_origin(pos, sf.ng, wi, err_scale);
+                    rd = wi;
+                    depth++;
+                    done = false;
+                }
+            }
+        }
+
+        if (done) {
+            for (int k = depth - 1; k >= 0; k--) L = unwind(stack[k], L);
+            acc0 += (double)L.x;
+            acc1 += (double)L.y;
+            acc2 += (double)L.z;
+            s++;
+            fresh = true;
+        }
+    }
+
+    // color / iterations * 2^EV  (renderer.rs:141)
+    const double it = (double)a.iterations;
+    R* out = a.out + 3 * (size_t)pix;
+    out[0] = (R)(acc0 / it * (double)a.exposure_scale);
+    out[1] = (R)(acc1 / it * (double)a.exposure_scale);
+    out[2] = (R)(acc2 / it * (double)a.exposure_scale);
+
+    if (a.counters) {
+        const unsigned m = __activemask();
+        const int leader = __ffs(m) - 1;
+        const uint32_t v0 = __reduce_add_sync(m, pc.segments), v1 = __reduce_add_sync(m, pc.rays);
+        const uint32_t v2 = __reduce_add_sync(m, pc.mesh_hits), v3 = __reduce_add_sync(m, pc.env_lookups);
+        // node/tri counters can exceed 2^32 per warp on long renders: reduce in two halves
+        const uint32_t n_lo = __reduce_add_sync(m, pc.ts.node_visits & 0xFFFFu), n_hi = __reduce_add_sync(m, pc.ts.node_visits >> 16);
+        const uint32_t t_lo = __reduce_add_sync(m, pc.ts.tri_tests & 0xFFFFu), t_hi = __reduce_add_sync(m, pc.ts.tri_tests >> 16);
+        if ((int)lane == leader) {
+            atomicAdd(&a.counters->segments, (unsigned long long)v0);
+            atomicAdd(&a.counters->rays, (unsigned long long)v1);
+            atomicAdd(&a.counters->mesh_hits, (unsigned long long)v2);
+            atomicAdd(&a.counters->env_lookups, (unsigned long long)v3);
+            if (STATS) {
+                atomicAdd(&a.counters->node_visits, (unsigned long long)n_lo + ((unsigned long long)n_hi << 16));
+                atomicAdd(&a.counters->tri_tests, (unsigned long long)t_lo + ((unsigned long long)t_hi << 16));
+            }
+        }
+    }
+}
+
+// Zero the pixels of tiles that belong to other shards (so an all-reduce(sum) of the
+// shard buffers is the full image, bit-identical for any shard count).
+template <class R>
+__global__ void clear_kernel(R* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (R)0;
+}
+
+// ---- K2: Renderer::get_closest_hit for a batch of world rays -----------------------
+template <class R, bool STATS>
+__global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restrict__ rays, uint64_t n, double tmin_d,
+                                   double* __restrict__ out_t, int32_t* __restrict__ out_obj,
+                                   double* __restrict__ out_n, DeviceCounters* counters) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStats ts = {0, 0};
+    if (i < n) {
+        const double* r = rays + 6 * i;
+        const Vec3<R> o = {(R)r[0], (R)r[1], (R)r[2]};
+        const Vec3<R> d = {(R)r[3], (R)r[4], (R)r[5]};
+        Hit<R> h;
+        h.t = M<R>::inf();
+        closest_hit<R, false, STATS>(sv, o, d, (R)tmin_d, h, ts);
+        out_obj[i] = h.obj;
+        out_t[i] = h.obj >= 0 ? (double)h.t : (double)INFINITY;
+        if (out_n) {
+            Vec3<R> nn = {(R)0, (R)0, (R)0};
+            if (h.obj >= 0) nn = finalize_hit(sv, sv.objects[h.obj], o, d, h).n;
+            out_n[3 * i] = (double)nn.x;
+            out_n[3 * i + 1] = (double)nn.y;
+            out_n[3 * i + 2] = (double)nn.z;
+        }
+    }
+    if (counters) {
+        if (i < n) atomicAdd(&counters->rays, 1ull);
+        if (STATS && i < n) {
+            atomicAdd(&counters->node_visits, (unsigned long long)ts.node_visits);
+            atomicAdd(&counters->tri_tests, (unsigned long long)ts.tri_tests);
+        }
+    }
+}
+
+// ---- point-wise Material::bsdf / sample_f ------------------------------------------------
+template <class R>
+__global__ void bsdf_kernel(const MaterialRec<R> m, const double* __restrict__ dirs, uint64_t n, double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* d = dirs + 9 * i;
+    const Vec3<R> f = bsdf(m, mk((R)d[0], (R)d[1], (R)d[2]), mk((R)d[3], (R)d[4], (R)d[5]), mk((R)d[6], (R)d[7], (R)d[8]));
+    out[3 * i] = (double)f.x;
+    out[3 * i + 1] = (double)f.y;
+    out[3 * i + 2] = (double)f.z;
+}
+
+template <class R>
+__global__ void sample_f_kernel(const MaterialRec<R> m, const double* __restrict__ dirs, uint64_t n, uint64_t seed,
+                                double* __restrict__ out_wi, double* __restrict__ out_pdf) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* d = dirs + 6 * i;
+    Rng<R> rng;
+    rng.p.init(seed, (uint32_t)i, 0);
+    Vec3<R> wi = {(R)0, (R)0, (R)0};
+    R pdf = (R)-1;
+    if (!sample_f(m, mk((R)d[0], (R)d[1], (R)d[2]), mk((R)d[3], (R)d[4], (R)d[5]), rng, wi, pdf)) {
+        wi = mk((R)0, (R)0, (R)0);
+        pdf = (R)-1;
+    }
+    out_wi[3 * i] = (double)wi.x;
+    out_wi[3 * i + 1] = (double)wi.y;
+    out_wi[3 * i + 2] = (double)wi.z;
+    out_pdf[i] = (double)pdf;
+}
+
+}  // namespace rptb

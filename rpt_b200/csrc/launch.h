@@ -1,0 +1,25 @@
+// launch.h -- host-callable launchers, one set per precision (each set lives in its
+// own translation unit so the f64 parity gate can be compiled with -fmad=false).
+#pragma once
+#include "scene_dev.cuh"
+
+namespace rptb {
+
+#define RPTB_DECLARE_LAUNCHERS(SUFFIX, R)                                                                          \
+    cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats,              \
+                                       cudaStream_t stream, uint32_t* launches);                                   \
+    cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,   \
+                                            double* out_t, int32_t* out_obj, double* out_n,                        \
+                                            DeviceCounters* counters, bool stats, cudaStream_t stream);            \
+    cudaError_t launch_bsdf_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, double* out,         \
+                                     cudaStream_t stream);                                                         \
+    cudaError_t launch_sample_f_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, uint64_t seed,   \
+                                         double* out_wi, double* out_pdf, cudaStream_t stream);
+
+RPTB_DECLARE_LAUNCHERS(f32, float)
+RPTB_DECLARE_LAUNCHERS(f64, double)
+
+// max_bounces the render kernels are instantiated for
+constexpr uint32_t MAX_BOUNCES_SUPPORTED = 64;
+
+}  // namespace rptb

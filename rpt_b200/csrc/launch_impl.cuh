@@ -1,0 +1,77 @@
+// launch_impl.cuh -- templated bodies of the launchers declared in launch.h.
+#pragma once
+#include "integrator.cuh"
+#include "launch.h"
+
+namespace rptb {
+
+template <class R>
+cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats, cudaStream_t stream,
+                               uint32_t* launches) {
+    uint32_t nl = 0;
+    const size_t nvals = (size_t)args.width * args.height * 3;
+    if (args.shard_count > 1) {  // other shards' pixels must read as zero
+        clear_kernel<R><<<(unsigned)((nvals + 255) / 256), 256, 0, stream>>>(args.out, nvals);
+        nl++;
+    }
+    if (args.ntiles_mine > 0) {
+        const dim3 grid(args.ntiles_mine), block(RENDER_THREADS);
+        if (args.max_bounces <= 16) {
+            if (stats) render_kernel<R, 16, true><<<grid, block, 0, stream>>>(sv, args);
+            else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
+        } else {
+            if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true><<<grid, block, 0, stream>>>(sv, args);
+            else render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false><<<grid, block, 0, stream>>>(sv, args);
+        }
+        nl++;
+    }
+    if (launches) *launches = nl;
+    return cudaGetLastError();
+}
+
+template <class R>
+cudaError_t launch_closest_hit_impl(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin, double* out_t,
+                                    int32_t* out_obj, double* out_n, DeviceCounters* counters, bool stats,
+                                    cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (stats) closest_hit_kernel<R, true><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    else closest_hit_kernel<R, false><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    return cudaGetLastError();
+}
+
+template <class R>
+cudaError_t launch_bsdf_impl(const MaterialRec<R>& m, const double* dirs, uint64_t n, double* out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    bsdf_kernel<R><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(m, dirs, n, out);
+    return cudaGetLastError();
+}
+
+template <class R>
+cudaError_t launch_sample_f_impl(const MaterialRec<R>& m, const double* dirs, uint64_t n, uint64_t seed, double* out_wi,
+                                 double* out_pdf, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    sample_f_kernel<R><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(m, dirs, n, seed, out_wi, out_pdf);
+    return cudaGetLastError();
+}
+
+#define RPTB_DEFINE_LAUNCHERS(SUFFIX, R)                                                                            \
+    cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats,               \
+                                       cudaStream_t stream, uint32_t* launches) {                                   \
+        return launch_render_impl<R>(sv, args, stats, stream, launches);                                            \
+    }                                                                                                               \
+    cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,    \
+                                            double* out_t, int32_t* out_obj, double* out_n,                         \
+                                            DeviceCounters* counters, bool stats, cudaStream_t stream) {            \
+        return launch_closest_hit_impl<R>(sv, rays, n, tmin, out_t, out_obj, out_n, counters, stats, stream);       \
+    }                                                                                                               \
+    cudaError_t launch_bsdf_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, double* out,          \
+                                     cudaStream_t stream) {                                                         \
+        return launch_bsdf_impl<R>(m, dirs, n, out, stream);                                                        \
+    }                                                                                                               \
+    cudaError_t launch_sample_f_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, uint64_t seed,    \
+                                         double* out_wi, double* out_pdf, cudaStream_t stream) {                    \
+        return launch_sample_f_impl<R>(m, dirs, n, seed, out_wi, out_pdf, stream);                                  \
+    }
+
+}  // namespace rptb

@@ -1,0 +1,159 @@
+// rng.cuh -- per-path Philox4x32-10 stream and the rand 0.8 / rand_distr 0.4
+// distributions the reference draws from:
+//   gen::<f64>()      src/material.rs:247, src/shape/mesh.rs:85-90, src/shape/cube.rs:75-76
+//   gen_range(a..b)   src/renderer.rs:137-138
+//   gen_bool(p)       src/material.rs:264
+//   Uniform(0..n)     src/kdtree.rs:140, src/shape/cube.rs:77
+//   UnitDisc          src/camera.rs:73, src/shape/sphere.rs:53, src/material.rs:271
+//   UnitCircle        src/material.rs:251
+// The reference seeds ChaCha12 from OS entropy per row (src/renderer.rs:121); here
+// key = (seed_lo, seed_hi), counter = (block, pixel, sample_lo, sample_hi).
+// Each block yields two 64-bit draws: (x0 | x1<<32), then (x2 | x3<<32).
+#pragma once
+#include "vec.cuh"
+
+namespace rptb {
+
+struct Philox {
+    uint32_t key0, key1;
+    uint32_t block, pixel, samp_lo, samp_hi;
+    uint32_t spare_lo, spare_hi;
+    bool have_spare;
+
+    RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) {
+        key0 = (uint32_t)seed;
+        key1 = (uint32_t)(seed >> 32);
+        block = 0;
+        pixel = pix;
+        samp_lo = (uint32_t)sample;
+        samp_hi = (uint32_t)(sample >> 32);
+        have_spare = false;
+        spare_lo = spare_hi = 0;
+    }
+
+    static RPTB_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+        lo = a * b;
+        hi = __umulhi(a, b);
+#else
+        const uint64_t p = (uint64_t)a * b;
+        lo = (uint32_t)p;
+        hi = (uint32_t)(p >> 32);
+#endif
+    }
+
+    static RPTB_HD void block10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                uint32_t out[4]) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(0xD2511F53u, c0, hi0, lo0);
+            mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+            const uint32_t n0 = hi1 ^ c1 ^ k0;
+            const uint32_t n2 = hi0 ^ c3 ^ k1;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+
+    RPTB_HD uint64_t next_u64() {
+        if (have_spare) {
+            have_spare = false;
+            return (uint64_t)spare_lo | ((uint64_t)spare_hi << 32);
+        }
+        uint32_t o[4];
+        block10(block, pixel, samp_lo, samp_hi, key0, key1, o);
+        block++;
+        spare_lo = o[2];
+        spare_hi = o[3];
+        have_spare = true;
+        return (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+    }
+};
+
+template <class R>
+struct Rng;
+
+// f64: bit-for-bit the oracle's conversions.
+template <>
+struct Rng<double> {
+    Philox p;
+    RPTB_HD double gen() { return (double)(p.next_u64() >> 11) * (1.0 / 9007199254740992.0); }
+    RPTB_HD double u52() { return (double)(p.next_u64() >> 12) * (1.0 / 4503599627370496.0); }
+};
+// f32: the top 24 bits of the same draw -- the f64 value truncated to a float in [0,1).
+template <>
+struct Rng<float> {
+    Philox p;
+    RPTB_HD float gen() { return (float)(uint32_t)(p.next_u64() >> 40) * (1.0f / 16777216.0f); }
+    RPTB_HD float u52() { return gen(); }
+};
+
+// Rng::gen_range(lo..hi) -> UniformFloat::sample_single
+template <class R>
+RPTB_HD R gen_range(Rng<R>& r, R lo, R hi) {
+    const R scale = hi - lo;
+    while (true) {
+        const R v12 = (R)1 + r.u52();
+        const R res = v12 * scale + (lo - scale);
+        if (res < hi) return res;
+    }
+}
+// Uniform::new(-1, 1).sample
+template <class R>
+RPTB_HD R uniform_pm1(Rng<R>& r) { return r.u52() * (R)2 + (R)(-1); }
+
+// Rng::gen_bool(p).  p >= 1 returns true (the reference's ALWAYS_TRUE case) but still
+// consumes one draw so that the number of draws per vertex is material-independent.
+template <class R>
+RPTB_HD bool gen_bool(Rng<R>& r, R prob) {
+    const uint64_t v = r.p.next_u64();
+    if (prob >= (R)1) return true;
+    const uint64_t p_int = (uint64_t)((double)prob * 18446744073709551616.0);
+    return v < p_int;
+}
+
+// Uniform::from(0..n) for usize: widening multiply with rejection zone
+template <class R>
+RPTB_HD uint64_t uniform_usize(Rng<R>& r, uint64_t n) {
+    const uint64_t ints_to_reject = (0xFFFFFFFFFFFFFFFFull - n + 1) % n;
+    const uint64_t zone = 0xFFFFFFFFFFFFFFFFull - ints_to_reject;
+    while (true) {
+        const uint64_t v = r.p.next_u64();
+        const uint64_t lo = v * n;
+#ifdef __CUDA_ARCH__
+        const uint64_t hi = __umul64hi(v, n);
+#else
+        const uint64_t hi = (uint64_t)(((unsigned __int128)v * n) >> 64);
+#endif
+        if (lo <= zone) return hi;
+    }
+}
+
+// rand_distr::UnitDisc: rejection from the square, boundary inclusive
+template <class R>
+RPTB_HD void unit_disc(Rng<R>& r, R& x, R& y) {
+    while (true) {
+        x = uniform_pm1(r);
+        y = uniform_pm1(r);
+        if (x * x + y * y <= (R)1) return;
+    }
+}
+// rand_distr::UnitCircle: von Neumann's method
+template <class R>
+RPTB_HD void unit_circle(Rng<R>& r, R& x, R& y) {
+    R x1, x2, sum;
+    while (true) {
+        x1 = uniform_pm1(r);
+        x2 = uniform_pm1(r);
+        sum = x1 * x1 + x2 * x2;
+        if (sum < (R)1) break;
+    }
+    const R diff = x1 * x1 - x2 * x2;
+    x = diff / sum;
+    y = (R)2 * x1 * x2 / sum;
+}
+
+}  // namespace rptb

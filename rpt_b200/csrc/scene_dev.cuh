@@ -1,0 +1,139 @@
+// scene_dev.cuh -- the flattened scene as the kernels see it (HBM layout).
+//
+// Reference structures being flattened:
+//   Scene{objects, lights, environment}   src/scene.rs:7-18
+//   Object{shape: Box<dyn Shape>, material} src/object.rs:10-16
+//   Transformed<T>{transform, linear, inverse_transform, normal_transform, scale} src/shape.rs:99-125
+//   KdTree<Triangle>{root, objects, bounds} src/kdtree.rs:99-104,226-233
+//   Triangle{v1,v2,v3,n1,n2,n3}           src/shape/mesh.rs:7-22
+//   Material (6 fields)                   src/material.rs:7-26
+//   Light                                 src/light.rs:7-19
+//   Hdri{width,height,buf}                src/environment.rs:4-14
+//
+// Layout (R = float unless the parity gate asks for double):
+//   objects[]   ObjectRec<R>   one per scene object, uniform access -> __constant__ when it fits
+//   lights[]    LightRec<R>
+//   materials[] MaterialRec<R> divergent access -> global (L1-resident)
+//   per mesh:   nodes[]  KdNodeDev (8 B: split f32 | (child<<2 | axis), leaf: first_ref | (count<<2 | 3))
+//                        for double: KdNodeDev64 (16 B)
+//               refs[]   u32 triangle indices, leaf order of the reference (ascending)
+//               tri48[]  3 x float4 per triangle (f32 only): plane + two barycentric functionals
+//               verts[]  9 R per triangle  (v1,v2,v3)  -- f64 intersect, light sampling
+//               norms[]  9 R per triangle  (n1,n2,n3)  -- fetched once per final hit
+#pragma once
+#include "vec.cuh"
+
+namespace rptb {
+
+enum : uint32_t { SHAPE_SPHERE = 0, SHAPE_PLANE = 1, SHAPE_CUBE = 2, SHAPE_MESH = 3 };
+enum : uint32_t { LIGHT_POINT = 0, LIGHT_AMBIENT = 1, LIGHT_DIRECTIONAL = 2, LIGHT_OBJECT = 3 };
+
+constexpr int KD_STACK = 64;          // max kd-tree depth the traversal stack holds
+constexpr int MAX_CONST_OBJECTS = 96;  // tables up to this size live in __constant__ memory
+constexpr int MAX_CONST_LIGHTS = 16;
+
+struct KdNodeDev {  // 8 B
+    union {
+        float split;         // interior
+        uint32_t first_ref;  // leaf
+    };
+    uint32_t word;  // interior: (right_child << 2) | axis ; leaf: (num_refs << 2) | 3
+};
+struct KdNodeDev64 {  // 16 B, parity gate
+    double split;
+    uint32_t word;       // as above
+    uint32_t first_ref;  // leaf
+};
+template <class R>
+struct NodeOf;
+template <>
+struct NodeOf<float> { typedef KdNodeDev type; };
+template <>
+struct NodeOf<double> { typedef KdNodeDev64 type; };
+
+template <class R>
+struct MeshRec {
+    const typename NodeOf<R>::type* nodes;
+    const uint32_t* refs;
+    const float4* tri48;  // f32 only (null for double)
+    const R* verts;       // 9 per triangle
+    const R* norms;       // 9 per triangle
+    R bmin[3], bmax[3];   // KdTree::bounds
+    uint32_t ntris;
+    uint32_t root_is_leaf;
+};
+
+template <class R>
+struct ObjectRec {
+    uint32_t kind, material, mesh, has_transform;
+    R inv[12];  // rows of inverse_transform (3x4): local = inv * (p,1)
+    R nrm[9];   // rows of normal_transform M^-T (3x3)
+    R fwd[12];  // rows of transform (3x4), for Transformed::sample
+    R det;      // `scale` = det(linear)
+    R plane_n[3];
+    R plane_v;
+    R plane_unit[3];  // normalize(plane normal), precomputed
+    R _pad;
+};
+
+template <class R>
+struct MaterialRec {
+    R color[3];
+    R index, roughness, metallic, emittance;
+    uint32_t transparent;
+};
+
+template <class R>
+struct LightRec {
+    uint32_t kind, _pad;
+    R color[3];
+    R vec[3];
+    R radiance[3];  // OBJECT: material.color * material.emittance
+    ObjectRec<R> object;
+};
+
+template <class R>
+struct EnvRec {
+    uint32_t kind, width, height, _pad;
+    R color[3];
+    const float4* texels_f4;  // f32: rgb + pad
+    const double* texels_f64; // f64: packed rgb
+};
+
+template <class R>
+struct SceneView {
+    const ObjectRec<R>* objects;  // global copies (always valid)
+    const LightRec<R>* lights;
+    const MaterialRec<R>* materials;
+    const MeshRec<R>* meshes;
+    uint32_t nobjects, nlights, nmaterials, nmeshes;
+    uint32_t tables_in_const;  // objects+lights also staged in __constant__
+    EnvRec<R> env;
+};
+
+// Camera with the per-render invariants hoisted (src/camera.rs:64-81 recomputes
+// d, right per sample; the values are identical).
+template <class R>
+struct CameraRec {
+    R eye[3], direction[3], up[3], right[3];
+    R d;  // 1 / tan(fov / 2)
+    R aperture, focal_distance;
+};
+
+struct DeviceCounters {
+    unsigned long long segments, rays, node_visits, tri_tests, mesh_hits, env_lookups;
+};
+
+template <class R>
+struct RenderArgs {
+    CameraRec<R> cam;
+    uint32_t width, height, iterations, max_bounces;
+    R exposure_scale;  // 2^EV
+    uint64_t seed, first_sample;
+    uint32_t shard_index, shard_count;
+    uint32_t tiles_x, tiles_y, ntiles_mine;
+    R* out;  // width*height*3
+    DeviceCounters* counters;
+};
+
+}  // namespace rptb

@@ -1,0 +1,222 @@
+"""The five BASELINE.json configs, restated from the reference's example scripts with
+the host mirror of rpt's API (rpt_b200.api).  Resolution / spp / bounces come from
+BASELINE.json; where it is silent, from the example file.
+
+    sphere   examples/sphere.rs:4-34
+    cornell  examples/cornell.rs:14-88
+    teapot   examples/teapot.rs:10-34
+    dragon   examples/dragon.rs:32-75   (mesh: procedural stand-in, see dragon_proxy)
+    glass    examples/glass.rs:27-49    (HDRI: synthetic stand-in, see synthetic_hdri)
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .api import (Camera, Environment, Hdri, Light, Material, Mesh, Object, Scene, cube, hex_color, plane, polygon,
+                  sphere, vec3)
+
+_ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+@dataclass
+class Config:
+    name: str
+    scene: Scene
+    camera: Camera
+    width: int
+    height: int
+    spp: int
+    max_bounces: int
+    note: str = ""
+
+    def nominal_segments(self) -> int:
+        return self.width * self.height * self.spp * (self.max_bounces + 1)
+
+
+def sphere_scene() -> Config:
+    scene = Scene()
+    scene.add(Object(sphere()))  # default red material
+    scene.add(Object(plane(vec3(0.0, 1.0, 0.0), -1.0)).material(Material.diffuse(hex_color(0xAAAAAA))))
+    scene.add(Light.Object(
+        Object(sphere().scale(vec3(2.0, 2.0, 2.0)).translate(vec3(0.0, 12.0, 0.0)))
+        .material(Material.light(hex_color(0xFFFFFF), 40.0))))
+    camera = Camera.look_at(vec3(-2.5, 4.0, 6.5), vec3(0.0, -0.25, 0.0), vec3(0.0, 1.0, 0.0), math.pi / 4)
+    return Config("sphere", scene, camera, 960, 540, 100, 2, "examples/sphere.rs verbatim")
+
+
+def cornell_scene() -> Config:
+    scene = Scene()
+    camera = Camera(eye=vec3(278.0, 273.0, -800.0), direction=vec3(0.0, 0.0, 1.0), up=vec3(0.0, 1.0, 0.0), fov=0.686)
+    white = Material.diffuse(hex_color(0xAAAAAA))
+    red = Material.diffuse(hex_color(0xBC0000))
+    green = Material.diffuse(hex_color(0x00BC00))
+    light_mtl = Material.light(hex_color(0xFFFEFA), 100.0)  # 6500 K
+    floor = polygon([vec3(0.0, 0.0, 0.0), vec3(0.0, 0.0, 559.2), vec3(556.0, 0.0, 559.2), vec3(556.0, 0.0, 0.0)])
+    ceiling = polygon([vec3(0.0, 548.9, 0.0), vec3(556.0, 548.9, 0.0), vec3(556.0, 548.9, 559.2),
+                       vec3(0.0, 548.9, 559.2)])
+    light_rect = polygon([vec3(343.0, 548.8, 227.0), vec3(343.0, 548.8, 332.0), vec3(213.0, 548.8, 332.0),
+                          vec3(213.0, 548.8, 227.0)])
+    back_wall = polygon([vec3(0.0, 0.0, 559.2), vec3(0.0, 548.9, 559.2), vec3(556.0, 548.9, 559.2),
+                         vec3(556.0, 0.0, 559.2)])
+    right_wall = polygon([vec3(0.0, 0.0, 0.0), vec3(0.0, 548.9, 0.0), vec3(0.0, 548.9, 559.2), vec3(0.0, 0.0, 559.2)])
+    left_wall = polygon([vec3(556.0, 0.0, 0.0), vec3(556.0, 0.0, 559.2), vec3(556.0, 548.9, 559.2),
+                         vec3(556.0, 548.9, 0.0)])
+    large_box = (cube().scale(vec3(165.0, 330.0, 165.0)).rotate_y(2.0 * math.pi * (-253.0 / 360.0))
+                 .translate(vec3(368.0, 165.0, 351.0)))
+    small_box = (cube().scale(vec3(165.0, 165.0, 165.0)).rotate_y(2.0 * math.pi * (-197.0 / 360.0))
+                 .translate(vec3(185.0, 82.5, 169.0)))
+    scene.add(Object(floor).material(white))
+    scene.add(Object(ceiling).material(white))
+    scene.add(Object(back_wall).material(white))
+    scene.add(Object(left_wall).material(red))
+    scene.add(Object(right_wall).material(green))
+    scene.add(Object(large_box).material(white))
+    scene.add(Object(small_box).material(white))
+    scene.add(Light.Object(Object(light_rect).material(light_mtl)))
+    return Config("cornell", scene, camera, 800, 800, 512, 6,
+                  "examples/cornell.rs geometry; 800x800x512 spp, max_bounces 6 per BASELINE.json")
+
+
+def teapot_triangles() -> np.ndarray:
+    return np.load(os.path.join(_ASSETS, "teapot_tris.npz"))["tris"]
+
+
+def teapot_scene() -> Config:
+    scene = Scene()
+    teapot = Mesh(teapot_triangles())
+    scene.add(Object(teapot.scale(vec3(0.5, 0.5, 0.5)).translate(vec3(0.0, -1.0, 0.0)))
+              .material(Material.metallic_(hex_color(0xFF0000), 0.4)))
+    scene.add(Object(plane(vec3(0.0, 1.0, 0.0), -1.0)).material(Material.diffuse(hex_color(0xAAAAAA))))
+    scene.add(Light.Ambient(vec3(0.02, 0.02, 0.02)))
+    scene.add(Light.Point(vec3(60.0, 60.0, 60.0), vec3(0.0, 5.0, 5.0)))
+    return Config("teapot", scene, Camera.default(), 1920, 1080, 256, 0,
+                  "examples/teapot.rs; teapot.obj has 2256 triangles; max_bounces 0 is the example's default")
+
+
+def dragon_proxy(n_u: int = 1320, n_v: int = 330, seed: int = 7) -> np.ndarray:
+    """A closed, bumpy (2,3) torus-knot tube with n_u*n_v*2 triangles (871 200 by default,
+    the Stanford dragon has 871 414), smooth vertex normals, scaled into the dragon's
+    bounding box so that `scale 3.4` rests it on the plane y = -1 like examples/dragon.rs.
+    The real dragon.obj is an HTTP download in the reference (examples/dragon.rs:11-14)
+    and is not available offline; every table labels this mesh "dragon-proxy"."""
+    rng = np.random.default_rng(seed)
+    u = np.linspace(0.0, 2.0 * np.pi, n_u, endpoint=False)
+    v = np.linspace(0.0, 2.0 * np.pi, n_v, endpoint=False)
+    p, q = 2.0, 3.0
+    # centre curve of the knot and a parallel-transport-free frame (Frenet is fine: no inflections)
+    r = np.cos(q * u) + 2.0
+    c = np.stack([r * np.cos(p * u), -np.sin(q * u), r * np.sin(p * u)], axis=1)
+    du = 1e-4
+    r2 = np.cos(q * (u + du)) + 2.0
+    c2 = np.stack([r2 * np.cos(p * (u + du)), -np.sin(q * (u + du)), r2 * np.sin(p * (u + du))], axis=1)
+    t = c2 - c
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    up = np.array([0.0, 1.0, 0.0])
+    b = np.cross(t, up)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    n = np.cross(b, t)
+    uu, vv = np.meshgrid(u, v, indexing="ij")
+    # scales ("bumps"): a few seeded octaves of periodic displacement of the tube radius
+    disp = np.zeros_like(uu)
+    for k in range(6):
+        fu, fv = int(rng.integers(3, 90)), int(rng.integers(1, 24))
+        ph = rng.uniform(0, 2 * np.pi, 2)
+        disp += (0.5 ** (k * 0.5)) * np.sin(fu * uu + ph[0]) * np.sin(fv * vv + ph[1])
+    rad = 0.42 * (1.0 + 0.11 * disp)
+    pos = (c[:, None, :] + rad[..., None] * (np.cos(vv)[..., None] * n[:, None, :] + np.sin(vv)[..., None] * b[:, None, :]))
+    # fit into the dragon's box: x in [-0.5, 0.5], y_min = -1/3.4
+    lo, hi = pos.reshape(-1, 3).min(0), pos.reshape(-1, 3).max(0)
+    s = 1.0 / (hi[0] - lo[0])
+    pos = (pos - (lo + hi) / 2.0) * s
+    pos[..., 1] += (-1.0 / 3.4) - pos[..., 1].min()
+    i0 = np.arange(n_u)[:, None]
+    j0 = np.arange(n_v)[None, :]
+    i1, j1 = (i0 + 1) % n_u, (j0 + 1) % n_v
+    a, bq, cq, dq = pos[i0, j0], pos[i1, j0], pos[i1, j1], pos[i0, j1]
+    # smooth normals: area-weighted face normals accumulated on the grid vertices
+    fn1 = np.cross(bq - a, cq - a)
+    fn2 = np.cross(cq - a, dq - a)
+    vn = np.zeros_like(pos)
+    for (ii, jj), f in (((i0, j0), fn1 + fn2), ((i1, j0), fn1), ((i1, j1), fn1 + fn2), ((i0, j1), fn2)):
+        np.add.at(vn, (np.broadcast_to(ii, fn1.shape[:2]), np.broadcast_to(jj, fn1.shape[:2])), f)
+    vn /= np.linalg.norm(vn, axis=2, keepdims=True)
+    na, nb, nc, nd = vn[i0, j0], vn[i1, j0], vn[i1, j1], vn[i0, j1]
+    t1 = np.concatenate([a, bq, cq, na, nb, nc], axis=2)
+    t2 = np.concatenate([a, cq, dq, na, nc, nd], axis=2)
+    tris = np.stack([t1, t2], axis=2).reshape(-1, 18)
+    # orient every triangle's winding with its vertex normals (outward)
+    return np.ascontiguousarray(tris)
+
+
+_DRAGON_CACHE = {}
+
+
+def dragon_mesh(n_u: int = 1320, n_v: int = 330) -> Mesh:
+    key = (n_u, n_v)
+    if key not in _DRAGON_CACHE:
+        path = os.environ.get("RPT_DRAGON_OBJ")
+        if path and os.path.exists(path):
+            from .api import load_obj
+            _DRAGON_CACHE[key] = load_obj(path)
+        else:
+            _DRAGON_CACHE[key] = Mesh(dragon_proxy(n_u, n_v))
+    return _DRAGON_CACHE[key]
+
+
+def dragon_scene(n_u: int = 1320, n_v: int = 330) -> Config:
+    scene = Scene()
+    dragon = dragon_mesh(n_u, n_v)
+    scene.add(Object(dragon.scale(vec3(3.4, 3.4, 3.4)).rotate_y(math.pi / 2))
+              .material(Material.specular(hex_color(0xB7CA79), 0.1)))
+    scene.add(Object(plane(vec3(0.0, 1.0, 0.0), -1.0)).material(Material.diffuse(hex_color(0xAAAAAA))))
+    scene.add(Light.Ambient(vec3(0.01, 0.01, 0.01)))
+    scene.add(Light.Object(Object(sphere().scale(vec3(2.0, 2.0, 2.0)).translate(vec3(0.0, 20.0, 3.0)))
+                           .material(Material.light(vec3(1.0, 1.0, 1.0), 160.0))))
+    scene.add(Light.Object(Object(sphere().scale(vec3(0.05, 0.05, 0.05)).translate(vec3(-1.0, 0.71, 0.0)))
+                           .material(Material.light(hex_color(0xFFAAAA), 400.0))))
+    camera = Camera.look_at(vec3(-2.5, 4.0, 6.5), vec3(0.0, 0.0, 0.0), vec3(0.0, 1.0, 0.0), math.pi / 6)
+    real = bool(os.environ.get("RPT_DRAGON_OBJ"))
+    return Config("dragon" if real else "dragon-proxy", scene, camera, 1920, 1080, 1024, 2,
+                  "examples/dragon.rs layout; mesh = %s (%d triangles)" % ("dragon.obj" if real else "procedural proxy", len(dragon)))
+
+
+def synthetic_hdri(width: int = 2048, height: int = 1024, seed: int = 11) -> Hdri:
+    """Stand-in for ballroom_2k.hdr (examples/glass.rs:30 fetches it over HTTPS): a smooth
+    vertical gradient 0.05..1.0 plus 8 Gaussian lamps of peak radiance 50 at seeded
+    directions, generated identically for the oracle and the GPU."""
+    rng = np.random.default_rng(seed)
+    y = (np.arange(height) + 0.5) / height
+    x = (np.arange(width) + 0.5) / width
+    base = 1.0 - 0.95 * y  # bright zenith, dim nadir
+    img = np.repeat(base[:, None, None], width, axis=1) * np.array([0.9, 0.95, 1.0])[None, None, :]
+    img = np.repeat(img, 1, axis=2)
+    for _ in range(8):
+        cx, cy = rng.uniform(0, 1), rng.uniform(0.1, 0.6)
+        sx, sy = rng.uniform(0.004, 0.02), rng.uniform(0.004, 0.02)
+        tint = rng.uniform(0.7, 1.0, 3)
+        dxw = np.minimum(np.abs(x - cx), 1.0 - np.abs(x - cx))  # wrap in azimuth
+        g = np.exp(-0.5 * (dxw[None, :] / sx) ** 2 - 0.5 * ((y[:, None] - cy) / sy) ** 2)
+        img = img + 50.0 * g[..., None] * tint[None, None, :]
+    return Hdri(width, height, img.reshape(-1, 3))
+
+
+def glass_scene(hdri_width: int = 2048, hdri_height: int = 1024) -> Config:
+    scene = Scene()
+    scene.environment = Environment.Hdri(synthetic_hdri(hdri_width, hdri_height))
+    scene.add(Object(sphere().translate(vec3(1.1, 0.0, 0.0))).material(Material.metallic_(hex_color(0xFFFFFF), 0.0001)))
+    scene.add(Object(sphere().translate(vec3(-1.1, 0.0, 0.0))).material(Material.clear(1.5, 0.0001)))
+    return Config("glass", scene, Camera.default(), 1920, 1080, 4096, 12,
+                  "examples/glass.rs; synthetic HDRI; 1920x1080x4096 spp, max_bounces 12 per BASELINE.json")
+
+
+CONFIGS = {
+    "sphere": sphere_scene,
+    "cornell": cornell_scene,
+    "teapot": teapot_scene,
+    "dragon": dragon_scene,
+    "glass": glass_scene,
+}
