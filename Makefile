@@ -3,7 +3,7 @@
 #   make lib        -> product only
 #   make oracle     -> oracle only
 NVCC      ?= nvcc
-CXX       ?= g++
+CXX       := g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC,-fopenmp -Xptxas -v
 CSRC      := rpt_b200/csrc

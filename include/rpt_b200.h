@@ -192,6 +192,7 @@ typedef struct rptb_stats {
     uint64_t tri_tests;   /* Triangle::intersect calls (mesh.rs:49), if collected */
     uint64_t mesh_hits;   /* closest hits that landed on a mesh                */
     uint64_t env_lookups; /* escaped paths that sampled an HDRI                */
+    uint64_t object_tests;/* Shape::intersect dispatches (objects tested per ray, summed) */
     double gpu_ms;        /* device time of the render launch(es)              */
     uint32_t launches;    /* kernels launched by the call                      */
     uint32_t _pad;

@@ -263,10 +263,10 @@ struct Rng {
 
 // ------------------------------------------------------------- counters ----
 struct Counters {
-    uint64_t segments = 0, rays = 0, node_visits = 0, tri_tests = 0, mesh_hits = 0, env_lookups = 0;
+    uint64_t segments = 0, rays = 0, node_visits = 0, tri_tests = 0, mesh_hits = 0, env_lookups = 0, object_tests = 0;
     void add(const Counters& o) {
         segments += o.segments; rays += o.rays; node_visits += o.node_visits;
-        tri_tests += o.tri_tests; mesh_hits += o.mesh_hits; env_lookups += o.env_lookups;
+        tri_tests += o.tri_tests; mesh_hits += o.mesh_hits; env_lookups += o.env_lookups; object_tests += o.object_tests;
     }
 };
 
@@ -895,8 +895,10 @@ struct Renderer {
         c.rays++;
         h = HitRecord();
         const Object* hit = nullptr;
-        for (const Object& object : scene->objects)
+        for (const Object& object : scene->objects) {
+            c.object_tests++;
             if (object.shape->intersect(ray, EPSILON, h, c)) hit = &object;
+        }
         return hit;
     }
     // sample_lights :177-204
@@ -1083,6 +1085,7 @@ void put_stats(const Counters& c, rptb_stats* s) {
     std::memset(s, 0, sizeof(*s));
     s->segments = c.segments; s->rays = c.rays; s->node_visits = c.node_visits;
     s->tri_tests = c.tri_tests; s->mesh_hits = c.mesh_hits; s->env_lookups = c.env_lookups;
+    s->object_tests = c.object_tests;
 }
 
 }  // namespace
@@ -1119,8 +1122,10 @@ int oracle_render(const oracle_scene* s, const rptb_camera* cam, const rptb_rend
                       v3(cam->up[0], cam->up[1], cam->up[2]), cam->fov, cam->aperture, cam->focal_distance};
     r.width = p->width; r.height = p->height; r.max_bounces = p->max_bounces; r.exposure_value = p->exposure_value;
     Counters total;
+    // Pixel tiles (16x8, round-robin) of other shards are left zero, mirroring the multi-GPU
+    // partition of the product (rpt_b200/distributed.py); shard_count <= 1 renders everything.
     const uint32_t shard_count = p->shard_count ? p->shard_count : 1;
-    (void)shard_count;
+    const uint32_t tiles_x = (p->width + 15) / 16;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -1130,8 +1135,13 @@ int oracle_render(const oracle_scene* s, const rptb_camera* cam, const rptb_rend
 #pragma omp for schedule(dynamic, 1)
         for (int64_t y = 0; y < (int64_t)p->height; y++) {
             for (uint32_t x = 0; x < p->width; x++) {
-                const V3 c = r.get_color(x, (uint32_t)y, p->iterations, p->seed, p->first_sample, local);
                 double* o = out_rgb + 3 * ((size_t)y * p->width + x);
+                const uint32_t tile = ((uint32_t)y / 8) * tiles_x + x / 16;
+                if (tile % shard_count != p->shard_index) {
+                    o[0] = o[1] = o[2] = 0.0;
+                    continue;
+                }
+                const V3 c = r.get_color(x, (uint32_t)y, p->iterations, p->seed, p->first_sample, local);
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             }
         }
@@ -1292,10 +1302,10 @@ double oracle_variance(const double* batches, uint32_t nbatches, uint64_t npixel
 }
 
 // Raw Philox blocks, for checking the device generator bit for bit.
-void oracle_philox(uint64_t seed, uint32_t pixel, uint64_t sample, uint32_t nblocks, uint32_t* out) {
+void oracle_philox(uint64_t seed, uint32_t pixel, uint64_t sample, uint32_t first_block, uint32_t nblocks, uint32_t* out) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     for (uint32_t b = 0; b < nblocks; b++) {
-        const uint32_t ctr[4] = {b, pixel, (uint32_t)sample, (uint32_t)(sample >> 32)};
+        const uint32_t ctr[4] = {first_block + b, pixel, (uint32_t)sample, (uint32_t)(sample >> 32)};
         Philox::block(ctr, key, out + 4 * b);
     }
 }

@@ -55,7 +55,7 @@ def lib() -> C.CDLL:
     L.oracle_film_resolve.argtypes = [dp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, capi.c_u8_p]
     L.oracle_variance.restype = C.c_double
     L.oracle_variance.argtypes = [dp, C.c_uint32, C.c_uint64]
-    L.oracle_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, capi.c_u32_p]
+    L.oracle_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, capi.c_u32_p]
     L.oracle_draws.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, dp]
     _lib = L
     return L
@@ -173,9 +173,9 @@ def variance(batches: np.ndarray) -> float:
     return float(lib().oracle_variance(_p(batches), batches.shape[0], batches.shape[1]))
 
 
-def philox(seed: int, pixel: int, sample: int, nblocks: int) -> np.ndarray:
+def philox(seed: int, pixel: int, sample: int, nblocks: int, first_block: int = 0) -> np.ndarray:
     out = np.empty(4 * nblocks, np.uint32)
-    lib().oracle_philox(seed, pixel, sample, nblocks, out.ctypes.data_as(capi.c_u32_p))
+    lib().oracle_philox(seed, pixel, sample, first_block, nblocks, out.ctypes.data_as(capi.c_u32_p))
     return out
 
 

@@ -142,6 +142,7 @@ class Stats(C.Structure):
         ("tri_tests", C.c_uint64),
         ("mesh_hits", C.c_uint64),
         ("env_lookups", C.c_uint64),
+        ("object_tests", C.c_uint64),
         ("gpu_ms", C.c_double),
         ("launches", C.c_uint32),
         ("_pad", C.c_uint32),

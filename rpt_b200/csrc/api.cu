@@ -536,6 +536,7 @@ void read_stats(const DeviceCounters& c, rptb_stats* st) {
     st->tri_tests = c.tri_tests;
     st->mesh_hits = c.mesh_hits;
     st->env_lookups = c.env_lookups;
+    st->object_tests = c.object_tests;
 }
 
 // Launch the render on `stream` into a device buffer of the precision's type.

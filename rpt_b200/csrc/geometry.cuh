@@ -35,7 +35,7 @@ struct Hit {
 };
 
 struct TravStats {
-    uint32_t node_visits, tri_tests;
+    uint32_t node_visits, tri_tests, object_tests;
 };
 
 template <class R>

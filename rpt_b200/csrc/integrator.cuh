@@ -62,6 +62,7 @@ RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, Hi
     h.bv = h.bw = (R)0;
     const uint32_t n = sv.nobjects;
     for (uint32_t i = 0; i < n; i++) {
+        if (STATS) ts.object_tests++;
         if (object_intersect<R, ANY, STATS>(sv, sv.objects[i], o, d, tmin, h, ts)) {
             h.obj = (int)i;
             if (ANY) return;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
     const Vec3<R> cup = {a.cam.up[0], a.cam.up[1], a.cam.up[2]};
     const Vec3<R> cright = {a.cam.right[0], a.cam.right[1], a.cam.right[2]};
 
-    PathCounters pc = {0, 0, 0, 0, {0, 0}};
+    PathCounters pc = {0, 0, 0, 0, {0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     Level<R> stack[MAXD];
     Rng<R> rng;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
         // node/tri counters can exceed 2^32 per warp on long renders: reduce in two halves
         const uint32_t n_lo = __reduce_add_sync(m, pc.ts.node_visits & 0xFFFFu), n_hi = __reduce_add_sync(m, pc.ts.node_visits >> 16);
         const uint32_t t_lo = __reduce_add_sync(m, pc.ts.tri_tests & 0xFFFFu), t_hi = __reduce_add_sync(m, pc.ts.tri_tests >> 16);
+        const uint32_t o_sum = __reduce_add_sync(m, pc.ts.object_tests);
         if ((int)lane == leader) {
             atomicAdd(&a.counters->segments, (unsigned long long)v0);
             atomicAdd(&a.counters->rays, (unsigned long long)v1);
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
             if (STATS) {
                 atomicAdd(&a.counters->node_visits, (unsigned long long)n_lo + ((unsigned long long)n_hi << 16));
                 atomicAdd(&a.counters->tri_tests, (unsigned long long)t_lo + ((unsigned long long)t_hi << 16));
+                atomicAdd(&a.counters->object_tests, (unsigned long long)o_sum);
             }
         }
     }
@@ -264,7 +267,7 @@ __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restri
                                    double* __restrict__ out_t, int32_t* __restrict__ out_obj,
                                    double* __restrict__ out_n, DeviceCounters* counters) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    TravStats ts = {0, 0};
+    TravStats ts = {0, 0, 0};
     if (i < n) {
         const double* r = rays + 6 * i;
         const Vec3<R> o = {(R)r[0], (R)r[1], (R)r[2]};
@@ -287,6 +290,7 @@ __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restri
         if (STATS && i < n) {
             atomicAdd(&counters->node_visits, (unsigned long long)ts.node_visits);
             atomicAdd(&counters->tri_tests, (unsigned long long)ts.tri_tests);
+            atomicAdd(&counters->object_tests, (unsigned long long)ts.object_tests);
         }
     }
 }

@@ -121,7 +121,7 @@ struct CameraRec {
 };
 
 struct DeviceCounters {
-    unsigned long long segments, rays, node_visits, tri_tests, mesh_hits, env_lookups;
+    unsigned long long segments, rays, node_visits, tri_tests, mesh_hits, env_lookups, object_tests;
 };
 
 template <class R>

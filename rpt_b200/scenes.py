@@ -145,10 +145,10 @@ def dragon_proxy(n_u: int = 1320, n_v: int = 330, seed: int = 7) -> np.ndarray:
         np.add.at(vn, (np.broadcast_to(ii, fn1.shape[:2]), np.broadcast_to(jj, fn1.shape[:2])), f)
     vn /= np.linalg.norm(vn, axis=2, keepdims=True)
     na, nb, nc, nd = vn[i0, j0], vn[i1, j0], vn[i1, j1], vn[i0, j1]
-    t1 = np.concatenate([a, bq, cq, na, nb, nc], axis=2)
-    t2 = np.concatenate([a, cq, dq, na, nc, nd], axis=2)
+    # wind the triangles (and flip the accumulated normals) so that both point out of the tube
+    t1 = np.concatenate([a, cq, bq, -na, -nc, -nb], axis=2)
+    t2 = np.concatenate([a, dq, cq, -na, -nd, -nc], axis=2)
     tris = np.stack([t1, t2], axis=2).reshape(-1, 18)
-    # orient every triangle's winding with its vertex normals (outward)
     return np.ascontiguousarray(tris)
 
 

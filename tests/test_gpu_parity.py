@@ -1,0 +1,387 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and -- at
+BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (stated once, used below):
+  * f64 parity gate vs oracle: closest hit bit-exact; BSDF / pdf rtol 1e-9 (CUDA's
+    exp/log/atan/sincos are <= 2 ulp, glibc's differ in the last bit); images: >= 98 % of
+    pixels within rtol 1e-9 -- the rest are rays whose EPSILON = 1e-12 self-intersection
+    test (src/renderer.rs:14,215) flips on a 1-ulp difference, a property of the reference.
+  * f32 product path vs oracle, same Philox streams: closest hit object agreement
+    >= 99.99 % and |dt|/t <= 1e-5; BSDF rtol 2e-4; images: RMSE <= 0.25 x the oracle's own
+    seed-to-seed RMSE (i.e. far inside Monte-Carlo noise) and image mean within 0.5 %.
+  * f32 vs oracle, different seeds (statistical): RMSE <= 1.25 x the oracle noise floor.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+from rpt_b200 import _capi as capi
+from rpt_b200 import api, scenes
+from rpt_b200.distributed import tile_owner
+from tests import util
+from tests.test_oracle import MATERIALS
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+F32, F64 = capi.PRECISION_F32, capi.PRECISION_F64
+
+
+def _rays_for(name, cfg, rng, n):
+    if name == "cornell":
+        return np.concatenate([util.camera_rays(cfg.camera, n, rng), util.interior_rays([1, 1, 1], [555, 548, 559], n, rng)])
+    if name == "sphere":
+        return np.concatenate([util.camera_rays(cfg.camera, n, rng), util.interior_rays([-3, -0.9, -3], [3, 3, 3], n, rng)])
+    if name == "glass":
+        return np.concatenate([util.camera_rays(cfg.camera, n, rng, spread=0.3), util.interior_rays([-2, -1, -1], [2, 1, 1], n, rng)])
+    return np.concatenate([util.camera_rays(cfg.camera, n, rng, spread=0.4), util.interior_rays([-2, -0.99, -2], [2, 1.5, 2], n, rng)])
+
+
+@pytest.fixture(scope="module")
+def cfgs(gpu_ok):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            if name == "dragon":
+                cfg = scenes.dragon_scene()
+            elif name == "glass":
+                cfg = scenes.glass_scene(256, 128)
+            else:
+                cfg = scenes.CONFIGS[name]()
+            flat = api.FlatScene(cfg.scene)
+            cache[name] = (cfg, flat, api.DeviceScene(flat))
+        return cache[name]
+
+    yield get
+    for _, _, ds in cache.values():
+        ds.close()
+
+
+# ------------------------------------------------------------ closest hit (K2, T2) --------
+@pytest.mark.parametrize("name", ["sphere", "cornell", "teapot", "glass", "dragon"])
+def test_closest_hit_parity(orc, cfgs, name):
+    cfg, flat, ds = cfgs(name)
+    osc = orc.OracleScene(flat)
+    rng = np.random.default_rng(11)
+    rays = _rays_for(name, cfg, rng, 100000 if name != "dragon" else 250000)
+    t0, o0, n0, s0 = osc.closest_hit(rays)
+    assert (o0 >= 0).mean() > 0.3
+    # f64 gate: the redesigned interval traversal finds exactly the reference's hit
+    t1, o1, n1, s1 = ds.closest_hit(rays, precision=F64, want_stats=True)
+    assert (o1 == o0).all()
+    np.testing.assert_array_equal(t1, t0)
+    np.testing.assert_allclose(n1, n0, atol=1e-15)
+    if s0["tri_tests"]:
+        # same leaves visited: counters agree (SURVEY 8d asks for 1 %)
+        assert abs(s1["tri_tests"] - s0["tri_tests"]) <= 0.01 * s0["tri_tests"]
+        assert abs(s1["node_visits"] - s0["node_visits"]) <= 0.01 * s0["node_visits"]
+    # f32 product path
+    t2, o2, n2, _ = ds.closest_hit(rays, precision=F32, want_stats=True)
+    agree = o2 == o0
+    assert agree.mean() >= 0.9999, agree.mean()
+    hit = agree & (o0 >= 0)
+    rel = np.abs(t2[hit] - t0[hit]) / np.abs(t0[hit])
+    assert np.quantile(rel, 0.9999) <= 1e-5, np.quantile(rel, 0.9999)
+    dn = np.abs(n2[hit] - n0[hit]).max(axis=1)
+    assert np.quantile(dn, 0.999) <= 2e-3
+
+
+def test_closest_hit_edge_cases(orc, cfgs):
+    cfg, flat, ds = cfgs("cornell")
+    osc = orc.OracleScene(flat)
+    rays = np.array([
+        [278, 273, -800, 0, 0, 1],      # straight into the box
+        [278, 273, -800, 0, 0, -1],     # away: miss
+        [278, 273, 280, 0, 1, 0],       # up to the ceiling from inside
+        [278, 273, 280, 1, 0, 0],       # axis-parallel (zero direction components)
+        [0, 0, 0, 0, 0, 1],             # starts on a corner, slides along two walls
+        [278, 1e-9, 280, 0, -1, 0],     # a hair above the floor
+        [185, 82.5, 169, 0.3, 0.9, 0.1],  # from inside the small box
+    ], dtype=np.float64)
+    rays[:, 3:] /= np.linalg.norm(rays[:, 3:], axis=1, keepdims=True)
+    t0, o0, n0, _ = osc.closest_hit(rays)
+    t1, o1, n1 = ds.closest_hit(rays, precision=F64)
+    assert (o0 == o1).all() and o0[1] == -1 and np.isinf(t1[1])
+    np.testing.assert_array_equal(t0, t1)
+    # empty batch
+    t, o, n = ds.closest_hit(np.zeros((0, 6)))
+    assert t.size == 0 and o.size == 0
+
+
+# ------------------------------------------------------------ BSDF / sample_f (T3) --------
+def _device_bsdf(m, dirs, precision):
+    out = np.empty((dirs.shape[0], 3))
+    mc = m.to_c()
+    d = np.ascontiguousarray(dirs)
+    capi.check(capi.lib().rptb_bsdf_eval(C.byref(mc), d.ctypes.data_as(capi.c_double_p), d.shape[0], precision, 0,
+                                         out.ctypes.data_as(capi.c_double_p)), "rptb_bsdf_eval")
+    return out
+
+
+def _device_sample_f(m, dirs, seed, precision):
+    n = dirs.shape[0]
+    wi = np.empty((n, 3))
+    pdf = np.empty(n)
+    mc = m.to_c()
+    d = np.ascontiguousarray(dirs)
+    capi.check(capi.lib().rptb_sample_f(C.byref(mc), d.ctypes.data_as(capi.c_double_p), n, seed, precision, 0,
+                                        wi.ctypes.data_as(capi.c_double_p), pdf.ctypes.data_as(capi.c_double_p)),
+               "rptb_sample_f")
+    return wi, pdf
+
+
+@pytest.mark.parametrize("mname", sorted(MATERIALS))
+def test_bsdf_pointwise_parity(orc, gpu_ok, mname):
+    m = MATERIALS[mname]
+    rng = np.random.default_rng(13)
+    n, wo, wi = util.random_unit(rng, 50000), util.random_unit(rng, 50000), util.random_unit(rng, 50000)
+    dirs = np.concatenate([n, wo, wi], axis=1)
+    ref = orc.bsdf(m, dirs)
+    got64 = _device_bsdf(m, dirs, F64)
+    fin = np.isfinite(ref).all(1)
+    np.testing.assert_allclose(got64[fin], ref[fin], rtol=1e-9, atol=1e-300)
+    got32 = _device_bsdf(m, dirs, F32)
+    # away from grazing configurations (where the f64 value itself is ill-conditioned)
+    cond = fin & (np.abs((n * wi).sum(1)) > 0.05) & (np.abs((n * wo).sum(1)) > 0.05) & (np.linalg.norm(wi + wo, axis=1) > 0.1)
+    scale = np.maximum(np.abs(ref[cond]), 1e-6)
+    err = np.abs(got32[cond] - ref[cond]) / scale
+    assert np.quantile(err, 0.999) < 2e-4, np.quantile(err, 0.999)
+    assert ((got32 == 0) == (ref == 0))[cond].all()  # same sidedness decisions
+
+
+@pytest.mark.parametrize("mname", sorted(MATERIALS))
+def test_sample_f_parity(orc, gpu_ok, mname):
+    m = MATERIALS[mname]
+    rng = np.random.default_rng(17)
+    nn, wo = util.random_unit(rng, 50000), util.random_unit(rng, 50000)
+    dirs = np.concatenate([nn, wo], axis=1)
+    wi0, pdf0 = orc.sample_f(m, dirs, seed=5)
+    wi1, pdf1 = _device_sample_f(m, dirs, 5, F64)
+    assert ((pdf0 < 0) == (pdf1 < 0)).all()  # same `None`s (TIR)
+    np.testing.assert_allclose(wi1, wi0, atol=1e-12)
+    ok = pdf0 > 0
+    np.testing.assert_allclose(pdf1[ok], pdf0[ok], rtol=1e-8)
+    # f32: same lobe decisions from the same stream except within rounding of a threshold
+    wi2, pdf2 = _device_sample_f(m, dirs, 5, F32)
+    same_none = ((pdf0 < 0) == (pdf2 < 0))
+    assert same_none.mean() > 0.9995
+    both = ok & (pdf2 > 0)
+    close = np.abs(wi2[both] - wi0[both]).max(axis=1) < 1e-3
+    assert close.mean() > 0.998, close.mean()
+    rel = np.abs(pdf2[both][close] - pdf0[both][close]) / pdf0[both][close]
+    assert np.quantile(rel, 0.99) < 5e-3
+
+
+def test_glass_roughness_1e4_f32_is_stable(orc, gpu_ok):
+    """examples/glass.rs uses roughness 1e-4: f * |cos| / pdf must stay finite and close to
+    the f64 value although D and the pdf individually reach ~1e8."""
+    for m in (api.Material.clear(1.5, 1e-4), api.Material.metallic_(api.hex_color(0xFFFFFF), 1e-4)):
+        rng = np.random.default_rng(19)
+        nn = util.random_unit(rng, 40000)
+        wo = util.normalize(nn + 0.8 * util.random_unit(rng, 40000))  # outside, moderate angles
+        dirs = np.concatenate([nn, wo], axis=1)
+        wi0, pdf0 = orc.sample_f(m, dirs, seed=3)
+        wi2, pdf2 = _device_sample_f(m, dirs, 3, F32)
+        ok = (pdf0 > 0) & (pdf2 > 0) & (np.abs(wi2 - wi0).max(axis=1) < 1e-3)
+        assert ok.mean() > 0.9
+        f0 = orc.bsdf(m, np.concatenate([nn, wo, wi0], axis=1))[ok]
+        f2 = _device_bsdf(m, np.concatenate([nn, wo, wi2], axis=1), F32)[ok]
+        w0 = f0 * (np.abs((wi0 * nn).sum(1)) / pdf0)[ok, None]
+        w2 = f2 * (np.abs((wi2 * nn).sum(1)) / pdf2)[ok, None]
+        assert np.isfinite(w2).all()
+        rel = np.abs(w2 - w0) / np.maximum(np.abs(w0), 1e-3)
+        assert np.quantile(rel, 0.99) < 2e-2, np.quantile(rel, 0.99)
+
+
+# ------------------------------------------------------------ images ----------------------
+SMALL = {  # name: (w, h, spp, max_bounces)
+    "sphere": (96, 54, 32, 2),
+    "cornell": (64, 64, 32, 6),
+    "teapot": (96, 54, 16, 0),
+    "glass": (96, 54, 32, 12),
+    "dragon": (96, 54, 16, 2),
+}
+
+
+def _gpu_render(cfg, ds, w, h, spp, mb, seed, precision, first_sample=0, shard=(0, 1), ev=0.0, stats=0):
+    r = api.Renderer(cfg.scene, cfg.camera).width(w).height(h).max_bounces(mb).seed(seed).precision(precision) \
+        .exposure_value(ev)
+    p = r.params(spp, first_sample, shard[0], shard[1], collect_stats=stats)
+    cam = cfg.camera.to_c()
+    out = np.empty((w * h, 3))
+    st = capi.Stats()
+    capi.check(capi.lib().rptb_render_samples(ds.handle, C.byref(cam), C.byref(p), out.ctypes.data_as(capi.c_double_p),
+                                              C.byref(st)), "rptb_render_samples")
+    return out, st.as_dict()
+
+
+def _oracle_render(orc, cfg, flat, w, h, spp, mb, seed):
+    r = api.Renderer(cfg.scene, cfg.camera).width(w).height(h).max_bounces(mb).seed(seed)
+    return orc.OracleScene(flat).render(cfg.camera, r.params(spp))
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_render_parity_same_stream(orc, cfgs, name):
+    cfg, flat, ds = cfgs(name)
+    w, h, spp, mb = SMALL[name]
+    ref, st0 = _oracle_render(orc, cfg, flat, w, h, spp, mb, 1)
+    ref2, _ = _oracle_render(orc, cfg, flat, w, h, spp, mb, 2)
+    cl = lambda a: np.clip(a, 0.0, 1.0)
+    noise = util.rmse(cl(ref), cl(ref2))
+    assert noise > 0
+    # f64 gate
+    g64, st64 = _gpu_render(cfg, ds, w, h, spp, mb, 1, F64)
+    rel = np.abs(g64 - ref) / np.maximum(np.abs(ref), 1e-6)
+    frac_exact = (rel.max(axis=1) < 1e-9).mean()
+    assert frac_exact >= 0.98, frac_exact
+    assert abs(st64["segments"] - st0["segments"]) <= 2e-3 * st0["segments"]
+    assert abs(st64["rays"] - st0["rays"]) <= 2e-3 * st0["rays"]
+    assert util.rmse(cl(g64), cl(ref)) <= 0.05 * noise
+    # f32 product, same streams
+    g32, st32 = _gpu_render(cfg, ds, w, h, spp, mb, 1, F32)
+    assert np.isfinite(g32).all()
+    assert util.rmse(cl(g32), cl(ref)) <= 0.25 * noise, (util.rmse(cl(g32), cl(ref)), noise)
+    assert abs(cl(g32).mean() - cl(ref).mean()) <= 5e-3 * cl(ref).mean()
+    assert abs(st32["segments"] - st0["segments"]) <= 0.05 * st0["segments"]
+    # f32 product, independent streams: statistical parity
+    g32b, _ = _gpu_render(cfg, ds, w, h, spp, mb, 2, F32)
+    assert util.rmse(cl(g32b), cl(ref)) <= 1.25 * noise
+
+
+@pytest.mark.parametrize("name", ["sphere", "cornell", "teapot", "glass"])
+def test_gpu_matches_committed_golden(cfgs, name):
+    """The f64 gate reproduces the committed oracle fixture (tests/golden, tools/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, f"{name}_render.npz"))
+    cfg, flat, ds = cfgs(name)
+    img, st = _gpu_render(cfg, ds, int(g["width"]), int(g["height"]), int(g["spp"]), int(g["max_bounces"]), int(g["seed"]), F64)
+    rel = np.abs(img - g["image"]) / np.maximum(np.abs(g["image"]), 1e-6)
+    assert (rel.max(axis=1) < 1e-9).mean() >= 0.98
+    assert abs(st["segments"] - int(g["segments"])) <= 2e-3 * int(g["segments"])
+
+
+@pytest.mark.parametrize("name", ["cornell", "teapot"])
+def test_gpu_hits_match_committed_golden(cfgs, name):
+    g = np.load(os.path.join(GOLDEN, f"{name}_hits.npz"))
+    cfg, flat, ds = cfgs(name)
+    t, o, n = ds.closest_hit(g["rays"], precision=F64)
+    assert (o == g["obj"]).all()
+    np.testing.assert_allclose(t, g["t"], rtol=1e-12)
+
+
+# ------------------------------------------------------------ properties ------------------
+@pytest.mark.parametrize("precision", [F32, F64])
+def test_shards_sum_to_the_full_image_bit_exact(cfgs, precision):
+    cfg, flat, ds = cfgs("cornell")
+    w, h, spp, mb = 100, 52, 4, 3  # ragged: not multiples of the 16x8 tile
+    full, st = _gpu_render(cfg, ds, w, h, spp, mb, 7, precision)
+    for n in (2, 3, 8):
+        acc = np.zeros_like(full)
+        segs = 0
+        own = tile_owner(w, h, n).reshape(-1)
+        for i in range(n):
+            part, sti = _gpu_render(cfg, ds, w, h, spp, mb, 7, precision, shard=(i, n))
+            assert (part[own != i] == 0).all()  # other shards' pixels are written as zero
+            acc += part
+            segs += sti["segments"]
+        np.testing.assert_array_equal(acc, full)
+        assert segs == st["segments"]
+
+
+def test_determinism_and_sample_range_additivity(cfgs):
+    cfg, flat, ds = cfgs("sphere")
+    w, h, mb = 64, 36, 2
+    a, _ = _gpu_render(cfg, ds, w, h, 16, mb, 3, F32)
+    b, _ = _gpu_render(cfg, ds, w, h, 16, mb, 3, F32)
+    np.testing.assert_array_equal(a, b)
+    lo, _ = _gpu_render(cfg, ds, w, h, 8, mb, 3, F32, first_sample=0)
+    hi, _ = _gpu_render(cfg, ds, w, h, 8, mb, 3, F32, first_sample=8)
+    np.testing.assert_allclose((lo + hi) / 2, a, rtol=2e-6, atol=1e-7)  # f32 output rounding only
+    c, _ = _gpu_render(cfg, ds, w, h, 16, mb, 4, F32)
+    assert not np.array_equal(a, c)  # the seed matters
+    e, _ = _gpu_render(cfg, ds, w, h, 16, mb, 3, F32, ev=1.0)
+    np.testing.assert_allclose(e, 2 * a, rtol=1e-6)  # 2^EV (src/renderer.rs:141)
+
+
+def test_full_size_cornell_properties(cfgs):
+    """BASELINE config 1 at full resolution (800x800, max_bounces 6), few spp: shard sum
+    identity, segment-count bounds, finite non-negative radiance, image statistics stable
+    between disjoint sample ranges."""
+    cfg, flat, ds = cfgs("cornell")
+    w, h, mb, spp = 800, 800, 6, 4
+    full, st = _gpu_render(cfg, ds, w, h, spp, mb, 1, F32, stats=1)
+    assert np.isfinite(full).all() and (full >= 0).all()
+    paths = w * h * spp
+    assert paths <= st["segments"] <= paths * (mb + 1)
+    assert st["segments"] <= st["rays"] <= 2 * st["segments"]  # one light: at most one shadow ray per vertex
+    assert st["tri_tests"] > 0 and st["node_visits"] > 0
+    parts = sum(_gpu_render(cfg, ds, w, h, spp, mb, 1, F32, shard=(i, 4))[0] for i in range(4))
+    np.testing.assert_array_equal(parts, full)
+    other, _ = _gpu_render(cfg, ds, w, h, spp, mb, 1, F32, first_sample=spp)
+    assert abs(other.mean() - full.mean()) < 0.01 * full.mean()
+    # the closed box: walls are lit, so almost every pixel inside the opening is non-black
+    assert (full.sum(axis=1) > 0).mean() > 0.95
+
+
+def test_teapot_direct_lighting_is_deterministic_in_rng(cfgs, orc):
+    """max_bounces 0 with a point light draws nothing after the camera jitter: with the
+    jitter shared, f32 and the oracle agree pixel by pixel to f32 accuracy."""
+    cfg, flat, ds = cfgs("teapot")
+    ref, _ = _oracle_render(orc, cfg, flat, 160, 90, 4, 0, 5)
+    got, _ = _gpu_render(cfg, ds, 160, 90, 4, 0, 5, F32)
+    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-4)
+    assert np.quantile(rel.max(axis=1), 0.995) < 1e-3
+
+
+# ------------------------------------------------------------ film (N1) -------------------
+def test_film_resolve_matches_oracle_bytes(orc, gpu_ok):
+    rng = np.random.default_rng(23)
+    w, h, nb = 70, 41, 3
+    sums = rng.uniform(0, 3.5, (w * h, 3))
+    for radius in (0, 1, 3):
+        out = np.empty((h, w, 3), np.uint8)
+        capi.check(capi.lib().rptb_film_resolve(sums.ctypes.data_as(capi.c_double_p), nb, w, h, radius, 0,
+                                                out.ctypes.data_as(capi.c_u8_p)), "rptb_film_resolve")
+        ref = orc.film_resolve(sums, nb, w, h, radius)
+        assert (np.abs(out.astype(int) - ref.astype(int)) <= 1).all()
+        assert (out == ref).mean() > 0.999  # pow() may differ in the last ulp before the truncating cast
+
+
+# ------------------------------------------------------------ host API end to end ---------
+def test_renderer_render_and_iterative_render(gpu_ok):
+    cfg = scenes.sphere_scene()
+    r = api.Renderer(cfg.scene, cfg.camera).width(64).height(36).max_bounces(2).num_samples(10).seed(1)
+    img = r.render()
+    assert img.shape == (36, 64, 3) and img.dtype == np.uint8 and img.max() > 50
+    calls = []
+    r2 = api.Renderer(cfg.scene, cfg.camera).width(64).height(36).max_bounces(2).num_samples(10).seed(1) \
+        .filter(api.Filter.Box(1))
+    r2.iterative_render(4, lambda it, buf: calls.append((it, len(buf.batches), buf.variance() if len(buf.batches) > 1 else None)))
+    assert [c[0] for c in calls] == [4, 8, 10] and [c[1] for c in calls] == [1, 2, 3]  # last batch is shorter (:110)
+    assert calls[-1][2] > 0
+    r.close()
+    r2.close()
+
+
+def test_gpu_error_statuses(cfgs):
+    cfg, flat, ds = cfgs("sphere")
+    lib = capi.lib()
+    r = api.Renderer(cfg.scene, cfg.camera).width(8).height(8)
+    cam = cfg.camera.to_c()
+    out = np.empty((64, 3))
+    for bad, needle in ((dict(iterations=0), b"iterations"), (dict(max_bounces=65), b"max_bounces"),
+                        (dict(shard=(2, 2)), b"shard")):
+        p = r.params(bad.get("iterations", 1), 0, *bad.get("shard", (0, 1)))
+        if "max_bounces" in bad:
+            p.max_bounces = bad["max_bounces"]
+        rc = lib.rptb_render_samples(ds.handle, C.byref(cam), C.byref(p), out.ctypes.data_as(capi.c_double_p), None)
+        assert rc < 0 and needle in lib.rptb_last_error()
+    # a plane cannot be a light (Plane::sample is unimplemented!() in the reference)
+    sc = api.Scene()
+    sc.add(api.Light.Object(api.Object(api.plane(api.vec3(0, 1, 0), 0.0))))
+    f2 = api.FlatScene(sc)
+    hnd = C.c_void_p()
+    assert lib.rptb_scene_create(C.byref(f2.desc), 0, C.byref(hnd)) == -5

@@ -1,0 +1,141 @@
+"""CPU tests of the host mirror of rpt's API (rpt_b200/api.py): builder semantics,
+transform composition, camera construction, OBJ parsing, scene flattening."""
+import io
+import math
+
+import numpy as np
+
+from rpt_b200 import api, scenes
+from rpt_b200 import _capi as capi
+from rpt_b200.distributed import tile_owner
+
+
+def test_renderer_defaults_and_builder():
+    r = api.Renderer(api.Scene(), api.Camera.default())
+    assert (r._width, r._height, r._exposure_value, r._max_bounces, r._num_samples) == (800, 600, 0.0, 0, 1)
+    assert r._filter.radius == 0  # src/renderer.rs:46-57
+    r2 = r.width(10).height(20).max_bounces(3).num_samples(7).exposure_value(1.5).filter(api.Filter.Box(2))
+    assert r2 is r and (r._width, r._height, r._max_bounces, r._num_samples) == (10, 20, 3, 7)
+    p = r.params(5, first_sample=11, shard_index=1, shard_count=4)
+    assert (p.width, p.height, p.iterations, p.max_bounces, p.first_sample, p.shard_index, p.shard_count) == \
+        (10, 20, 5, 3, 11, 1, 4)
+
+
+def test_camera_default_look_at_focus():
+    c = api.Camera.default()
+    np.testing.assert_array_equal(c.eye, [0, 0, 10])
+    np.testing.assert_array_equal(c.direction, [0, 0, -1])
+    assert c.fov == math.pi / 6 and c.aperture == 0 and c.focal_distance == 0
+    c = api.Camera.look_at(api.vec3(-2.5, 4.0, 6.5), api.vec3(0, -0.25, 0), api.vec3(0, 1, 0), math.pi / 4)
+    assert abs(np.linalg.norm(c.direction) - 1) < 1e-15 and abs(np.linalg.norm(c.up) - 1) < 1e-15
+    assert abs(np.dot(c.direction, c.up)) < 1e-15  # up re-orthogonalised (src/camera.rs:45)
+    c2 = c.focus(api.vec3(0, 0, 0), 0.1)
+    assert c2 is c and c.aperture == 0.1
+    np.testing.assert_allclose(c.focal_distance, np.dot(-c.eye, c.direction))
+
+
+def test_transform_chaining_composes_left_to_right():
+    """cube().scale(s).rotate_y(a).translate(t) == T * R * S (src/shape.rs:234-284)."""
+    s, a, t = api.vec3(165, 330, 165), 2 * math.pi * (-253 / 360), api.vec3(368, 165, 351)
+    tr = api.cube().scale(s).rotate_y(a).translate(t)
+    assert isinstance(tr, api.Transformed) and isinstance(tr.shape, api.Cube)
+    S = np.diag([165, 330, 165, 1.0])
+    c, sn = math.cos(a), math.sin(a)
+    R = np.array([[c, 0, sn, 0], [0, 1, 0, 0], [-sn, 0, c, 0], [0, 0, 0, 1.0]])
+    T = np.eye(4)
+    T[:3, 3] = t
+    np.testing.assert_allclose(tr.matrix, T @ R @ S, atol=1e-12)
+    # a point on the cube's top face centre goes to (368, 330, 351)
+    np.testing.assert_allclose(tr.matrix @ np.array([0, 0.5, 0, 1.0]), [368, 330, 351, 1], atol=1e-9)
+    # rotate about an arbitrary axis normalises the axis (glm::rotate)
+    r1 = api.sphere().rotate(0.3, api.vec3(0, 2, 0)).matrix
+    r2 = api.sphere().rotate_y(0.3).matrix
+    np.testing.assert_allclose(r1, r2, atol=1e-15)
+
+
+def test_materials_constructors():
+    d = api.Material.diffuse(api.vec3(1, 1, 1))
+    assert (d.index, d.roughness, d.metallic, d.emittance, d.transparent) == (1.5, 1.0, 0.0, 0.0, False)
+    c = api.Material.clear(1.33, 0.01)
+    assert c.transparent and c.index == 1.33 and (c.color == 1).all()
+    m = api.Material.metallic_(api.vec3(1, 0, 0), 0.4)
+    assert m.metallic == 1.0 and m.index == 1.5
+    li = api.Material.light(api.vec3(1, 1, 1), 40.0)
+    assert li.index == 1.0 and li.roughness == 1.0 and li.emittance == 40.0
+    df = api.Material.default()
+    np.testing.assert_allclose(df.color, api.hex_color(0xFF0000))
+    assert df.roughness == 0.5
+
+
+def test_parse_obj_fan_normals_negative_indices():
+    obj = """
+# comment
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+vn 0 0 1
+vt 0.5 0.5
+usemtl foo
+f 1 2 3 4
+f 1//1 2//1 3//1
+f -4 -3 -2
+"""
+    tris = api.parse_obj(io.StringIO(obj))
+    assert tris.shape == (4, 18)  # quad -> 2 (fan), + 2
+    np.testing.assert_array_equal(tris[0, :9], [0, 0, 0, 1, 0, 0, 1, 1, 0])
+    np.testing.assert_array_equal(tris[1, :9], [0, 0, 0, 1, 1, 0, 0, 1, 0])
+    np.testing.assert_array_equal(tris[2, 9:], [0, 0, 1] * 3)  # explicit normals
+    np.testing.assert_array_equal(tris[3, :9], tris[0, :9])  # negative indices
+    np.testing.assert_allclose(tris[0, 9:12], [0, 0, 1])  # inferred normal
+
+
+def test_teapot_asset_is_the_reference_mesh():
+    t = scenes.teapot_triangles()
+    assert t.shape == (2256, 18)  # SURVEY [probe]: teapot.obj has 2256 triangles
+    assert np.isfinite(t).all()
+
+
+def test_flatten_cornell():
+    cfg = scenes.cornell_scene()
+    flat = api.FlatScene(cfg.scene)
+    d = flat.desc
+    assert (d.nobjects, d.nlights, d.nmeshes) == (7, 1, 6)
+    kinds = [flat.objects[i].kind for i in range(7)]
+    assert kinds == [capi.SHAPE_MESH] * 5 + [capi.SHAPE_CUBE] * 2
+    assert [flat.objects[i].has_transform for i in range(7)] == [0] * 5 + [1] * 2
+    assert flat.lights[0].kind == capi.LIGHT_OBJECT and flat.lights[0].object.kind == capi.SHAPE_MESH
+    lm = flat.materials[flat.lights[0].object.material]
+    assert lm.emittance == 100.0
+    assert flat.meshes[0].ntris == 2 and flat.meshes[0].nnodes == 1
+    # column-major transform: translation in elements 12..14
+    assert list(flat.objects[5].transform)[12:15] == [368.0, 165.0, 351.0]
+    assert flat.host_bytes() > 0
+
+
+def test_tile_owner_partition():
+    for (w, h, n) in [(800, 800, 8), (37, 19, 3), (16, 8, 2), (1, 1, 4)]:
+        own = tile_owner(w, h, n)
+        assert own.shape == (h, w) and own.min() >= 0 and own.max() < n
+        tiles_x = (w + 15) // 16
+        assert own[0, 0] == 0
+        if w > 16:
+            assert own[0, 16] == 1 % n
+        if h > 8:
+            assert own[8, 0] == tiles_x % n
+    own = tile_owner(1920, 1080, 8)
+    frac = np.bincount(own.ravel(), minlength=8) / own.size
+    assert np.abs(frac - 1 / 8).max() < 0.01  # interleaving balances the shards
+
+
+def test_dragon_proxy_is_closed_and_outward():
+    tris = scenes.dragon_proxy(120, 30)
+    assert tris.shape == (120 * 30 * 2, 18)
+    v1, v2, v3 = tris[:, 0:3], tris[:, 3:6], tris[:, 6:9]
+    fn = np.cross(v2 - v1, v3 - v1)
+    nn = tris[:, 9:12]
+    assert ((fn * nn).sum(1) > 0).mean() > 0.999  # vertex normals agree with the winding
+    # outward: signed volume positive
+    vol = (v1 * np.cross(v2, v3)).sum(1).sum() / 6.0
+    assert vol > 0
+    assert abs(tris[:, [1, 4, 7]].min() * 3.4 + 1.0) < 1e-9  # rests on the plane y = -1 after scale 3.4

@@ -1,0 +1,110 @@
+"""Helpers shared by the tests: an independent numpy restatement of the BSDF / pdf
+formulas (second implementation, used to validate the oracle), ray generators, and
+image-comparison metrics."""
+import math
+
+import numpy as np
+
+
+def normalize(v):
+    v = np.asarray(v, dtype=np.float64)
+    return v / np.linalg.norm(v, axis=-1, keepdims=True)
+
+
+def random_unit(rng, n):
+    return normalize(rng.normal(size=(n, 3)))
+
+
+# ---- independent restatement of src/material.rs:125-210 (vectorised over wi) -------------
+def bsdf_ref(color, index, roughness, metallic, transparent, n, wo, wi):
+    color = np.asarray(color, dtype=np.float64)
+    n, wo, wi = (np.asarray(a, dtype=np.float64) for a in (n, wo, wi))
+    ndwi = (n * wi).sum(-1)
+    ndwo = (n * wo).sum(-1)
+    wi_out = ~np.signbit(ndwi)
+    wo_out = ~np.signbit(ndwo)
+    m2 = roughness * roughness
+    f0s = ((index - 1.0) / (index + 1.0)) ** 2
+    f0 = f0s * (1.0 - metallic) + color * metallic
+    out = np.zeros(wi.shape)
+    with np.errstate(all="ignore"):
+        # same side
+        h = normalize(wi + wo)
+        wodh = (wo * h).sum(-1)
+        ndh = (n * h).sum(-1)
+        nh2 = ndh**2
+        d = np.exp((nh2 - 1.0) / (m2 * nh2)) / (m2 * math.pi * nh2 * nh2)
+        tir = (~wi_out) & (np.sqrt(1.0 - wodh * wodh) * index > 1.0)
+        f = f0[None, :] + (1.0 - f0[None, :]) * ((1.0 - wodh) ** 5)[:, None]
+        f = np.where(tir[:, None], 1.0, f)
+        g = np.minimum(1.0, 2.0 * np.minimum(ndwi * ndh, ndwo * ndh) / wodh)
+        spec = d[:, None] * f * g[:, None] / (4.0 * ndwo * ndwi)[:, None]
+        same = spec if transparent else spec + (1.0 - f) * color[None, :] / math.pi
+        # opposite sides
+        eta = np.where(wo_out, index, 1.0 / index)
+        h2 = normalize(wi * eta[:, None] + wo)
+        widh = (wi * h2).sum(-1)
+        wodh2 = (wo * h2).sum(-1)
+        ndh2 = (n * h2).sum(-1)
+        nh22 = ndh2**2
+        d2 = np.exp((nh22 - 1.0) / (m2 * nh22)) / (m2 * math.pi * nh22 * nh22)
+        f2 = f0[None, :] + (1.0 - f0[None, :]) * ((1.0 - np.abs(widh)) ** 5)[:, None]
+        g2 = np.minimum(1.0, 2.0 * np.minimum(np.abs(ndwi * ndh2), np.abs(ndwo * ndh2)) / np.abs(wodh2))
+        btdf = (np.abs(widh * wodh2 / (ndwi * ndwo)) * d2 * g2 / (eta * widh + wodh2) ** 2)[:, None] * (1.0 - f2)
+        opp = btdf * color[None, :]
+    side = wi_out == wo_out
+    out = np.where(side[:, None], same, opp)
+    if not transparent:
+        out = np.where((wi_out & wo_out)[:, None], out, 0.0)
+    return out
+
+
+# ---- independent restatement of the pdf of src/material.rs:290-312 ------------------------
+def pdf_ref(color, index, roughness, metallic, transparent, n, wo, wi):
+    color = np.asarray(color, dtype=np.float64)
+    n, wo, wi = (np.asarray(a, dtype=np.float64) for a in (n, wo, wi))
+    m2 = roughness * roughness
+    f0 = ((index - 1.0) / (index + 1.0)) ** 2
+    f = 0.8 * ((1.0 - metallic) * f0 + metallic * color.mean()) + 0.2
+    wodn = (wo * n).sum(-1)
+    eta = np.where(wodn > 0.0, index, 1.0 / index)
+
+    def p_h(h):
+        c = np.abs((h * n).sum(-1))
+        s = np.sqrt(1.0 - c * c)
+        return np.exp(-((s / c) ** 2) / m2) / (math.pi * m2 * c**3)
+
+    with np.errstate(all="ignore"):
+        h = normalize(wi + wo)
+        p = f * p_h(h) / (4.0 * np.abs((h * wo).sum(-1)))
+        widn = (wi * n).sum(-1)
+        if not transparent:
+            p = p + (1.0 - f) * np.maximum(widn, 0.0) / math.pi
+        else:
+            h2 = normalize(wi * eta[:, None] + wo)
+            hwo = (h2 * wo).sum(-1)
+            hwi = (h2 * wi).sum(-1)
+            t = (1.0 - f) * p_h(h2) * np.abs(hwo) / (eta * hwi + hwo) ** 2
+            p = p + np.where(np.signbit(wodn) != np.signbit(widn), t, 0.0)
+    return p
+
+
+def camera_rays(camera, n, rng, spread=0.7, jitter=0.0):
+    """Rays from the camera eye fanned over the field of view (mostly hitting the scene)."""
+    right = np.cross(camera.direction, camera.up)
+    right = right / np.linalg.norm(right)
+    d = (camera.direction[None, :] / math.tan(camera.fov / 2.0) + rng.uniform(-1, 1, (n, 1)) * right[None, :]
+         + rng.uniform(-spread, spread, (n, 1)) * camera.up[None, :])
+    d = normalize(d)
+    o = np.tile(camera.eye, (n, 1)) + rng.normal(0.0, jitter, (n, 3))
+    return np.concatenate([o, d], axis=1)
+
+
+def interior_rays(lo, hi, n, rng):
+    """Random rays starting inside a box -- exercises inside hits and all directions."""
+    o = rng.uniform(lo, hi, (n, 3))
+    return np.concatenate([o, random_unit(rng, n)], axis=1)
+
+
+def rmse(a, b):
+    return float(np.sqrt(np.mean((np.asarray(a) - np.asarray(b)) ** 2)))
