@@ -16,9 +16,11 @@ all: lib oracle
 lib: $(LIB)
 oracle: $(ORACLE)
 
+# the f32 product path: SFU approximations for divide/sqrt/exp/log (|rel err| ~ 1e-6, far
+# inside the f32 parity tolerance), denormals flushed
 $(OBJDIR)/kernels_f32.o: $(CSRC)/kernels_f32.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/kernels_f32.ptxas.log || (cat $(OBJDIR)/kernels_f32.ptxas.log; false)
+	$(NVCC) $(NVFLAGS) --use_fast_math -c $< -o $@ 2> $(OBJDIR)/kernels_f32.ptxas.log || (cat $(OBJDIR)/kernels_f32.ptxas.log; false)
 # the parity gate keeps products and sums separately rounded, like the reference's f64 code
 $(OBJDIR)/kernels_f64.o: $(CSRC)/kernels_f64.cu $(HDRS)
 	@mkdir -p $(OBJDIR)

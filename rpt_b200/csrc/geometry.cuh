@@ -197,12 +197,6 @@ RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, 
 }
 
 // ------------------------------------------------------------ kd traversal -----
-template <class R>
-RPTB_D void node_fields(const KdNodeDev& n, R& split, uint32_t& word, uint32_t& first_ref) {
-    split = n.split;
-    word = n.word;
-    first_ref = n.first_ref;
-}
 RPTB_D KdNodeDev load_node(const KdNodeDev* p) {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
     KdNodeDev n;
@@ -217,9 +211,25 @@ RPTB_D uint32_t node_first_ref(const KdNodeDev& n) { return n.first_ref; }
 RPTB_D uint32_t node_first_ref(const KdNodeDev64& n) { return n.first_ref; }
 
 // KdTree::intersect.  `o`,`d` are in the mesh's local space (d not normalised, so
-// t is the world t).  Returns true if some triangle tightened h.t.
-template <class R, bool ANY, bool STATS>
-RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, Hit<R>& h, TravStats& ts) {
+// t is the world t).  Returns true if some triangle tightened h.t.  `any` = shadow
+// query: return at the first leaf that produced a hit.
+template <class R, bool STATS>
+RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
+    if (!M<R>::literal && m.root_is_leaf) {
+        // f32 only (the f64 gate keeps the reference's control flow).  A tree that is one leaf (e.g. every `polygon` of the Cornell box): the root cull
+        // of kdtree.rs:130-134 can only prune, never change the hit, so all lanes test the
+        // few triangles directly -- no divergent slab test.
+        bool hit = false;
+        if (STATS) ts.node_visits++;
+        for (uint32_t tri = 0; tri < m.ntris; tri++) {
+            if (STATS) ts.tri_tests++;
+            if (tri_intersect(m, tri, o, d, tmin, h.t, h.bv, h.bw)) {
+                h.aux = tri;
+                hit = true;
+            }
+        }
+        return hit;
+    }
     // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
     R lo, hi;
     Vec3<R> inv;
@@ -246,7 +256,7 @@ RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, Hit<
     R st_lo[KD_STACK], st_hi[KD_STACK];
     int sp = 0;
     uint32_t node = 0;
-    bool any = false;
+    bool hit = false;
 
     while (true) {
         auto nd = load_node(m.nodes + node);
@@ -286,14 +296,14 @@ RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, Hit<
                 if (STATS) ts.tri_tests++;
                 if (tri_intersect(m, tri, o, d, tmin, h.t, h.bv, h.bw)) {
                     h.aux = tri;
-                    any = true;
+                    hit = true;
                 }
             }
         }
-        if (ANY && any) return true;
+        if (any && hit) return true;
         // pop; skip far cells that start beyond the hit found so far (kdtree.rs:212-213)
         while (true) {
-            if (sp == 0) return any;
+            if (sp == 0) return hit;
             sp--;
             node = st_node[sp];
             lo = st_lo[sp];
@@ -304,9 +314,9 @@ RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, Hit<
 }
 
 // ------------------------------------------------------- object dispatch ------
-template <class R, bool ANY, bool STATS>
-RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> o, Vec3<R> d, R tmin, Hit<R>& h,
-                             TravStats& ts) {
+template <class R, bool STATS>
+RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> o, Vec3<R> d, R tmin, bool any,
+                             Hit<R>& h, TravStats& ts) {
     if (ob.has_transform) {  // Ray::apply_transform(inverse_transform)
         const Vec3<R> lo = xform_point(ob.inv, o);
         const Vec3<R> ld = xform_dir(ob.inv, d);
@@ -317,7 +327,7 @@ RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec
         case SHAPE_SPHERE: return sphere_intersect(o, d, tmin, h.t);
         case SHAPE_PLANE: return plane_intersect(ob.plane_n, ob.plane_v, o, d, tmin, h.t);
         case SHAPE_CUBE: return cube_intersect(o, d, tmin, h.t, h.aux);
-        default: return kd_intersect<R, ANY, STATS>(sv.meshes[ob.mesh], o, d, tmin, h, ts);
+        default: return kd_intersect<R, STATS>(sv.meshes[ob.mesh], o, d, tmin, any, h, ts);
     }
 }
 

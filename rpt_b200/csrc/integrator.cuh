@@ -53,19 +53,20 @@ struct PathCounters {
     TravStats ts;
 };
 
-// get_closest_hit: linear scan of scene.objects.  ANY = shadow query (first hit with
-// t < h.t ends the scan; the caller preloads h.t with the light distance).
-template <class R, bool ANY, bool STATS>
-RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, Hit<R>& h, TravStats& ts) {
+// get_closest_hit: linear scan of scene.objects.  `any` = shadow query (the first
+// object with a hit at t < h.t ends the scan; the caller preloads h.t with the light
+// distance).
+template <class R, bool STATS>
+RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
     h.obj = -1;
     h.aux = 0;
     h.bv = h.bw = (R)0;
     const uint32_t n = sv.nobjects;
     for (uint32_t i = 0; i < n; i++) {
         if (STATS) ts.object_tests++;
-        if (object_intersect<R, ANY, STATS>(sv, sv.objects[i], o, d, tmin, h, ts)) {
+        if (object_intersect<R, STATS>(sv, sv.objects[i], o, d, tmin, any, h, ts)) {
             h.obj = (int)i;
-            if (ANY) return;
+            if (any) return;
         }
     }
 }
@@ -83,6 +84,15 @@ RPTB_D Vec3<double> offset_origin(Vec3<double> p, Vec3<double>, Vec3<double>, do
 template <class R>
 RPTB_D R max_abs3(Vec3<R> a) { return M<R>::max(M<R>::max(M<R>::abs(a.x), M<R>::abs(a.y)), M<R>::abs(a.z)); }
 
+// Per-lane phases of the flattened trace_ray recursion.  One loop iteration = one ray
+// through the single closest_hit call site, whatever the ray is for.
+enum : int {
+    PH_NEW = 0,     // needs a camera ray (start of get_color's next sample)
+    PH_LIGHTS = 1,  // at a surface: walking scene.lights (sample_lights)
+    PH_BOUNCE = 2,  // at a surface: lights done, try Material::sample_f
+    PH_FINISH = 3   // path ended with radiance Lterm: unwind the per-level clamps
+};
+
 template <class R, int MAXD, bool STATS>
 __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
     const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
@@ -92,32 +102,100 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
     const uint32_t y = ty * TILE_H + (warp >> 1) * 4u + (lane >> 3);
     if (x >= a.width || y >= a.height) return;
     const uint32_t pix = y * a.width + x;
+    // The lanes of this warp that own a pixel.  They stay together until all of them have
+    // finished their samples, and re-converge explicitly before every trace (independent
+    // thread scheduling gives no such guarantee by itself).
+    const unsigned wmask = __activemask();
 
     const R tmin = (R)1e-12;  // EPSILON, renderer.rs:14
     const R dim = (R)max(a.width, a.height);
     const R xn = ((R)(2u * x + 1u) - (R)a.width) / dim;
     const R yn = ((R)(2u * (a.height - y) - 1u) - (R)a.height) / dim;
-    const Vec3<R> eye = {a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]};
-    const Vec3<R> cdir = {a.cam.direction[0], a.cam.direction[1], a.cam.direction[2]};
-    const Vec3<R> cup = {a.cam.up[0], a.cam.up[1], a.cam.up[2]};
-    const Vec3<R> cright = {a.cam.right[0], a.cam.right[1], a.cam.right[2]};
 
     PathCounters pc = {0, 0, 0, 0, {0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     Level<R> stack[MAXD];
     Rng<R> rng;
-    Vec3<R> ro = eye, rd = cdir;
+    rng.p.init(a.seed, pix, a.first_sample);
+
+    // current ray
+    Vec3<R> ro = {(R)0, (R)0, (R)0}, rd = {(R)0, (R)0, (R)1};
+    R tmax = M<R>::inf();
+    bool shadow = false;
+    // surface context of the vertex being shaded (valid in PH_LIGHTS / PH_BOUNCE)
+    Vec3<R> pos = ro, n = rd, ng = rd, wo = rd;
+    Vec3<R> color = {(R)0, (R)0, (R)0};    // Le + direct light gathered so far at this vertex
+    Vec3<R> contrib = {(R)0, (R)0, (R)0};  // f (.) I (wi.n) of the light sample whose shadow ray is in flight
+    Vec3<R> Lterm = {(R)0, (R)0, (R)0};
+    R err_scale = (R)0;
+    uint32_t mat_id = 0, li = 0;
+    bool dead = false;
     uint32_t s = 0;
     int depth = 0;
-    bool fresh = true;
+    int phase = PH_NEW;
+    bool idle = false;  // all samples of this pixel are done; waiting for the rest of the warp
 
     while (true) {
-        if (fresh) {
-            if (s >= a.iterations) break;
+        // ================= A. decide the next ray of this lane =======================
+        Vec3<R> wi = rd;
+        R pdf = (R)1;
+        Vec3<R> intensity = {(R)0, (R)0, (R)0};
+        R dist = M<R>::inf();
+        bool need_f = false;
+
+        if (phase == PH_LIGHTS) {  // sample_lights: next light that needs a shadow ray
+            const MaterialRec<R> mat = sv.materials[mat_id];
+            while (li < sv.nlights) {
+                const LightRec<R>& l = sv.lights[li];
+                li++;
+                if (l.kind == LIGHT_AMBIENT) {
+                    color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
+                    continue;
+                }
+                if (dead) continue;
+                illuminate(sv, l, pos, rng, intensity, wi, dist);
+                if (!M<R>::literal) {
+                    // provably zero contribution: no shadow ray (the draws above are still consumed)
+                    const bool zero_i = intensity.x == (R)0 && intensity.y == (R)0 && intensity.z == (R)0;
+                    if (zero_i || (!mat.transparent && M<R>::signbit(dot(n, wi)))) continue;
+                }
+                need_f = true;
+                break;
+            }
+            if (!need_f) phase = PH_BOUNCE;
+        }
+        if (phase == PH_BOUNCE) {
+            bool bounce = false;
+            if ((uint32_t)depth < a.max_bounces && !dead) {
+                const MaterialRec<R> mat = sv.materials[mat_id];
+                bounce = sample_f(mat, n, wo, rng, wi, pdf);
+            }
+            if (bounce) {
+                need_f = true;
+            } else {
+                Lterm = color;
+                phase = PH_FINISH;
+            }
+        }
+        if (phase == PH_FINISH) {
+            Vec3<R> L = Lterm;
+            for (int k = depth - 1; k >= 0; k--) L = unwind(stack[k], L);
+            acc0 += (double)L.x;
+            acc1 += (double)L.y;
+            acc2 += (double)L.z;
+            s++;
+            phase = PH_NEW;
+        }
+        if (phase == PH_NEW && s >= a.iterations) idle = true;
+        if (phase == PH_NEW && !idle) {
             rng.p.init(a.seed, pix, a.first_sample + s);
             const R dx = gen_range(rng, (R)-1 / dim, (R)1 / dim);
             const R dy = gen_range(rng, (R)-1 / dim, (R)1 / dim);
-            // Camera::cast_ray
+            // Camera::cast_ray (camera.rs:64-81)
+            const Vec3<R> eye = {a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]};
+            const Vec3<R> cdir = {a.cam.direction[0], a.cam.direction[1], a.cam.direction[2]};
+            const Vec3<R> cup = {a.cam.up[0], a.cam.up[1], a.cam.up[2]};
+            const Vec3<R> cright = {a.cam.right[0], a.cam.right[1], a.cam.right[2]};
             const R cx = xn + dx, cy = yn + dy;
             Vec3<R> origin = eye;
             Vec3<R> new_dir = a.cam.d * cdir + cx * cright + cy * cup;
@@ -130,96 +208,77 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
             }
             ro = origin;
             rd = M<R>::normalize(new_dir);
+            tmax = M<R>::inf();
+            shadow = false;
             depth = 0;
-            fresh = false;
+        }
+        if (need_f) {  // the one Material::bsdf site: light sample or bounce direction
+            const MaterialRec<R> mat = sv.materials[mat_id];
+            const Vec3<R> f = bsdf(mat, n, wo, wi);
+            if (phase == PH_LIGHTS) {
+                contrib = cmul(f, intensity) * dot(wi, n);  // renderer.rs:198-199 (signed cosine)
+                shadow = true;
+                tmax = M<R>::next_up(dist);  // occluded iff some hit has t <= dist (renderer.rs:197)
+            } else {  // PH_BOUNCE: renderer.rs:157-164
+                const R abscos = M<R>::abs(dot(wi, n));
+                Level<R>& lv = stack[depth];
+                lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
+                if constexpr (M<R>::literal) {
+                    lv.f[0] = f.x; lv.f[1] = f.y; lv.f[2] = f.z;
+                    lv.inv_pdf = (R)1 / pdf;
+                    lv.abscos = abscos;
+                } else {
+                    const R k = abscos / pdf;
+                    lv.w[0] = f.x * k; lv.w[1] = f.y * k; lv.w[2] = f.z * k;
+                }
+                depth++;
+                shadow = false;
+                tmax = M<R>::inf();
+            }
+            ro = offset_origin(pos, ng, wi, err_scale);
+            rd = wi;
         }
 
-        // ---- one trace_ray invocation ------------------------------------------
-        pc.segments++;
-        pc.rays++;
+        // ================= B. the single get_closest_hit site ========================
+        if (__all_sync(wmask, idle)) break;  // also the re-convergence point of the warp
         Hit<R> h;
-        h.t = M<R>::inf();
-        closest_hit<R, false, STATS>(sv, ro, rd, tmin, h, pc.ts);
-
-        Vec3<R> L;
-        bool done;
-        if (h.obj < 0) {
-            if (sv.env.kind != 0) pc.env_lookups++;
-            L = env_color(sv.env, rd);
-            done = true;
-        } else {
-            const ObjectRec<R>& ob = sv.objects[h.obj];
-            const Surface<R> sf = finalize_hit(sv, ob, ro, rd, h);
-            if (sf.on_mesh) pc.mesh_hits++;
-            const Vec3<R> pos = ro + h.t * rd;
-            const MaterialRec<R> mat = sv.materials[ob.material];
-            const Vec3<R> wo = -M<R>::normalize(rd);
-            const Vec3<R> n = sf.n;
-            const R err_scale = M<R>::literal ? (R)0 : M<R>::max(max_abs3(pos), max_abs3(ro));
-            Vec3<R> color = mat.emittance * mat_color(mat);
-            // opaque surface seen from its back: bsdf == 0 for every wi (material.rs:130-133),
-            // so neither the lights nor the bounce can contribute.
-            const bool dead = !M<R>::literal && !mat.transparent && M<R>::signbit(dot(n, wo));
-
-            // sample_lights
-            for (uint32_t li = 0; li < sv.nlights; li++) {
-                const LightRec<R>& l = sv.lights[li];
-                if (l.kind == LIGHT_AMBIENT) {
-                    color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
-                    continue;
-                }
-                if (dead) continue;
-                Vec3<R> intensity, wi;
-                R dist;
-                illuminate(sv, l, pos, rng, intensity, wi, dist);
-                if (!M<R>::literal) {
-                    // provably zero contribution: skip the shadow ray (the draws above are still consumed)
-                    const bool zero_i = intensity.x == (R)0 && intensity.y == (R)0 && intensity.z == (R)0;
-                    if (zero_i || (!mat.transparent && M<R>::signbit(dot(n, wi)))) continue;
-                }
-                pc.rays++;
-                Hit<R> sh;
-                sh.t = M<R>::next_up(dist);  // occluded iff some hit has t <= dist (renderer.rs:197)
-                closest_hit<R, true, STATS>(sv, offset_origin(pos, sf.ng, wi, err_scale), wi, tmin, sh, pc.ts);
-                if (sh.obj < 0) {
-                    const Vec3<R> f = bsdf(mat, n, wo, wi);
-                    color = color + cmul(f, intensity) * dot(wi, n);
-                }
-            }
-
-            done = true;
-            L = color;
-            if ((uint32_t)depth < a.max_bounces && !dead) {
-                Vec3<R> wi;
-                R pdf;
-                if (sample_f(mat, n, wo, rng, wi, pdf)) {
-                    const Vec3<R> f = bsdf(mat, n, wo, wi);
-                    const R abscos = M<R>::abs(dot(wi, n));
-                    Level<R>& lv = stack[depth];
-                    lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
-                    if constexpr (M<R>::literal) {
-                        lv.f[0] = f.x; lv.f[1] = f.y; lv.f[2] = f.z;
-                        lv.inv_pdf = (R)1 / pdf;
-                        lv.abscos = abscos;
-                    } else {
-                        const R k = abscos / pdf;
-                        lv.w[0] = f.x * k; lv.w[1] = f.y * k; lv.w[2] = f.z * k;
-                    }
-                    ro = offset_origin(pos, sf.ng, wi, err_scale);
-                    rd = wi;
-                    depth++;
-                    done = false;
-                }
-            }
+        h.t = tmax;
+        h.obj = -1;
+        if (!idle) {
+            pc.rays++;
+            closest_hit<R, STATS>(sv, ro, rd, tmin, shadow, h, pc.ts);
         }
 
-        if (done) {
-            for (int k = depth - 1; k >= 0; k--) L = unwind(stack[k], L);
-            acc0 += (double)L.x;
-            acc1 += (double)L.y;
-            acc2 += (double)L.z;
-            s++;
-            fresh = true;
+        // ================= C. consume the answer ====================================
+        if (idle) {
+            // nothing: this lane only keeps the warp's trace site convergent
+        } else if (shadow) {
+            if (h.obj < 0) color = color + contrib;
+            // phase stays PH_LIGHTS: the walk resumes at light `li`
+        } else {
+            pc.segments++;  // one trace_ray invocation
+            if (h.obj < 0) {
+                if (sv.env.kind != 0) pc.env_lookups++;
+                Lterm = env_color(sv.env, rd);
+                phase = PH_FINISH;
+            } else {
+                const ObjectRec<R>& ob = sv.objects[h.obj];
+                const Surface<R> sf = finalize_hit(sv, ob, ro, rd, h);
+                if (sf.on_mesh) pc.mesh_hits++;
+                pos = ro + h.t * rd;
+                n = sf.n;
+                ng = sf.ng;
+                wo = -M<R>::normalize(rd);
+                mat_id = ob.material;
+                const MaterialRec<R> mat = sv.materials[mat_id];
+                err_scale = M<R>::literal ? (R)0 : M<R>::max(max_abs3(pos), max_abs3(ro));
+                color = mat.emittance * mat_color(mat);
+                // opaque surface seen from its back: bsdf == 0 for every wi (material.rs:130-133),
+                // so neither the lights nor the bounce can contribute (f32 only; f64 stays literal)
+                dead = !M<R>::literal && !mat.transparent && M<R>::signbit(dot(n, wo));
+                li = 0;
+                phase = PH_LIGHTS;
+            }
         }
     }
 
@@ -238,7 +297,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
         // node/tri counters can exceed 2^32 per warp on long renders: reduce in two halves
         const uint32_t n_lo = __reduce_add_sync(m, pc.ts.node_visits & 0xFFFFu), n_hi = __reduce_add_sync(m, pc.ts.node_visits >> 16);
         const uint32_t t_lo = __reduce_add_sync(m, pc.ts.tri_tests & 0xFFFFu), t_hi = __reduce_add_sync(m, pc.ts.tri_tests >> 16);
-        const uint32_t o_sum = __reduce_add_sync(m, pc.ts.object_tests);
+        const uint32_t o_lo = __reduce_add_sync(m, pc.ts.object_tests & 0xFFFFu), o_hi = __reduce_add_sync(m, pc.ts.object_tests >> 16);
         if ((int)lane == leader) {
             atomicAdd(&a.counters->segments, (unsigned long long)v0);
             atomicAdd(&a.counters->rays, (unsigned long long)v1);
@@ -247,7 +306,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
             if (STATS) {
                 atomicAdd(&a.counters->node_visits, (unsigned long long)n_lo + ((unsigned long long)n_hi << 16));
                 atomicAdd(&a.counters->tri_tests, (unsigned long long)t_lo + ((unsigned long long)t_hi << 16));
-                atomicAdd(&a.counters->object_tests, (unsigned long long)o_sum);
+                atomicAdd(&a.counters->object_tests, (unsigned long long)o_lo + ((unsigned long long)o_hi << 16));
             }
         }
     }
@@ -274,7 +333,7 @@ __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restri
         const Vec3<R> d = {(R)r[3], (R)r[4], (R)r[5]};
         Hit<R> h;
         h.t = M<R>::inf();
-        closest_hit<R, false, STATS>(sv, o, d, (R)tmin_d, h, ts);
+        closest_hit<R, STATS>(sv, o, d, (R)tmin_d, false, h, ts);
         out_obj[i] = h.obj;
         out_t[i] = h.obj >= 0 ? (double)h.t : (double)INFINITY;
         if (out_n) {

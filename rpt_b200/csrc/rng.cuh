@@ -58,18 +58,38 @@ struct Philox {
         out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
     }
 
-    RPTB_HD uint64_t next_u64() {
-        if (have_spare) {
-            have_spare = false;
-            return (uint64_t)spare_lo | ((uint64_t)spare_hi << 32);
-        }
+    // One Philox block costs ~60 instructions; the integrator draws from ~20 call sites, so
+    // the block function is kept out of line (a pure function of register arguments: one
+    // copy in the instruction cache instead of 20, generator state stays in registers).
+#ifdef __CUDA_ARCH__
+    static __device__ __noinline__ uint4 block_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                    uint32_t k1) {
+        uint32_t o[4];
+        block10(c0, c1, c2, c3, k0, k1, o);
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#endif
+    RPTB_HD uint64_t refill() {
+#ifdef __CUDA_ARCH__
+        const uint4 v = block_call(block, pixel, samp_lo, samp_hi, key0, key1);
+        const uint32_t o[4] = {v.x, v.y, v.z, v.w};
+#else
         uint32_t o[4];
         block10(block, pixel, samp_lo, samp_hi, key0, key1, o);
+#endif
         block++;
         spare_lo = o[2];
         spare_hi = o[3];
         have_spare = true;
         return (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+    }
+
+    RPTB_HD uint64_t next_u64() {
+        if (have_spare) {
+            have_spare = false;
+            return (uint64_t)spare_lo | ((uint64_t)spare_hi << 32);
+        }
+        return refill();
     }
 };
 
