@@ -84,15 +84,21 @@ RPTB_D Vec3<double> offset_origin(Vec3<double> p, Vec3<double>, Vec3<double>, do
 template <class R>
 RPTB_D R max_abs3(Vec3<R> a) { return M<R>::max(M<R>::max(M<R>::abs(a.x), M<R>::abs(a.y)), M<R>::abs(a.z)); }
 
-// Per-lane phases of the flattened trace_ray recursion.  One loop iteration = one ray
-// through the single closest_hit call site, whatever the ray is for.
+// Per-lane status in the flattened trace_ray recursion.
 enum : int {
-    PH_NEW = 0,     // needs a camera ray (start of get_color's next sample)
-    PH_LIGHTS = 1,  // at a surface: walking scene.lights (sample_lights)
-    PH_BOUNCE = 2,  // at a surface: lights done, try Material::sample_f
-    PH_FINISH = 3   // path ended with radiance Lterm: unwind the per-level clamps
+    ST_FRESH = 0,   // needs a camera ray (start of get_color's next sample)
+    ST_VERTEX = 1,  // at a surface: lights are walked in the light slots, the bounce in the segment slot
+    ST_FINISH = 2,  // path ended with radiance Lterm: unwind the per-level clamps at the next segment slot
+    ST_IDLE = 3     // all samples of this pixel are done; waiting for the rest of the warp
 };
 
+// The warp runs a fixed slot schedule: slot j < Ks traces the shadow ray of the j-th
+// sampled (non-ambient) light for every lane standing at a vertex, slot Ks traces the
+// segment rays (Material::sample_f bounces and fresh camera rays).  The slot counter is
+// warp-uniform, so all lanes execute the same shading code in the same iteration and meet
+// at the single get_closest_hit site; a lane with nothing to do in a slot (light sample
+// with provably zero contribution, path just ended) sits that trace out.  Per lane the
+// order of operations -- and of random draws -- is exactly trace_ray's.
 template <class R, int MAXD, bool STATS>
 __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
     const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
@@ -103,8 +109,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
     if (x >= a.width || y >= a.height) return;
     const uint32_t pix = y * a.width + x;
     // The lanes of this warp that own a pixel.  They stay together until all of them have
-    // finished their samples, and re-converge explicitly before every trace (independent
-    // thread scheduling gives no such guarantee by itself).
+    // finished their samples (independent thread scheduling gives no such guarantee).
     const unsigned wmask = __activemask();
 
     const R tmin = (R)1e-12;  // EPSILON, renderer.rs:14
@@ -112,17 +117,19 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
     const R xn = ((R)(2u * x + 1u) - (R)a.width) / dim;
     const R yn = ((R)(2u * (a.height - y) - 1u) - (R)a.height) / dim;
 
+    uint32_t Ks = 0;  // lights that need a shadow ray (warp-uniform)
+    for (uint32_t i = 0; i < sv.nlights; i++) Ks += sv.lights[i].kind != LIGHT_AMBIENT ? 1u : 0u;
+
     PathCounters pc = {0, 0, 0, 0, {0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     Level<R> stack[MAXD];
     Rng<R> rng;
-    rng.p.init(a.seed, pix, a.first_sample);
+    rng.init(a.seed, pix, a.first_sample);
 
     // current ray
     Vec3<R> ro = {(R)0, (R)0, (R)0}, rd = {(R)0, (R)0, (R)1};
     R tmax = M<R>::inf();
-    bool shadow = false;
-    // surface context of the vertex being shaded (valid in PH_LIGHTS / PH_BOUNCE)
+    // surface context of the vertex being shaded (valid in ST_VERTEX)
     Vec3<R> pos = ro, n = rd, ng = rd, wo = rd;
     Vec3<R> color = {(R)0, (R)0, (R)0};    // Le + direct light gathered so far at this vertex
     Vec3<R> contrib = {(R)0, (R)0, (R)0};  // f (.) I (wi.n) of the light sample whose shadow ray is in flight
@@ -132,154 +139,160 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(const SceneView<
     bool dead = false;
     uint32_t s = 0;
     int depth = 0;
-    int phase = PH_NEW;
-    bool idle = false;  // all samples of this pixel are done; waiting for the rest of the warp
+    int status = ST_FRESH;
+    uint32_t slot = Ks;  // every lane starts with a camera ray
 
     while (true) {
-        // ================= A. decide the next ray of this lane =======================
-        Vec3<R> wi = rd;
-        R pdf = (R)1;
-        Vec3<R> intensity = {(R)0, (R)0, (R)0};
-        R dist = M<R>::inf();
-        bool need_f = false;
+        rng.ensure();  // converged here: one Philox block serves all 32 lanes
+        const bool light_slot = slot < Ks;
+        bool active = false;  // this lane sends a ray through the trace site in this slot
 
-        if (phase == PH_LIGHTS) {  // sample_lights: next light that needs a shadow ray
-            const MaterialRec<R> mat = sv.materials[mat_id];
-            while (li < sv.nlights) {
+        if (light_slot) {
+            // ================= sample_lights, one sampled light per slot ==================
+            if (status == ST_VERTEX && !dead) {
+                const MaterialRec<R> mat = sv.materials[mat_id];
+                while (sv.lights[li].kind == LIGHT_AMBIENT) {  // ambient lights listed before it
+                    const LightRec<R>& l = sv.lights[li];
+                    color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
+                    li++;
+                }
                 const LightRec<R>& l = sv.lights[li];
                 li++;
-                if (l.kind == LIGHT_AMBIENT) {
-                    color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
-                    continue;
-                }
-                if (dead) continue;
+                Vec3<R> intensity, wi;
+                R dist;
                 illuminate(sv, l, pos, rng, intensity, wi, dist);
+                bool skip = false;
                 if (!M<R>::literal) {
                     // provably zero contribution: no shadow ray (the draws above are still consumed)
                     const bool zero_i = intensity.x == (R)0 && intensity.y == (R)0 && intensity.z == (R)0;
-                    if (zero_i || (!mat.transparent && M<R>::signbit(dot(n, wi)))) continue;
+                    skip = zero_i || (!mat.transparent && M<R>::signbit(dot(n, wi)));
                 }
-                need_f = true;
-                break;
+                if (!skip) {
+                    const Vec3<R> f = bsdf(mat, n, wo, wi);
+                    contrib = cmul(f, intensity) * dot(wi, n);  // renderer.rs:198-199 (signed cosine)
+                    tmax = M<R>::next_up(dist);  // occluded iff some hit has t <= dist (renderer.rs:197)
+                    ro = offset_origin(pos, ng, wi, err_scale);
+                    rd = wi;
+                    active = true;
+                }
             }
-            if (!need_f) phase = PH_BOUNCE;
-        }
-        if (phase == PH_BOUNCE) {
-            bool bounce = false;
-            if ((uint32_t)depth < a.max_bounces && !dead) {
+        } else {
+            // ================= segment slot: bounce, finish, regenerate ====================
+            if (status == ST_VERTEX) {
                 const MaterialRec<R> mat = sv.materials[mat_id];
-                bounce = sample_f(mat, n, wo, rng, wi, pdf);
-            }
-            if (bounce) {
-                need_f = true;
-            } else {
-                Lterm = color;
-                phase = PH_FINISH;
-            }
-        }
-        if (phase == PH_FINISH) {
-            Vec3<R> L = Lterm;
-            for (int k = depth - 1; k >= 0; k--) L = unwind(stack[k], L);
-            acc0 += (double)L.x;
-            acc1 += (double)L.y;
-            acc2 += (double)L.z;
-            s++;
-            phase = PH_NEW;
-        }
-        if (phase == PH_NEW && s >= a.iterations) idle = true;
-        if (phase == PH_NEW && !idle) {
-            rng.p.init(a.seed, pix, a.first_sample + s);
-            const R dx = gen_range(rng, (R)-1 / dim, (R)1 / dim);
-            const R dy = gen_range(rng, (R)-1 / dim, (R)1 / dim);
-            // Camera::cast_ray (camera.rs:64-81)
-            const Vec3<R> eye = {a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]};
-            const Vec3<R> cdir = {a.cam.direction[0], a.cam.direction[1], a.cam.direction[2]};
-            const Vec3<R> cup = {a.cam.up[0], a.cam.up[1], a.cam.up[2]};
-            const Vec3<R> cright = {a.cam.right[0], a.cam.right[1], a.cam.right[2]};
-            const R cx = xn + dx, cy = yn + dy;
-            Vec3<R> origin = eye;
-            Vec3<R> new_dir = a.cam.d * cdir + cx * cright + cy * cup;
-            if (a.cam.aperture > (R)0) {
-                const Vec3<R> focal_point = origin + M<R>::normalize(new_dir) * a.cam.focal_distance;
-                R ax, ay;
-                unit_disc(rng, ax, ay);
-                origin = origin + (ax * cright + ay * cup) * a.cam.aperture;
-                new_dir = focal_point - origin;
-            }
-            ro = origin;
-            rd = M<R>::normalize(new_dir);
-            tmax = M<R>::inf();
-            shadow = false;
-            depth = 0;
-        }
-        if (need_f) {  // the one Material::bsdf site: light sample or bounce direction
-            const MaterialRec<R> mat = sv.materials[mat_id];
-            const Vec3<R> f = bsdf(mat, n, wo, wi);
-            if (phase == PH_LIGHTS) {
-                contrib = cmul(f, intensity) * dot(wi, n);  // renderer.rs:198-199 (signed cosine)
-                shadow = true;
-                tmax = M<R>::next_up(dist);  // occluded iff some hit has t <= dist (renderer.rs:197)
-            } else {  // PH_BOUNCE: renderer.rs:157-164
-                const R abscos = M<R>::abs(dot(wi, n));
-                Level<R>& lv = stack[depth];
-                lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
-                if constexpr (M<R>::literal) {
-                    lv.f[0] = f.x; lv.f[1] = f.y; lv.f[2] = f.z;
-                    lv.inv_pdf = (R)1 / pdf;
-                    lv.abscos = abscos;
-                } else {
-                    const R k = abscos / pdf;
-                    lv.w[0] = f.x * k; lv.w[1] = f.y * k; lv.w[2] = f.z * k;
+                while (li < sv.nlights) {  // trailing ambient lights (and, for a dead vertex, all of them)
+                    const LightRec<R>& l = sv.lights[li];
+                    if (l.kind == LIGHT_AMBIENT) color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
+                    li++;
                 }
-                depth++;
-                shadow = false;
-                tmax = M<R>::inf();
+                Vec3<R> wi = rd;
+                R pdf = (R)1;
+                bool bounce = false;
+                if ((uint32_t)depth < a.max_bounces && !dead) bounce = sample_f(mat, n, wo, rng, wi, pdf);
+                if (bounce) {  // renderer.rs:157-164
+                    const Vec3<R> f = bsdf(mat, n, wo, wi);
+                    const R abscos = M<R>::abs(dot(wi, n));
+                    Level<R>& lv = stack[depth];
+                    lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
+                    if constexpr (M<R>::literal) {
+                        lv.f[0] = f.x; lv.f[1] = f.y; lv.f[2] = f.z;
+                        lv.inv_pdf = (R)1 / pdf;
+                        lv.abscos = abscos;
+                    } else {
+                        const R k = abscos / pdf;
+                        lv.w[0] = f.x * k; lv.w[1] = f.y * k; lv.w[2] = f.z * k;
+                    }
+                    depth++;
+                    tmax = M<R>::inf();
+                    ro = offset_origin(pos, ng, wi, err_scale);
+                    rd = wi;
+                    active = true;
+                } else {
+                    Lterm = color;
+                    status = ST_FINISH;
+                }
             }
-            ro = offset_origin(pos, ng, wi, err_scale);
-            rd = wi;
+            if (status == ST_FINISH) {
+                Vec3<R> L = Lterm;
+                for (int k = depth - 1; k >= 0; k--) L = unwind(stack[k], L);
+                acc0 += (double)L.x;
+                acc1 += (double)L.y;
+                acc2 += (double)L.z;
+                s++;
+                status = ST_FRESH;
+            }
+            if (status == ST_FRESH) {
+                if (s >= a.iterations) {
+                    status = ST_IDLE;
+                } else {
+                    rng.init(a.seed, pix, a.first_sample + s);
+                    const R dx = gen_range(rng, (R)-1 / dim, (R)1 / dim);
+                    const R dy = gen_range(rng, (R)-1 / dim, (R)1 / dim);
+                    // Camera::cast_ray (camera.rs:64-81)
+                    const Vec3<R> eye = {a.cam.eye[0], a.cam.eye[1], a.cam.eye[2]};
+                    const Vec3<R> cdir = {a.cam.direction[0], a.cam.direction[1], a.cam.direction[2]};
+                    const Vec3<R> cup = {a.cam.up[0], a.cam.up[1], a.cam.up[2]};
+                    const Vec3<R> cright = {a.cam.right[0], a.cam.right[1], a.cam.right[2]};
+                    const R cx = xn + dx, cy = yn + dy;
+                    Vec3<R> origin = eye;
+                    Vec3<R> new_dir = a.cam.d * cdir + cx * cright + cy * cup;
+                    if (a.cam.aperture > (R)0) {
+                        const Vec3<R> focal_point = origin + M<R>::normalize(new_dir) * a.cam.focal_distance;
+                        R ax, ay;
+                        unit_disc(rng, ax, ay);
+                        origin = origin + (ax * cright + ay * cup) * a.cam.aperture;
+                        new_dir = focal_point - origin;
+                    }
+                    ro = origin;
+                    rd = M<R>::normalize(new_dir);
+                    tmax = M<R>::inf();
+                    depth = 0;
+                    active = true;
+                }
+            }
         }
 
-        // ================= B. the single get_closest_hit site ========================
-        if (__all_sync(wmask, idle)) break;  // also the re-convergence point of the warp
+        // ================= the single get_closest_hit site ==============================
+        if (__all_sync(wmask, status == ST_IDLE)) break;  // also re-converges the warp
         Hit<R> h;
         h.t = tmax;
         h.obj = -1;
-        if (!idle) {
+        if (active) {
             pc.rays++;
-            closest_hit<R, STATS>(sv, ro, rd, tmin, shadow, h, pc.ts);
+            closest_hit<R, STATS>(sv, ro, rd, tmin, light_slot, h, pc.ts);
         }
 
-        // ================= C. consume the answer ====================================
-        if (idle) {
-            // nothing: this lane only keeps the warp's trace site convergent
-        } else if (shadow) {
-            if (h.obj < 0) color = color + contrib;
-            // phase stays PH_LIGHTS: the walk resumes at light `li`
-        } else {
-            pc.segments++;  // one trace_ray invocation
-            if (h.obj < 0) {
-                if (sv.env.kind != 0) pc.env_lookups++;
-                Lterm = env_color(sv.env, rd);
-                phase = PH_FINISH;
+        // ================= consume the answer ============================================
+        if (active) {
+            if (light_slot) {
+                if (h.obj < 0) color = color + contrib;
             } else {
-                const ObjectRec<R>& ob = sv.objects[h.obj];
-                const Surface<R> sf = finalize_hit(sv, ob, ro, rd, h);
-                if (sf.on_mesh) pc.mesh_hits++;
-                pos = ro + h.t * rd;
-                n = sf.n;
-                ng = sf.ng;
-                wo = -M<R>::normalize(rd);
-                mat_id = ob.material;
-                const MaterialRec<R> mat = sv.materials[mat_id];
-                err_scale = M<R>::literal ? (R)0 : M<R>::max(max_abs3(pos), max_abs3(ro));
-                color = mat.emittance * mat_color(mat);
-                // opaque surface seen from its back: bsdf == 0 for every wi (material.rs:130-133),
-                // so neither the lights nor the bounce can contribute (f32 only; f64 stays literal)
-                dead = !M<R>::literal && !mat.transparent && M<R>::signbit(dot(n, wo));
-                li = 0;
-                phase = PH_LIGHTS;
+                pc.segments++;  // one trace_ray invocation
+                if (h.obj < 0) {
+                    if (sv.env.kind != 0) pc.env_lookups++;
+                    Lterm = env_color(sv.env, rd);
+                    status = ST_FINISH;
+                } else {
+                    const ObjectRec<R>& ob = sv.objects[h.obj];
+                    const Surface<R> sf = finalize_hit(sv, ob, ro, rd, h);
+                    if (sf.on_mesh) pc.mesh_hits++;
+                    pos = ro + h.t * rd;
+                    n = sf.n;
+                    ng = sf.ng;
+                    wo = -M<R>::normalize(rd);
+                    mat_id = ob.material;
+                    const MaterialRec<R> mat = sv.materials[mat_id];
+                    err_scale = M<R>::literal ? (R)0 : M<R>::max(max_abs3(pos), max_abs3(ro));
+                    color = mat.emittance * mat_color(mat);
+                    // opaque surface seen from its back: bsdf == 0 for every wi (material.rs:130-133),
+                    // so neither the lights nor the bounce can contribute (f32 only; f64 stays literal)
+                    dead = !M<R>::literal && !mat.transparent && M<R>::signbit(dot(n, wo));
+                    li = 0;
+                    status = ST_VERTEX;
+                }
             }
         }
+        slot = slot >= Ks ? 0u : slot + 1u;
     }
 
     // color / iterations * 2^EV  (renderer.rs:141)
@@ -373,7 +386,7 @@ __global__ void sample_f_kernel(const MaterialRec<R> m, const double* __restrict
     if (i >= n) return;
     const double* d = dirs + 6 * i;
     Rng<R> rng;
-    rng.p.init(seed, (uint32_t)i, 0);
+    rng.init(seed, (uint32_t)i, 0);
     Vec3<R> wi = {(R)0, (R)0, (R)0};
     R pdf = (R)-1;
     if (!sample_f(m, mk((R)d[0], (R)d[1], (R)d[2]), mk((R)d[3], (R)d[4], (R)d[5]), rng, wi, pdf)) {

@@ -96,19 +96,99 @@ struct Philox {
 template <class R>
 struct Rng;
 
-// f64: bit-for-bit the oracle's conversions.
+// f64: bit-for-bit the oracle's conversions of the 64-bit draws.
 template <>
 struct Rng<double> {
     Philox p;
+    RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) { p.init(seed, pix, sample); }
+    RPTB_HD void ensure() {}
     RPTB_HD double gen() { return (double)(p.next_u64() >> 11) * (1.0 / 9007199254740992.0); }
     RPTB_HD double u52() { return (double)(p.next_u64() >> 12) * (1.0 / 4503599627370496.0); }
+    // Rng::gen_bool(p): Bernoulli -> u64 < p * 2^64
+    RPTB_HD bool bernoulli(double prob) {
+        const uint64_t v = p.next_u64();
+        if (prob >= 1.0) return true;
+        return v < (uint64_t)(prob * 18446744073709551616.0);
+    }
+    // Uniform::from(0..n) for usize: widening multiply with rejection zone
+    RPTB_HD uint64_t below(uint64_t n) {
+        const uint64_t ints_to_reject = (0xFFFFFFFFFFFFFFFFull - n + 1) % n;
+        const uint64_t zone = 0xFFFFFFFFFFFFFFFFull - ints_to_reject;
+        while (true) {
+            const uint64_t v = p.next_u64();
+            const uint64_t lo = v * n;
+#ifdef __CUDA_ARCH__
+            const uint64_t hi = __umul64hi(v, n);
+#else
+            const uint64_t hi = (uint64_t)(((unsigned __int128)v * n) >> 64);
+#endif
+            if (lo <= zone) return hi;
+        }
+    }
 };
-// f32: the top 24 bits of the same draw -- the f64 value truncated to a float in [0,1).
+
+// f32: only the HIGH 32-bit word of each 64-bit draw is kept -- its top 24 bits are the f64
+// value truncated to a float in [0,1), so both precisions see the same stream.  The words
+// are produced a block (two draws) at a time into a 4-entry register FIFO by ensure(),
+// which the integrator calls where the whole warp is converged: the ~60-instruction
+// Philox block then runs once for 32 lanes instead of once per lane per call site.
+// gen_bool / Uniform(0..n) decide on the high word alone; the decision differs from the
+// 64-bit one with probability <= n * 2^-32 per draw (f32 mode only).
 template <>
 struct Rng<float> {
-    Philox p;
-    RPTB_HD float gen() { return (float)(uint32_t)(p.next_u64() >> 40) * (1.0f / 16777216.0f); }
+    uint32_t key0, key1, block, pixel, samp_lo, samp_hi;
+    uint32_t q0, q1, q2, q3;
+    uint32_t avail;
+    RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) {
+        key0 = (uint32_t)seed;
+        key1 = (uint32_t)(seed >> 32);
+        block = 0;
+        pixel = pix;
+        samp_lo = (uint32_t)sample;
+        samp_hi = (uint32_t)(sample >> 32);
+        q0 = q1 = q2 = q3 = 0;
+        avail = 0;
+    }
+    RPTB_HD void push_block() {  // requires avail <= 2
+#ifdef __CUDA_ARCH__
+        const uint4 v = Philox::block_call(block, pixel, samp_lo, samp_hi, key0, key1);
+        const uint32_t a = v.y, b = v.w;
+#else
+        uint32_t o[4];
+        Philox::block10(block, pixel, samp_lo, samp_hi, key0, key1, o);
+        const uint32_t a = o[1], b = o[3];
+#endif
+        block++;
+        if (avail == 0) { q0 = a; q1 = b; }
+        else if (avail == 1) { q1 = a; q2 = b; }
+        else { q2 = a; q3 = b; }
+        avail += 2;
+    }
+    RPTB_HD void ensure() {
+        if (avail <= 2) push_block();
+        if (avail <= 2) push_block();
+    }
+    RPTB_HD uint32_t next32() {
+        if (avail == 0) push_block();  // rare: a slot consumed more than the FIFO held
+        const uint32_t v = q0;
+        q0 = q1; q1 = q2; q2 = q3;
+        avail--;
+        return v;
+    }
+    RPTB_HD float gen() { return (float)(next32() >> 8) * (1.0f / 16777216.0f); }
     RPTB_HD float u52() { return gen(); }
+    RPTB_HD bool bernoulli(float prob) {
+        const uint32_t v = next32();
+        if (prob >= 1.0f) return true;
+        return v < (uint32_t)((uint64_t)((double)prob * 18446744073709551616.0) >> 32);
+    }
+    RPTB_HD uint64_t below(uint64_t n) {
+#ifdef __CUDA_ARCH__
+        return (uint64_t)__umulhi(next32(), (uint32_t)n);
+#else
+        return ((uint64_t)next32() * (uint32_t)n) >> 32;
+#endif
+    }
 };
 
 // Rng::gen_range(lo..hi) -> UniformFloat::sample_single
@@ -128,29 +208,11 @@ RPTB_HD R uniform_pm1(Rng<R>& r) { return r.u52() * (R)2 + (R)(-1); }
 // Rng::gen_bool(p).  p >= 1 returns true (the reference's ALWAYS_TRUE case) but still
 // consumes one draw so that the number of draws per vertex is material-independent.
 template <class R>
-RPTB_HD bool gen_bool(Rng<R>& r, R prob) {
-    const uint64_t v = r.p.next_u64();
-    if (prob >= (R)1) return true;
-    const uint64_t p_int = (uint64_t)((double)prob * 18446744073709551616.0);
-    return v < p_int;
-}
+RPTB_HD bool gen_bool(Rng<R>& r, R prob) { return r.bernoulli(prob); }
 
-// Uniform::from(0..n) for usize: widening multiply with rejection zone
+// Uniform::from(0..n) for usize
 template <class R>
-RPTB_HD uint64_t uniform_usize(Rng<R>& r, uint64_t n) {
-    const uint64_t ints_to_reject = (0xFFFFFFFFFFFFFFFFull - n + 1) % n;
-    const uint64_t zone = 0xFFFFFFFFFFFFFFFFull - ints_to_reject;
-    while (true) {
-        const uint64_t v = r.p.next_u64();
-        const uint64_t lo = v * n;
-#ifdef __CUDA_ARCH__
-        const uint64_t hi = __umul64hi(v, n);
-#else
-        const uint64_t hi = (uint64_t)(((unsigned __int128)v * n) >> 64);
-#endif
-        if (lo <= zone) return hi;
-    }
-}
+RPTB_HD uint64_t uniform_usize(Rng<R>& r, uint64_t n) { return r.below(n); }
 
 // rand_distr::UnitDisc: rejection from the square, boundary inclusive
 template <class R>
