@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librpt_b200.so")
+LIB_PATH = os.environ.get("RPTB_LIB") or os.path.join(_HERE, "lib", "librpt_b200.so")  # RPTB_LIB: A/B builds only
 
 # ---- enums (include/rpt_b200.h) ------------------------------------------------
 OK = 0

@@ -256,7 +256,10 @@ def test_render_parity_same_stream(orc, cfgs, name):
     assert np.isfinite(g32).all()
     assert util.rmse(cl(g32), cl(ref)) <= 0.25 * noise, (util.rmse(cl(g32), cl(ref)), noise)
     assert abs(cl(g32).mean() - cl(ref).mean()) <= 5e-3 * cl(ref).mean()
-    assert abs(st32["segments"] - st0["segments"]) <= 0.05 * st0["segments"]
+    # the f32 path does not trace subtrees whose weight is exactly zero (opaque surface seen from
+    # behind, direction sampled below the surface): never more segments than the reference, and
+    # at most ~15 % fewer
+    assert 0.85 * st0["segments"] <= st32["segments"] <= 1.001 * st0["segments"]
     # f32 product, independent streams: statistical parity
     g32b, _ = _gpu_render(cfg, ds, w, h, spp, mb, 2, F32)
     assert util.rmse(cl(g32b), cl(ref)) <= 1.25 * noise

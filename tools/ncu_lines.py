@@ -14,6 +14,7 @@ asm = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_outp
 lines = []
 inside = False
 cur = ("?", 0)
+fresh_group = True  # nvdisasm prints one //## line per inline level, innermost first
 for ln in asm:
     if ln.startswith("\t.section\t.text."):
         inside = (".text." + kern + ",") in ln
@@ -22,11 +23,14 @@ for ln in asm:
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
     if m:
-        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        if fresh_group:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            fresh_group = False
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*);", ln)
     if m:
         lines.append((int(m.group(1), 16), cur, m.group(2).strip()))
+        fresh_group = True
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(csvtxt)))
 hdr = rows[1]
