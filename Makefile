@@ -45,6 +45,11 @@ $(ORACLE): oracle/oracle.cpp include/rpt_b200.h
 	@mkdir -p oracle/_build
 	$(CXX) -std=c++17 -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp -fPIC -shared -Wall -Wextra -o $@ $<
 
+# C++ host mirror example (needs a GPU to run)
+examples: build/sphere_cpp
+build/sphere_cpp: examples/sphere.cpp include/rpt.hpp include/rpt_b200.h $(LIB)
+	$(CXX) -std=c++17 -O2 -Wall -o $@ $< -Lrpt_b200/lib -lrpt_b200 -Wl,-rpath,'$$ORIGIN/../rpt_b200/lib'
+
 clean:
 	rm -rf build $(LIB) $(ORACLE)
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle examples clean

@@ -164,6 +164,13 @@ def ncu_traffic(workload_name: str):
 
 
 # ------------------------------------------------------------------ CPU arm -----------
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def oracle_rate(cfg, budget_s: float = 15.0):
     """Time the CPU restatement of the same workload on all host threads, on a bounded
     sample: whole-resolution renders at reduced spp (the rate is spp-independent)."""
@@ -173,16 +180,16 @@ def oracle_rate(cfg, budget_s: float = 15.0):
     flat = api.FlatScene(cfg.scene)
     osc = orc.OracleScene(flat)
     r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces).seed(1)
-    cores = orc.hardware_threads()
+    cores = host_threads()
     t0 = time.perf_counter()
-    _, st = osc.render(cfg.camera, r.params(1))
+    _, st = osc.render(cfg.camera, r.params(1), nthreads=cores)
     t1 = time.perf_counter() - t0
     spp = 1
     segs, secs = st["segments"], t1
     if t1 < budget_s / 2:
         spp = int(max(1, min(16, math.floor(budget_s / max(t1, 1e-3)) - 1)))
         t0 = time.perf_counter()
-        _, st = osc.render(cfg.camera, r.params(spp, first_sample=1))
+        _, st = osc.render(cfg.camera, r.params(spp, first_sample=1), nthreads=cores)
         secs = time.perf_counter() - t0
         segs = st["segments"]
     return {
@@ -207,14 +214,14 @@ def run_reference(args):
     flat = api.FlatScene(cfg.scene)
     osc = orc.OracleScene(flat)
     r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces).seed(1)
-    cores = orc.hardware_threads()
+    cores = host_threads()  # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
     sample_spp = 1  # one sample per pixel of the full-resolution image per step
     for i in range(args.warmup):
-        osc.render(cfg.camera, r.params(sample_spp, first_sample=i))
+        osc.render(cfg.camera, r.params(sample_spp, first_sample=i), nthreads=cores)
     segs, t = 0, 0.0
     for i in range(args.steps):
         t0 = time.perf_counter()
-        _, st = osc.render(cfg.camera, r.params(sample_spp, first_sample=args.warmup + i))
+        _, st = osc.render(cfg.camera, r.params(sample_spp, first_sample=args.warmup + i), nthreads=cores)
         t += time.perf_counter() - t0
         segs += st["segments"]
     value = segs / t / 1e6

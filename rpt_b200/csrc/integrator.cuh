@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
                         lv.inv_pdf = (R)1 / pdf;
                         lv.abscos = abscos;
                     } else {
-                        const R k = abscos / pdf;
+                        // exp() underflows in f32 long before it does in f64: a pdf of exactly 0 can only
+                        // pair with a direction whose true weight is negligible -> weight 0, not 0/0
+                        const R k = pdf > (R)0 ? abscos / pdf : (R)0;
                         const Vec3<R> w = {f.x * k, f.y * k, f.z * k};
                         lv.w[0] = w.x; lv.w[1] = w.y; lv.w[2] = w.z;
                         // forward accumulation: Y0 = sum_k T_k (.) local_k  with T_{k+1} = T_k (.) w_k

@@ -303,6 +303,9 @@ RPTB_D void illuminate(const SceneView<R>& sv, const LightRec<R>& l, Vec3<R> pos
         const R cosine = M<R>::max(-dot(disp, n), (R)0) / len;
         const R surface_area = M<R>::max(cosine, (R)0) / (len * len);
         intensity = mk(l.radiance[0], l.radiance[1], l.radiance[2]) * surface_area / p;
+        // f32: a UnitDisc draw exactly on the rim (x^2 + y^2 == 1, probability ~1e-7 with 24-bit
+        // uniforms, ~1e-16 in f64) gives z = 0 -> pdf 0 and cosine 0 -> 0/0.  Its weight is 0.
+        if (!M<R>::literal && !(p > (R)0)) intensity = mk((R)0, (R)0, (R)0);
         wi = disp / len;
         dist = len;
     }
