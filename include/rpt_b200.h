@@ -171,6 +171,15 @@ typedef enum rptb_precision {
     RPTB_PRECISION_F64 = 1  /* parity gate: literal f64 semantics, no ray offsets */
 } rptb_precision;
 
+/* How the integrator is scheduled on the device (results agree to f32 rounding):
+ *   MEGAKERNEL  one thread per pixel, whole path in registers -- best when rays are cheap
+ *               (analytic shapes, tiny meshes: sphere, cornell, glass)
+ *   WAVEFRONT   path state in HBM, a shade kernel and a persistent trace kernel per path
+ *               vertex -- best when kd-tree traversal dominates (teapot, dragon)
+ * AUTO picks WAVEFRONT iff some mesh's kd-tree has more than one node (f32 only; the f64
+ * parity gate always runs the megakernel).                                             */
+typedef enum rptb_engine { RPTB_ENGINE_AUTO = 0, RPTB_ENGINE_MEGAKERNEL = 1, RPTB_ENGINE_WAVEFRONT = 2 } rptb_engine;
+
 typedef struct rptb_render_params {
     uint32_t width;
     uint32_t height;
@@ -183,6 +192,8 @@ typedef struct rptb_render_params {
     uint32_t shard_count; /* t % shard_count == shard_index; others stay 0 */
     uint32_t precision;   /* rptb_precision */
     uint32_t collect_stats; /* 0 = segments only; 1 = + node visits / tri tests */
+    uint32_t engine;      /* rptb_engine: 0 = pick by scene                   */
+    uint32_t _pad;
 } rptb_render_params;
 
 typedef struct rptb_stats {

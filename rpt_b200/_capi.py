@@ -17,6 +17,7 @@ SHAPE_SPHERE, SHAPE_PLANE, SHAPE_CUBE, SHAPE_MESH = 0, 1, 2, 3
 LIGHT_POINT, LIGHT_AMBIENT, LIGHT_DIRECTIONAL, LIGHT_OBJECT = 0, 1, 2, 3
 ENV_COLOR, ENV_HDRI = 0, 1
 PRECISION_F32, PRECISION_F64 = 0, 1
+ENGINE_AUTO, ENGINE_MEGAKERNEL, ENGINE_WAVEFRONT = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)
@@ -131,6 +132,8 @@ class RenderParams(C.Structure):
         ("shard_count", C.c_uint32),
         ("precision", C.c_uint32),
         ("collect_stats", C.c_uint32),
+        ("engine", C.c_uint32),
+        ("_pad", C.c_uint32),
     ]
 
 

@@ -655,6 +655,7 @@ class Renderer:
         self._seed = 0
         self._device = 0
         self._precision = capi.PRECISION_F32
+        self._engine = capi.ENGINE_AUTO
         self._dev_scene: Optional[DeviceScene] = None
         self._next_sample = 0
         self.last_stats: Optional[dict] = None
@@ -695,6 +696,10 @@ class Renderer:
         self._precision = int(precision)
         return self
 
+    def engine(self, engine: int) -> "Renderer":
+        self._engine = int(engine)
+        return self
+
     def params(self, iterations: int, first_sample: int = 0, shard_index: int = 0, shard_count: int = 1,
                collect_stats: int = 0) -> capi.RenderParams:
         p = capi.RenderParams()
@@ -705,6 +710,7 @@ class Renderer:
         p.shard_index, p.shard_count = shard_index, shard_count
         p.precision = self._precision
         p.collect_stats = collect_stats
+        p.engine = self._engine
         return p
 
     def device_scene(self) -> DeviceScene:

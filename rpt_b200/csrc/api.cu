@@ -350,6 +350,13 @@ struct rptb_scene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex lock;
     uint64_t f32_bytes = 0;
+    // wavefront engine: scratch memory (path state, rays, hits) cached between calls
+    bool has_tree = false;          // some mesh's kd-tree is more than one leaf
+    uint64_t tree_nodes = 0;        // kd nodes over all meshes
+    uint32_t sampled_lights = 0;    // non-ambient lights
+    void* wf_mem = nullptr;
+    size_t wf_bytes = 0;
+    uint32_t* wf_pinned = nullptr;  // page-locked word for the step loop's termination check
 };
 
 namespace {
@@ -443,6 +450,8 @@ int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
         }
         a.ntris = b.ntris = hm.ntris;
         a.root_is_leaf = b.root_is_leaf = (hm.nodes32[0].word & 3u) == 3u;
+        if (!a.root_is_leaf) s->has_tree = true;
+        s->tree_nodes += hm.nodes32.size();
     }
     {
         const uint64_t before = s->arena.bytes;
@@ -476,6 +485,9 @@ int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
         s->view32.env.width = s->view64.env.width = w;
         s->view32.env.height = s->view64.env.height = h;
     }
+    for (uint32_t i = 0; i < d->nlights; i++)
+        if (d->lights[i].kind != RPTB_LIGHT_AMBIENT) s->sampled_lights++;
+    CU(cudaHostAlloc((void**)&s->wf_pinned, sizeof(uint32_t), cudaHostAllocDefault));
     CU(cudaMalloc(&s->counters, sizeof(DeviceCounters)));
     CU(cudaMemset(s->counters, 0, sizeof(DeviceCounters)));
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -526,7 +538,22 @@ int check_params(const rptb_scene* s, const rptb_camera* cam, const rptb_render_
     const uint32_t sc = p->shard_count ? p->shard_count : 1;
     if (p->shard_index >= sc) return fail(RPTB_ERR_BAD_ARG, "shard_index %u >= shard_count %u", p->shard_index, sc);
     if (p->precision > RPTB_PRECISION_F64) return fail(RPTB_ERR_BAD_ARG, "bad precision %u", p->precision);
+    if (p->engine > RPTB_ENGINE_WAVEFRONT) return fail(RPTB_ERR_BAD_ARG, "bad engine %u", p->engine);
+    if (p->engine == RPTB_ENGINE_WAVEFRONT && p->precision != RPTB_PRECISION_F32)
+        return fail(RPTB_ERR_UNSUPPORTED, "the wavefront engine is f32 only (the f64 parity gate is the megakernel)");
+    if (p->engine == RPTB_ENGINE_WAVEFRONT && s->sampled_lights > 8)
+        return fail(RPTB_ERR_UNSUPPORTED, "the wavefront engine handles at most 8 sampled lights (scene has %u)", s->sampled_lights);
     return RPTB_OK;
+}
+
+// Which schedule renders this call (include/rpt_b200.h, rptb_engine).
+bool use_wavefront(const rptb_scene* s, const rptb_render_params* p) {
+    if (p->precision != RPTB_PRECISION_F32) return false;
+    if (p->engine == RPTB_ENGINE_WAVEFRONT) return true;
+    if (p->engine == RPTB_ENGINE_MEGAKERNEL) return false;
+    // measured on one B200: the megakernel wins while traversal is cheap (teapot: 2 487 nodes,
+    // 5.2 vs 2.1 Gsamples/s), the wavefront wins once it dominates (dragon proxy: 823 k nodes)
+    return s->has_tree && s->tree_nodes >= 50000 && s->sampled_lights <= 8;
 }
 
 void read_stats(const DeviceCounters& c, rptb_stats* st) {
@@ -548,7 +575,23 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         fill_args(cam, p, a);
         a.out = out32;
         a.counters = want_counters ? s->counters : nullptr;
-        CU(launch_render_f32(s->view32, a, p->collect_stats != 0, stream, launches));
+        if (use_wavefront(s, p)) {
+            const uint32_t npaths = a.ntiles_mine * 128u;
+            const uint32_t maxd = p->max_bounces > 0 ? p->max_bounces : 1;
+            const size_t need = wavefront_bytes(npaths, s->sampled_lights, maxd);
+            if (need > s->wf_bytes) {
+                if (s->wf_mem) cudaFree(s->wf_mem);
+                s->wf_mem = nullptr;
+                s->wf_bytes = 0;
+                CU(cudaMalloc(&s->wf_mem, need));
+                s->wf_bytes = need;
+            }
+            std::vector<char> bufs(wavefront_struct_size());
+            wavefront_carve(s->wf_mem, npaths, s->sampled_lights, maxd, (WfBuffers*)bufs.data());
+            CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, stream, s->wf_pinned, launches));
+        } else {
+            CU(launch_render_f32(s->view32, a, p->collect_stats != 0, stream, launches));
+        }
     } else {
         RenderArgs<double> a;
         fill_args(cam, p, a);
@@ -638,6 +681,8 @@ void rptb_scene_destroy(rptb_scene* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->arena.release();
     if (s->counters) cudaFree(s->counters);
+    if (s->wf_mem) cudaFree(s->wf_mem);
+    if (s->wf_pinned) cudaFreeHost(s->wf_pinned);
     if (s->out32) cudaFree(s->out32);
     if (s->out64) cudaFree(s->out64);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -1,5 +1,82 @@
 // kernels_f32.cu -- the product path: every kernel instantiated for Real = float.
 #include "launch_impl.cuh"
+#include "wavefront.cuh"
+
 namespace rptb {
 RPTB_DEFINE_LAUNCHERS(f32, float)
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t wavefront_struct_size() { return sizeof(WfBuffers); }
+
+size_t wavefront_bytes(uint32_t npaths, uint32_t Ks, uint32_t maxd) {
+    const size_t n = npaths, slots = n * (Ks + 1);
+    return align256(n * sizeof(WfPath)) + align256(n * Ks * 3 * sizeof(float) + 16) + align256(n * maxd * 6 * sizeof(float) + 16) +
+           align256(slots * sizeof(WfRay)) + align256(slots * sizeof(WfHit)) + align256(slots * sizeof(uint32_t)) + 256;
 }
+
+void wavefront_carve(void* mem, uint32_t npaths, uint32_t Ks, uint32_t maxd, WfBuffers* out) {
+    char* p = (char*)mem;
+    const size_t n = npaths, slots = n * (Ks + 1);
+    out->paths = (WfPath*)p; p += align256(n * sizeof(WfPath));
+    out->contrib = (float*)p; p += align256(n * Ks * 3 * sizeof(float) + 16);
+    out->levels = (float*)p; p += align256(n * maxd * 6 * sizeof(float) + 16);
+    out->rays = (WfRay*)p; p += align256(slots * sizeof(WfRay));
+    out->hits = (WfHit*)p; p += align256(slots * sizeof(WfHit));
+    out->list = (uint32_t*)p; p += align256(slots * sizeof(uint32_t));
+    out->count = (uint32_t*)p;
+    out->npaths = npaths;
+    out->Ks = Ks;
+    out->maxd = maxd;
+}
+
+cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float>& args, const WfBuffers* bufs,
+                              bool stats, cudaStream_t stream, uint32_t* pinned, uint32_t* launches) {
+    const WfBuffers b = *bufs;
+    uint32_t nl = 0;
+    cudaError_t e;
+    const size_t nvals = (size_t)args.width * args.height * 3;
+    if (args.shard_count > 1) {
+        clear_kernel<float><<<(unsigned)((nvals + 255) / 256), 256, 0, stream>>>(args.out, nvals);
+        nl++;
+    }
+    if (b.npaths == 0) {
+        if (launches) *launches = nl;
+        return cudaGetLastError();
+    }
+    const unsigned pgrid = (b.npaths + WF_THREADS - 1) / WF_THREADS;
+    wf_init_kernel<<<pgrid, WF_THREADS, 0, stream>>>(args, b);
+    nl++;
+    // persistent trace grid: as many CTAs as are resident at once
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (stats) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<true>, WF_THREADS, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<false>, WF_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    const unsigned tgrid = (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
+    // a sample with n <= max_bounces + 1 segments takes n + 1 steps (camera ray, one per vertex,
+    // and the step that consumes the last vertex's shadow rays and emits the next camera ray)
+    const unsigned long long max_steps = (unsigned long long)args.iterations * (args.max_bounces + 2ull) + 2ull;
+    for (unsigned long long step = 0; step < max_steps; step++) {
+        e = cudaMemsetAsync(b.count, 0, 2 * sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+        if (stats) wf_shade_kernel<true><<<pgrid, WF_THREADS, 0, stream>>>(sv, args, b);
+        else wf_shade_kernel<false><<<pgrid, WF_THREADS, 0, stream>>>(sv, args, b);
+        if (stats) wf_trace_kernel<true><<<tgrid, WF_THREADS, 0, stream>>>(sv, b, args.counters);
+        else wf_trace_kernel<false><<<tgrid, WF_THREADS, 0, stream>>>(sv, b, nullptr);
+        nl += 2;
+        if ((step & 3ull) == 3ull || step + 1 == max_steps) {
+            e = cudaMemcpyAsync(pinned, b.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return e;
+            if (*pinned == 0) break;
+        }
+    }
+    wf_finish_kernel<<<pgrid, WF_THREADS, 0, stream>>>(args, b);
+    nl++;
+    if (launches) *launches = nl;
+    return cudaGetLastError();
+}
+}  // namespace rptb

@@ -19,6 +19,18 @@ namespace rptb {
 RPTB_DECLARE_LAUNCHERS(f32, float)
 RPTB_DECLARE_LAUNCHERS(f64, double)
 
+// ---- wavefront engine (f32 only; wavefront.cuh) -------------------------------------------
+struct WfBuffers;
+// bytes of device memory the engine needs for (npaths, Ks sampled lights, maxd levels)
+size_t wavefront_bytes(uint32_t npaths, uint32_t Ks, uint32_t maxd);
+// carve `mem` (wavefront_bytes big, 256-byte aligned) into the engine's arrays
+void wavefront_carve(void* mem, uint32_t npaths, uint32_t Ks, uint32_t maxd, WfBuffers* out);
+size_t wavefront_struct_size();
+// run Renderer::sample with the wavefront schedule; blocks until the image is in args.out
+// (the step loop is driven from the host).  `pinned` = 4 bytes of page-locked host memory.
+cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float>& args, const WfBuffers* bufs,
+                              bool stats, cudaStream_t stream, uint32_t* pinned, uint32_t* launches);
+
 // max_bounces the render kernels are instantiated for
 constexpr uint32_t MAX_BOUNCES_SUPPORTED = 64;
 

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(capi.Object) == 16 + 128 + 32
     assert C.sizeof(capi.Light) == 8 + 48 + C.sizeof(capi.Object)
     assert C.sizeof(capi.Camera) == 96
-    assert C.sizeof(capi.RenderParams) == 56
+    assert C.sizeof(capi.RenderParams) == 64
     assert C.sizeof(capi.Stats) == 72
 
 

@@ -421,3 +421,47 @@ def test_cpp_host_mirror_matches_python_host(gpu_ok, tmp_path):
     img_py = r.render()
     r.close()
     np.testing.assert_array_equal(img_cpp, img_py)
+
+
+# ------------------------------------------------------------ the two schedules ------------
+def _render_engine(cfg, ds, w, h, spp, mb, seed, engine, shard=(0, 1), stats=0):
+    r = api.Renderer(cfg.scene, cfg.camera).width(w).height(h).max_bounces(mb).seed(seed).engine(engine)
+    p = r.params(spp, 0, shard[0], shard[1], collect_stats=stats)
+    cam = cfg.camera.to_c()
+    out = np.empty((w * h, 3))
+    st = capi.Stats()
+    capi.check(capi.lib().rptb_render_samples(ds.handle, C.byref(cam), C.byref(p), out.ctypes.data_as(capi.c_double_p),
+                                              C.byref(st)), "rptb_render_samples")
+    return out, st.as_dict()
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_wavefront_engine_matches_megakernel(cfgs, name):
+    """Both schedules run the same per-path operation sequence on the same Philox streams:
+    identical ray/segment counts, images equal up to FMA contraction."""
+    cfg, flat, ds = cfgs(name)
+    w, h, spp, mb = SMALL[name]
+    a, sa = _render_engine(cfg, ds, w, h, spp, mb, 3, capi.ENGINE_MEGAKERNEL, stats=1)
+    b, sb = _render_engine(cfg, ds, w, h, spp, mb, 3, capi.ENGINE_WAVEFRONT, stats=1)
+    assert np.isfinite(b).all()
+    rel = np.abs(a - b) / np.maximum(np.abs(a), 1e-4)
+    assert np.quantile(rel.max(axis=1), 0.99) < 1e-4, np.quantile(rel.max(axis=1), 0.99)
+    assert abs(sa["segments"] - sb["segments"]) <= 1e-4 * sa["segments"]
+    assert abs(sa["rays"] - sb["rays"]) <= 1e-4 * sa["rays"]
+    assert abs(b.mean() - a.mean()) <= 1e-4 * a.mean()
+
+
+def test_wavefront_shards_and_determinism(cfgs):
+    cfg, flat, ds = cfgs("teapot")
+    w, h, spp, mb = 100, 52, 4, 2
+    full, st = _render_engine(cfg, ds, w, h, spp, mb, 9, capi.ENGINE_WAVEFRONT)
+    again, _ = _render_engine(cfg, ds, w, h, spp, mb, 9, capi.ENGINE_WAVEFRONT)
+    np.testing.assert_array_equal(full, again)
+    acc = np.zeros_like(full)
+    segs = 0
+    for i in range(3):
+        part, sti = _render_engine(cfg, ds, w, h, spp, mb, 9, capi.ENGINE_WAVEFRONT, shard=(i, 3))
+        acc += part
+        segs += sti["segments"]
+    np.testing.assert_array_equal(acc, full)
+    assert segs == st["segments"]
