@@ -307,6 +307,7 @@ def run_native(args):
             dist.all_reduce(tot)
         total = dict(zip(keys, [int(v) for v in tot.tolist()]))
         launches_per_step = int(st.launches)
+        engine = int(st.engine)
 
         for _ in range(W):
             step()
@@ -405,7 +406,9 @@ def run_native(args):
             "e2e": e2e,
             "gpu_launches": launches_per_step * K,
             "roofline": {
-                "bound": "hbm", "kernel": "rptb::render_kernel<float,16,false>",
+                "bound": "hbm",
+                "kernel": "rptb::render_kernel<float,16,false> (megakernel: the step's one launch)" if engine != 2 else
+                          "rptb::wf_trace_kernel<false> (+ wf_shade_kernel; wavefront engine: the duration is the whole step's kernels)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(cfg.name), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_all / world,

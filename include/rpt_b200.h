@@ -206,7 +206,7 @@ typedef struct rptb_stats {
     uint64_t object_tests;/* Shape::intersect dispatches (objects tested per ray, summed) */
     double gpu_ms;        /* device time of the render launch(es)              */
     uint32_t launches;    /* kernels launched by the call                      */
-    uint32_t _pad;
+    uint32_t engine;      /* rptb_engine that rendered the call (1 or 2)       */
 } rptb_stats;
 
 typedef struct rptb_scene rptb_scene; /* opaque */

@@ -148,7 +148,7 @@ class Stats(C.Structure):
         ("object_tests", C.c_uint64),
         ("gpu_ms", C.c_double),
         ("launches", C.c_uint32),
-        ("_pad", C.c_uint32),
+        ("engine", C.c_uint32),
     ]
 
     def as_dict(self):

@@ -197,6 +197,7 @@ struct HostMesh {
     std::vector<KdNodeDev64> nodes64;
     std::vector<uint32_t> refs;
     std::vector<float4> tri48;
+    std::vector<float4> leaf_planes;
     std::vector<float> verts32, norms32;
     std::vector<double> verts64, norms64;
     double bmin[3], bmax[3];
@@ -353,6 +354,7 @@ struct rptb_scene {
     // wavefront engine: scratch memory (path state, rays, hits) cached between calls
     bool has_tree = false;          // some mesh's kd-tree is more than one leaf
     uint64_t tree_nodes = 0;        // kd nodes over all meshes
+    double wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};  // world bounds of the meshes
     uint32_t sampled_lights = 0;    // non-ambient lights
     void* wf_mem = nullptr;
     size_t wf_bytes = 0;
@@ -429,6 +431,11 @@ int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
         CU(s->arena.upload(hm.nodes32, &a.nodes));
         CU(s->arena.upload(hm.refs, &a.refs));
         CU(s->arena.upload(hm.tri48, &a.tri48));
+        if ((hm.nodes32[0].word & 3u) != 3u) {  // a real tree: planes in leaf order for the trace kernel
+            hm.leaf_planes.resize(hm.refs.size());
+            for (size_t k = 0; k < hm.refs.size(); k++) hm.leaf_planes[k] = hm.tri48[3 * (size_t)hm.refs[k]];
+            CU(s->arena.upload(hm.leaf_planes, &a.leaf_planes));
+        }
         CU(s->arena.upload(hm.verts32, &a.verts));
         CU(s->arena.upload(hm.norms32, &a.norms));
         s->f32_bytes += s->arena.bytes - before;
@@ -452,6 +459,20 @@ int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
         a.root_is_leaf = b.root_is_leaf = (hm.nodes32[0].word & 3u) == 3u;
         if (!a.root_is_leaf) s->has_tree = true;
         s->tree_nodes += hm.nodes32.size();
+        // world-space bounds of every object that uses this mesh (8 transformed corners), for the ray sort keys
+        for (uint32_t oi = 0; oi < d->nobjects; oi++) {
+            const rptb_object& o = d->objects[oi];
+            if (o.kind != RPTB_SHAPE_MESH || o.mesh != i) continue;
+            for (int c = 0; c < 8; c++) {
+                const double p[3] = {(c & 1) ? hm.bmax[0] : hm.bmin[0], (c & 2) ? hm.bmax[1] : hm.bmin[1], (c & 4) ? hm.bmax[2] : hm.bmin[2]};
+                for (int r = 0; r < 3; r++) {
+                    double v = p[r];
+                    if (o.has_transform) v = o.transform[0 * 4 + r] * p[0] + o.transform[1 * 4 + r] * p[1] + o.transform[2 * 4 + r] * p[2] + o.transform[3 * 4 + r];
+                    s->wlo[r] = std::fmin(s->wlo[r], v);
+                    s->whi[r] = std::fmax(s->whi[r], v);
+                }
+            }
+        }
     }
     {
         const uint64_t before = s->arena.bytes;
@@ -587,7 +608,13 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
                 s->wf_bytes = need;
             }
             std::vector<char> bufs(wavefront_struct_size());
-            wavefront_carve(s->wf_mem, npaths, s->sampled_lights, maxd, (WfBuffers*)bufs.data());
+            float blo[3], binv[3];
+            for (int r = 0; r < 3; r++) {
+                const double ext = s->whi[r] - s->wlo[r];
+                blo[r] = (float)s->wlo[r];
+                binv[r] = (float)(ext > 0 && std::isfinite(ext) ? 1.0 / ext : 0.0);
+            }
+            wavefront_carve(s->wf_mem, npaths, s->sampled_lights, maxd, blo, binv, (WfBuffers*)bufs.data());
             CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, stream, s->wf_pinned, launches));
         } else {
             CU(launch_render_f32(s->view32, a, p->collect_stats != 0, stream, launches));
@@ -726,6 +753,7 @@ int rptb_render_samples_device(rptb_scene* s, const rptb_camera* cam, const rptb
         CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         stats->gpu_ms = ms;
         stats->launches = launches;
+        stats->engine = use_wavefront(s, p) ? RPTB_ENGINE_WAVEFRONT : RPTB_ENGINE_MEGAKERNEL;
     } else if (!stream_v) {
         CU(cudaStreamSynchronize(stream));
     }
@@ -765,6 +793,7 @@ int rptb_render_samples(rptb_scene* s, const rptb_camera* cam, const rptb_render
         CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         stats->gpu_ms = ms;
         stats->launches = launches;
+        stats->engine = use_wavefront(s, p) ? RPTB_ENGINE_WAVEFRONT : RPTB_ENGINE_MEGAKERNEL;
     }
     return RPTB_OK;
 }

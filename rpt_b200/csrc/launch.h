@@ -24,7 +24,8 @@ struct WfBuffers;
 // bytes of device memory the engine needs for (npaths, Ks sampled lights, maxd levels)
 size_t wavefront_bytes(uint32_t npaths, uint32_t Ks, uint32_t maxd);
 // carve `mem` (wavefront_bytes big, 256-byte aligned) into the engine's arrays
-void wavefront_carve(void* mem, uint32_t npaths, uint32_t Ks, uint32_t maxd, WfBuffers* out);
+void wavefront_carve(void* mem, uint32_t npaths, uint32_t Ks, uint32_t maxd, const float* bounds_lo,
+                     const float* bounds_inv_extent, WfBuffers* out);
 size_t wavefront_struct_size();
 // run Renderer::sample with the wavefront schedule; blocks until the image is in args.out
 // (the step loop is driven from the host).  `pinned` = 4 bytes of page-locked host memory.

@@ -18,6 +18,8 @@
 //                        for double: KdNodeDev64 (16 B)
 //               refs[]   u32 triangle indices, leaf order of the reference (ascending)
 //               tri48[]  3 x float4 per triangle (f32 only): plane + two barycentric functionals
+//               leaf_planes[] float4 per leaf ref (f32): the plane of refs[k], so a leaf's planes are one
+//                        contiguous stream instead of one dependent gather per triangle
 //               verts[]  9 R per triangle  (v1,v2,v3)  -- f64 intersect, light sampling
 //               norms[]  9 R per triangle  (n1,n2,n3)  -- fetched once per final hit
 #pragma once
@@ -56,6 +58,7 @@ struct MeshRec {
     const typename NodeOf<R>::type* nodes;
     const uint32_t* refs;
     const float4* tri48;  // f32 only (null for double)
+    const float4* leaf_planes;  // f32, kd-tree meshes only: tri48[3*refs[k]] for every leaf ref k (planes in leaf order)
     const R* verts;       // 9 per triangle
     const R* norms;       // 9 per triangle
     R bmin[3], bmax[3];   // KdTree::bounds

@@ -82,8 +82,43 @@ struct WfBuffers {
     WfHit* hits;      // npaths * (Ks + 1)
     uint32_t* list;   // compact list of live ray slots
     uint32_t* count;  // [0] rays emitted this step, [1] fetch cursor of the trace kernel
+    // ray sorting (coherence): Morton keys of the listed rays and the double buffers of the radix sort
+    uint32_t* keys;
+    uint32_t* keys_alt;
+    uint32_t* list_alt;
+    void* sort_tmp;
+    size_t sort_tmp_bytes;
+    float bounds_lo[3], bounds_inv[3];  // world bounds of the kd-tree meshes (key quantisation)
     uint32_t npaths, Ks, maxd;
 };
+
+// Sort key of a ray: [shadow?:1][Morton code of the origin, 9 bits per axis, with the direction octant
+// spliced in below its top 15 bits].  Rays that start in the same cell and head the same way descend the
+// same part of the tree: neighbouring lanes then share nodes (L1 hits) and leave the descent loop
+// together.  Unused list entries get the maximal key and sort to the end.
+RPTB_D uint32_t wf_spread3(uint32_t v) {  // 9 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void wf_key_kernel(const WfBuffers b, uint32_t capacity) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= capacity) return;
+    uint32_t key = 0xFFFFFFFFu;
+    if (i < b.count[0]) {
+        const WfRay r = b.rays[b.list[i]];
+        const float fx = fminf(fmaxf((r.ox - b.bounds_lo[0]) * b.bounds_inv[0], 0.f), 1.f);
+        const float fy = fminf(fmaxf((r.oy - b.bounds_lo[1]) * b.bounds_inv[1], 0.f), 1.f);
+        const float fz = fminf(fmaxf((r.oz - b.bounds_lo[2]) * b.bounds_inv[2], 0.f), 1.f);
+        const uint32_t qx = min((uint32_t)(fx * 512.f), 511u), qy = min((uint32_t)(fy * 512.f), 511u), qz = min((uint32_t)(fz * 512.f), 511u);
+        const uint32_t morton = (wf_spread3(qx) << 2) | (wf_spread3(qy) << 1) | wf_spread3(qz);  // 27 bits
+        const uint32_t oct = (r.dx < 0.f ? 4u : 0u) | (r.dy < 0.f ? 2u : 0u) | (r.dz < 0.f ? 1u : 0u);
+        key = ((r.any ? 1u : 0u) << 30) | ((morton >> 12) << 15) | (oct << 12) | (morton & 0xFFFu);
+    }
+    b.keys[i] = key;
+}
 
 RPTB_D void wf_pixel_of(const RenderArgs<float>& a, uint32_t p, uint32_t& x, uint32_t& y) {
     const uint32_t k = p / RENDER_THREADS, tid = p % RENDER_THREADS;
@@ -391,6 +426,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade_kernel(const SceneView<fl
 // triangles and pops.
 template <bool STATS>
 __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<float> sv, const WfBuffers b,
+                                                              const uint32_t* __restrict__ list,
                                                               DeviceCounters* counters) {
     typedef float R;
     const R tmin = (R)1e-12;
@@ -429,7 +465,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<fl
                 if (want) {
                     const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
                     if (idx < total) {
-                        slot = b.list[idx];
+                        slot = list[idx];
                         const WfRay r = b.rays[slot];
                         wo_ = {r.ox, r.oy, r.oz};
                         wd_ = {r.dx, r.dy, r.dz};
@@ -498,9 +534,11 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<fl
                 const uint32_t axis = nd.word & 3u;
                 const uint32_t right = nd.word >> 2;
                 const R split = nd.split;
-                const R oa = comp(lo_o, (int)axis), da = comp(lo_d, (int)axis);
-                const R t_split = (split - oa) * comp(inv, (int)axis);
-                const bool left_first = (oa < split) || (oa == split && da <= (R)0);
+                const R oa = comp(lo_o, (int)axis), ia = comp(inv, (int)axis);
+                const R sd = split - oa;
+                const R t_split = sd * ia;
+                // (o < split) || (o == split && d <= 0); sign(1/d) == sign(d)
+                const bool left_first = (sd > (R)0) || (sd == (R)0 && ia <= (R)0);
                 const uint32_t first = left_first ? node + 1u : right;
                 const uint32_t second = left_first ? right : node + 1u;
                 if (t_split > fminf(hi, h.t) || t_split <= (R)0) {
@@ -526,16 +564,14 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<fl
                 const uint32_t first_ref = nd.first_ref;
                 const uint32_t cnt = nd.word >> 2;
                 const float4* T = mesh->tri48;
+                const float4* LP = mesh->leaf_planes + first_ref;  // this leaf's planes, contiguous
                 const R slack = (fabsf(lo) + fabsf(hi)) * 1e-4f + 1e-6f;
                 const R c_lo = fmaxf(lo - slack, tmin), c_hi = hi + slack;
                 for (uint32_t i = 0; i < cnt; i += 4) {
                     const uint32_t n4 = min(4u, cnt - i);
-                    uint32_t tr[4];
                     float4 q0[4];
 #pragma unroll
-                    for (uint32_t j = 0; j < 4; j++) tr[j] = __ldg(mesh->refs + first_ref + i + min(j, n4 - 1u));
-#pragma unroll
-                    for (uint32_t j = 0; j < 4; j++) q0[j] = __ldg(T + 3 * (size_t)tr[j]);
+                    for (uint32_t j = 0; j < 4; j++) q0[j] = __ldg(LP + i + min(j, n4 - 1u));
 #pragma unroll
                     for (uint32_t j = 0; j < 4; j++) {
                         if (j >= n4) break;
@@ -544,8 +580,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<fl
                         if (fabsf(cosine) < 1e-8f) continue;
                         const float time = __fdividef(q0[j].w - (q0[j].x * lo_o.x + q0[j].y * lo_o.y + q0[j].z * lo_o.z), cosine);
                         if (time < c_lo || time >= h.t || time > c_hi) continue;
-                        const float4 q1 = __ldg(T + 3 * (size_t)tr[j] + 1);
-                        const float4 q2 = __ldg(T + 3 * (size_t)tr[j] + 2);
+                        const uint32_t tri = __ldg(mesh->refs + first_ref + i + j);
+                        const float4 q1 = __ldg(T + 3 * (size_t)tri + 1);
+                        const float4 q2 = __ldg(T + 3 * (size_t)tri + 2);
                         const float px = fmaf(time, lo_d.x, lo_o.x), py = fmaf(time, lo_d.y, lo_o.y), pz = fmaf(time, lo_d.z, lo_o.z);
                         const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
                         const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
@@ -554,7 +591,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<fl
                             h.t = time;
                             h.bv = v;
                             h.bw = w;
-                            h.aux = tr[j];
+                            h.aux = tri;
                             mesh_hit = true;
                         }
                     }
