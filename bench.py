@@ -187,7 +187,7 @@ def oracle_rate(cfg, budget_s: float = 15.0):
     spp = 1
     segs, secs = st["segments"], t1
     if t1 < budget_s / 2:
-        spp = int(max(1, min(16, math.floor(budget_s / max(t1, 1e-3)) - 1)))
+        spp = int(max(1, min(96, math.floor(budget_s / max(t1, 1e-3)) - 1)))
         t0 = time.perf_counter()
         _, st = osc.render(cfg.camera, r.params(spp, first_sample=1), nthreads=cores)
         secs = time.perf_counter() - t0

@@ -68,25 +68,49 @@ struct DeviceGuard {
     }
 };
 
+// Stream-ordered allocations from the device's default memory pool, which is told to keep what
+// is freed: creating and destroying a scene per call (what the reference's `Renderer::render` on a
+// host `Scene` amounts to) then costs microseconds instead of the 1-400 ms cudaMalloc/cudaFree took.
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t stream) {
+    static std::mutex m;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lk(m);
+        if (!configured[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            configured[dev] = true;
+        }
+    }
+    return cudaMallocAsync(p, bytes, stream);
+}
+
 // All device allocations of a scene, freed together.
 struct Arena {
     std::vector<void*> ptrs;
     uint64_t bytes = 0;
+    cudaStream_t stream = nullptr;
     template <class T>
     cudaError_t upload(const std::vector<T>& host, const T** dev) {
         *dev = nullptr;
         if (host.empty()) return cudaSuccess;
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, host.size() * sizeof(T));
+        cudaError_t e = pool_alloc(&p, host.size() * sizeof(T), stream);
         if (e != cudaSuccess) return e;
         ptrs.push_back(p);
         bytes += host.size() * sizeof(T);
-        e = cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+        // pageable source: the call returns once the bytes are staged, `host` may die afterwards
+        e = cudaMemcpyAsync(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
         *dev = (const T*)p;
         return e;
     }
     void release() {
-        for (void* p : ptrs) cudaFree(p);
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
         ptrs.clear();
     }
 };
@@ -413,6 +437,8 @@ int upload_tables(rptb_scene* s, const Tables<R>& t, SceneView<R>& v) {
 }
 
 int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->arena.stream = s->stream;
     Tables<float> t32;
     Tables<double> t64;
     fill_tables(d, t32);
@@ -508,12 +534,11 @@ int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
     }
     for (uint32_t i = 0; i < d->nlights; i++)
         if (d->lights[i].kind != RPTB_LIGHT_AMBIENT) s->sampled_lights++;
-    CU(cudaHostAlloc((void**)&s->wf_pinned, sizeof(uint32_t), cudaHostAllocDefault));
-    CU(cudaMalloc(&s->counters, sizeof(DeviceCounters)));
-    CU(cudaMemset(s->counters, 0, sizeof(DeviceCounters)));
-    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(pool_alloc((void**)&s->counters, sizeof(DeviceCounters), s->stream));
+    CU(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), s->stream));
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
+    CU(cudaStreamSynchronize(s->stream));  // the scene is resident when create returns
     return RPTB_OK;
 }
 
@@ -601,12 +626,14 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
             const uint32_t maxd = p->max_bounces > 0 ? p->max_bounces : 1;
             const size_t need = wavefront_bytes(npaths, s->sampled_lights, maxd);
             if (need > s->wf_bytes) {
-                if (s->wf_mem) cudaFree(s->wf_mem);
+                if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
                 s->wf_mem = nullptr;
                 s->wf_bytes = 0;
-                CU(cudaMalloc(&s->wf_mem, need));
+                CU(pool_alloc(&s->wf_mem, need, s->stream));
+                CU(cudaStreamSynchronize(s->stream));  // the render may run on a caller's stream
                 s->wf_bytes = need;
             }
+            if (!s->wf_pinned) CU(cudaHostAlloc((void**)&s->wf_pinned, sizeof(uint32_t), cudaHostAllocDefault));
             std::vector<char> bufs(wavefront_struct_size());
             float blo[3], binv[3];
             for (int r = 0; r < 3; r++) {
@@ -631,13 +658,14 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
 
 int ensure_out(rptb_scene* s, size_t nvals) {
     if (s->out_vals >= nvals) return RPTB_OK;
-    if (s->out32) cudaFree(s->out32);
-    if (s->out64) cudaFree(s->out64);
+    if (s->out32) cudaFreeAsync(s->out32, s->stream);
+    if (s->out64) cudaFreeAsync(s->out64, s->stream);
     s->out32 = nullptr;
     s->out64 = nullptr;
     s->out_vals = 0;
-    CU(cudaMalloc(&s->out32, nvals * sizeof(float)));
-    CU(cudaMalloc(&s->out64, nvals * sizeof(double)));
+    CU(pool_alloc((void**)&s->out32, nvals * sizeof(float), s->stream));
+    CU(pool_alloc((void**)&s->out64, nvals * sizeof(double), s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     s->out_vals = nvals;
     return RPTB_OK;
 }
@@ -705,13 +733,14 @@ int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out)
 void rptb_scene_destroy(rptb_scene* s) {
     if (!s) return;
     DeviceGuard g(s->device);
-    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaDeviceSynchronize();  // renders may have been enqueued on a caller's stream
     s->arena.release();
-    if (s->counters) cudaFree(s->counters);
-    if (s->wf_mem) cudaFree(s->wf_mem);
+    if (s->counters) cudaFreeAsync(s->counters, s->stream);
+    if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
     if (s->wf_pinned) cudaFreeHost(s->wf_pinned);
-    if (s->out32) cudaFree(s->out32);
-    if (s->out64) cudaFree(s->out64);
+    if (s->out32) cudaFreeAsync(s->out32, s->stream);
+    if (s->out64) cudaFreeAsync(s->out64, s->stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);

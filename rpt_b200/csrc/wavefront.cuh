@@ -30,7 +30,10 @@
 namespace rptb {
 
 constexpr int WF_THREADS = 128;
-constexpr int WF_MAX_SHADOW = 8;  // sampled (non-ambient) lights per scene the wavefront engine handles
+constexpr int WF_MAX_SHADOW = 8;
+#ifndef WF_TRACE_MIN_BLOCKS
+#define WF_TRACE_MIN_BLOCKS 8  // resident CTAs/SM the trace kernel is compiled for (64 registers; latency bound: measured best of 7/8/10)
+#endif  // sampled (non-ambient) lights per scene the wavefront engine handles
 
 struct __align__(16) WfRay {
     float ox, oy, oz, tmax;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade_kernel(const SceneView<fl
 // lane into the TRAVERSE state, where each loop iteration descends to one leaf, tests its
 // triangles and pops.
 template <bool STATS>
-__global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<float> sv, const WfBuffers b,
+__global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kernel(const SceneView<float> sv, const WfBuffers b,
                                                               const uint32_t* __restrict__ list,
                                                               DeviceCounters* counters) {
     typedef float R;
@@ -527,6 +530,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(const SceneView<fl
             }
         }
         // ---- one round of the kd traversal: descend to a leaf, test it, pop ---------------
+        // ("while-while".  A finer-grained "if-if" schedule -- a few node steps, then one 4-triangle
+        // batch per loop iteration -- was measured on the dragon proxy and lost: 101 vs 143 Msamples/s,
+        // +35 % instructions for +1.5 active lanes.)
         if (have && trav) {
             auto nd = load_node(mesh->nodes + node);
             while ((nd.word & 3u) != 3u) {
