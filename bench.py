@@ -236,7 +236,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -251,10 +251,6 @@ def free_port():
 
 def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus > 1 and world == 1:  # convenience: re-launch under torchrun like the driver does
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
-               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -419,7 +415,7 @@ def run_native(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = oracle_rate(cfg)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -429,9 +425,30 @@ def run_native(args):
 
 def main():
     args = parse_args()
+    # Exactly ONE line may reach stdout.  Libraries write there too (NCCL prints its version banner
+    # to stdout when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the JSON
+    # line goes to the saved descriptor.
+    if args.impl == "native" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torchrun exactly like the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":

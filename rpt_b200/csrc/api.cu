@@ -382,6 +382,8 @@ struct rptb_scene {
     uint32_t sampled_lights = 0;    // non-ambient lights
     void* wf_mem = nullptr;
     size_t wf_bytes = 0;
+    double* partial = nullptr;      // per-chunk pixel sums of the megakernel (nchunks > 1)
+    size_t partial_bytes = 0;
     uint32_t* wf_pinned = nullptr;  // page-locked word for the step loop's termination check
 };
 
@@ -573,6 +575,8 @@ void fill_args(const rptb_camera* cam, const rptb_render_params* p, RenderArgs<R
     a.tiles_y = (p->height + 7) / 8;
     const uint32_t ntiles = a.tiles_x * a.tiles_y;
     a.ntiles_mine = ntiles > a.shard_index ? (ntiles - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
+    sample_chunks(p->iterations, a.nchunks, a.chunk);
+    a.partial = nullptr;
 }
 
 int check_params(const rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p) {
@@ -612,6 +616,23 @@ void read_stats(const DeviceCounters& c, rptb_stats* st) {
     st->object_tests = c.object_tests;
 }
 
+// Chunk-sum scratch of the megakernel: nchunks * ntiles_mine * 128 * 3 doubles.
+template <class R>
+int ensure_partial(rptb_scene* s, RenderArgs<R>& a) {
+    if (a.nchunks <= 1) return RPTB_OK;
+    const size_t need = (size_t)a.nchunks * a.ntiles_mine * 128u * 3u * sizeof(double);
+    if (need > s->partial_bytes) {
+        if (s->partial) cudaFreeAsync(s->partial, s->stream);
+        s->partial = nullptr;
+        s->partial_bytes = 0;
+        CU(pool_alloc((void**)&s->partial, need, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        s->partial_bytes = need;
+    }
+    a.partial = s->partial;
+    return RPTB_OK;
+}
+
 // Launch the render on `stream` into a device buffer of the precision's type.
 int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p, float* out32, double* out64,
                   cudaStream_t stream, bool want_counters, uint32_t* launches) {
@@ -644,6 +665,8 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
             wavefront_carve(s->wf_mem, npaths, s->sampled_lights, maxd, blo, binv, (WfBuffers*)bufs.data());
             CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, stream, s->wf_pinned, launches));
         } else {
+            const int rc = ensure_partial(s, a);
+            if (rc != RPTB_OK) return rc;
             CU(launch_render_f32(s->view32, a, p->collect_stats != 0, stream, launches));
         }
     } else {
@@ -651,6 +674,8 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         fill_args(cam, p, a);
         a.out = out64;
         a.counters = want_counters ? s->counters : nullptr;
+        const int rc = ensure_partial(s, a);
+        if (rc != RPTB_OK) return rc;
         CU(launch_render_f64(s->view64, a, p->collect_stats != 0, stream, launches));
     }
     return RPTB_OK;
@@ -737,6 +762,7 @@ void rptb_scene_destroy(rptb_scene* s) {
     s->arena.release();
     if (s->counters) cudaFreeAsync(s->counters, s->stream);
     if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
+    if (s->partial) cudaFreeAsync(s->partial, s->stream);
     if (s->wf_pinned) cudaFreeHost(s->wf_pinned);
     if (s->out32) cudaFreeAsync(s->out32, s->stream);
     if (s->out64) cudaFreeAsync(s->out64, s->stream);

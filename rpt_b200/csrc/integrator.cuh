@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
     R err_scale = (R)0;
     uint32_t mat_id = 0, li = 0;
     bool dead = false;
-    uint32_t s = 0;
+    // this thread's run of samples: [s, s_end) of [0, iterations)
+    uint32_t s = blockIdx.y * a.chunk;
+    const uint32_t s_end = min(s + a.chunk, a.iterations);
     int depth = 0;
     int status = ST_FRESH;
     // f32 only: the path's radiance accumulated forwards (A + T (.) L), the running minimum of
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
                 status = ST_FRESH;
             }
             if (status == ST_FRESH) {
-                if (s >= a.iterations) {
+                if (s >= s_end) {
                     status = ST_IDLE;
                 } else {
                     rng.init(a.seed, pix, a.first_sample + s);
@@ -335,11 +337,17 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
     }
 
     // color / iterations * 2^EV  (renderer.rs:141)
-    const double it = (double)a.iterations;
-    R* out = a.out + 3 * (size_t)pix;
-    out[0] = (R)(acc0 / it * (double)a.exposure_scale);
-    out[1] = (R)(acc1 / it * (double)a.exposure_scale);
-    out[2] = (R)(acc2 / it * (double)a.exposure_scale);
+    if (a.nchunks > 1) {  // partial sum of this chunk; resolve_chunks_kernel finishes the pixel
+        const size_t slot = (size_t)blockIdx.x * RENDER_THREADS + threadIdx.x;
+        double* o = a.partial + ((size_t)blockIdx.y * ((size_t)a.ntiles_mine * RENDER_THREADS) + slot) * 3;
+        o[0] = acc0; o[1] = acc1; o[2] = acc2;
+    } else {
+        const double it = (double)a.iterations;
+        R* out = a.out + 3 * (size_t)pix;
+        out[0] = (R)(acc0 / it * (double)a.exposure_scale);
+        out[1] = (R)(acc1 / it * (double)a.exposure_scale);
+        out[2] = (R)(acc2 / it * (double)a.exposure_scale);
+    }
 
     if (a.counters) {
         const unsigned m = __activemask();
@@ -362,6 +370,29 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
             }
         }
     }
+}
+
+// Add the chunk sums of every pixel in chunk order and apply 1/iterations * 2^EV (renderer.rs:141).
+template <class R>
+__global__ void resolve_chunks_kernel(const RenderArgs<R> a) {
+    const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
+    const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t x = tx * TILE_W + (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t y = ty * TILE_H + (warp >> 1) * 4u + (lane >> 3);
+    if (x >= a.width || y >= a.height) return;
+    const size_t slot = (size_t)blockIdx.x * RENDER_THREADS + threadIdx.x;
+    const size_t stride = (size_t)a.ntiles_mine * RENDER_THREADS;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (uint32_t c = 0; c < a.nchunks; c++) {
+        const double* p = a.partial + ((size_t)c * stride + slot) * 3;
+        s0 += p[0]; s1 += p[1]; s2 += p[2];
+    }
+    const double it = (double)a.iterations;
+    R* out = a.out + 3 * ((size_t)y * a.width + x);
+    out[0] = (R)(s0 / it * (double)a.exposure_scale);
+    out[1] = (R)(s1 / it * (double)a.exposure_scale);
+    out[2] = (R)(s2 / it * (double)a.exposure_scale);
 }
 
 // Zero the pixels of tiles that belong to other shards (so an all-reduce(sum) of the

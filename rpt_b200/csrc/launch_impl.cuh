@@ -15,7 +15,7 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
         nl++;
     }
     if (args.ntiles_mine > 0) {
-        const dim3 grid(args.ntiles_mine), block(RENDER_THREADS);
+        const dim3 grid(args.ntiles_mine, args.nchunks), block(RENDER_THREADS);
         if (args.max_bounces <= 16) {
             if (stats) render_kernel<R, 16, true><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
@@ -24,6 +24,10 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             else render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false><<<grid, block, 0, stream>>>(sv, args);
         }
         nl++;
+        if (args.nchunks > 1) {
+            resolve_chunks_kernel<R><<<args.ntiles_mine, RENDER_THREADS, 0, stream>>>(args);
+            nl++;
+        }
     }
     if (launches) *launches = nl;
     return cudaGetLastError();

@@ -137,6 +137,22 @@ struct RenderArgs {
     uint32_t tiles_x, tiles_y, ntiles_mine;
     R* out;  // width*height*3
     DeviceCounters* counters;
+    // Sample chunks: the `iterations` samples of a pixel are cut into `nchunks` runs of `chunk`
+    // samples, each summed sequentially by one thread into partial[(c * npix_slots + slot) * 3]
+    // (double); resolve adds the chunk sums in chunk order.  The split depends on `iterations`
+    // only -- never on the GPU count -- so the image stays bit-identical for any sharding, while
+    // the grid keeps tiles * nchunks CTAs however few tiles a shard owns.
+    uint32_t nchunks, chunk;
+    double* partial;  // nchunks > 1 only
 };
+
+// nchunks = min(16, ceil(iterations / 32)), chunk = ceil(iterations / nchunks)
+inline void sample_chunks(uint32_t iterations, uint32_t& nchunks, uint32_t& chunk) {
+    nchunks = (iterations + 31u) / 32u;
+    if (nchunks > 16u) nchunks = 16u;
+    if (nchunks < 1u) nchunks = 1u;
+    chunk = (iterations + nchunks - 1u) / nchunks;
+    nchunks = (iterations + chunk - 1u) / chunk;
+}
 
 }  // namespace rptb
