@@ -576,6 +576,7 @@ void fill_args(const rptb_camera* cam, const rptb_render_params* p, RenderArgs<R
     const uint32_t ntiles = a.tiles_x * a.tiles_y;
     a.ntiles_mine = ntiles > a.shard_index ? (ntiles - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
     sample_chunks(p->iterations, a.nchunks, a.chunk);
+    sample_groups(a.ntiles_mine, a.nchunks, a.ngroups, a.chunks_per_group);
     a.partial = nullptr;
 }
 

@@ -140,9 +140,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
     R err_scale = (R)0;
     uint32_t mat_id = 0, li = 0;
     bool dead = false;
-    // this thread's run of samples: [s, s_end) of [0, iterations)
-    uint32_t s = blockIdx.y * a.chunk;
-    const uint32_t s_end = min(s + a.chunk, a.iterations);
+    // this thread's run of samples: [s, s_end) of [0, iterations) = chunks_per_group whole chunks
+    uint32_t s = blockIdx.y * a.chunks_per_group * a.chunk;
+    const uint32_t s_end = min(s + a.chunks_per_group * a.chunk, a.iterations);
+    uint32_t chunk_id = blockIdx.y * a.chunks_per_group, chunk_left = a.chunk;
+    const size_t pslot = (size_t)blockIdx.x * RENDER_THREADS + threadIdx.x;
+    const size_t pstride = (size_t)a.ntiles_mine * RENDER_THREADS;
     int depth = 0;
     int status = ST_FRESH;
     // f32 only: the path's radiance accumulated forwards (A + T (.) L), the running minimum of
@@ -260,6 +263,13 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
                 acc1 += (double)L.y;
                 acc2 += (double)L.z;
                 s++;
+                if (a.nchunks > 1 && (--chunk_left == 0 || s == s_end)) {  // chunk complete: publish its sum
+                    double* o = a.partial + ((size_t)chunk_id * pstride + pslot) * 3;
+                    o[0] = acc0; o[1] = acc1; o[2] = acc2;
+                    acc0 = acc1 = acc2 = 0.0;
+                    chunk_id++;
+                    chunk_left = a.chunk;
+                }
                 status = ST_FRESH;
             }
             if (status == ST_FRESH) {
@@ -337,10 +347,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
     }
 
     // color / iterations * 2^EV  (renderer.rs:141)
-    if (a.nchunks > 1) {  // partial sum of this chunk; resolve_chunks_kernel finishes the pixel
-        const size_t slot = (size_t)blockIdx.x * RENDER_THREADS + threadIdx.x;
-        double* o = a.partial + ((size_t)blockIdx.y * ((size_t)a.ntiles_mine * RENDER_THREADS) + slot) * 3;
-        o[0] = acc0; o[1] = acc1; o[2] = acc2;
+    if (a.nchunks > 1) {
+        // the chunk sums were published as they completed; resolve_chunks_kernel finishes the pixel
     } else {
         const double it = (double)a.iterations;
         R* out = a.out + 3 * (size_t)pix;

@@ -15,7 +15,7 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
         nl++;
     }
     if (args.ntiles_mine > 0) {
-        const dim3 grid(args.ntiles_mine, args.nchunks), block(RENDER_THREADS);
+        const dim3 grid(args.ntiles_mine, args.ngroups), block(RENDER_THREADS);
         if (args.max_bounces <= 16) {
             if (stats) render_kernel<R, 16, true><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);

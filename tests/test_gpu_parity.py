@@ -465,3 +465,21 @@ def test_wavefront_shards_and_determinism(cfgs):
         segs += sti["segments"]
     np.testing.assert_array_equal(acc, full)
     assert segs == st["segments"]
+
+
+def test_sample_chunks_keep_shards_bit_identical(cfgs):
+    """150 spp = 3 chunks of 64/64/22 samples: however the chunks are grouped over CTAs (the grouping
+    depends on how many tiles a shard owns), the chunk sums and their resolve order are fixed."""
+    cfg, flat, ds = cfgs("sphere")
+    w, h, spp, mb = 40, 24, 150, 2
+    for prec in (F32, F64):
+        full, st = _gpu_render(cfg, ds, w, h, spp, mb, 5, prec)
+        acc = np.zeros_like(full)
+        for i in range(3):
+            acc += _gpu_render(cfg, ds, w, h, spp, mb, 5, prec, shard=(i, 3))[0]
+        np.testing.assert_array_equal(acc, full)
+    # and two half-ranges average to the whole (first_sample offsets the Philox sample index)
+    a, _ = _gpu_render(cfg, ds, w, h, 128, mb, 5, F64)
+    lo, _ = _gpu_render(cfg, ds, w, h, 64, mb, 5, F64, first_sample=0)
+    hi, _ = _gpu_render(cfg, ds, w, h, 64, mb, 5, F64, first_sample=64)
+    np.testing.assert_allclose((lo + hi) / 2, a, rtol=1e-12)
