@@ -403,7 +403,7 @@ def run_native(args):
             "gpu_launches": launches_per_step * K,
             "roofline": {
                 "bound": "hbm",
-                "kernel": "rptb::render_kernel<float,16,false> (megakernel: the step's one launch)" if engine != 2 else
+                "kernel": "rptb::render_kernel<float,16,false,FEAT> (megakernel: one launch per step, + chunk resolve)" if engine != 2 else
                           "rptb::wf_trace_kernel<false> (+ wf_shade_kernel; wavefront engine: the duration is the whole step's kernels)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(cfg.name), "peak_source": peak_src,

@@ -376,6 +376,7 @@ struct rptb_scene {
     std::mutex lock;
     uint64_t f32_bytes = 0;
     // wavefront engine: scratch memory (path state, rays, hits) cached between calls
+    int features = 0;               // F_TREE | F_TRANSP | F_HDRI actually present in the scene
     bool has_tree = false;          // some mesh's kd-tree is more than one leaf
     uint64_t tree_nodes = 0;        // kd nodes over all meshes
     double wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};  // world bounds of the meshes
@@ -536,6 +537,10 @@ int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
     }
     for (uint32_t i = 0; i < d->nlights; i++)
         if (d->lights[i].kind != RPTB_LIGHT_AMBIENT) s->sampled_lights++;
+    if (s->has_tree) s->features |= F_TREE;
+    for (uint32_t i = 0; i < d->nmaterials; i++)
+        if (d->materials[i].transparent) s->features |= F_TRANSP;
+    if (d->environment.kind == RPTB_ENV_HDRI) s->features |= F_HDRI;
     CU(pool_alloc((void**)&s->counters, sizeof(DeviceCounters), s->stream));
     CU(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), s->stream));
     CU(cudaEventCreate(&s->ev0));
@@ -644,9 +649,15 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         a.out = out32;
         a.counters = want_counters ? s->counters : nullptr;
         if (use_wavefront(s, p)) {
-            const uint32_t npaths = a.ntiles_mine * 128u;
+            const uint32_t npix = a.ntiles_mine * 128u;
+            const uint32_t G = wavefront_groups(npix, a.nchunks);
+            const uint32_t npaths = npix * G;
             const uint32_t maxd = p->max_bounces > 0 ? p->max_bounces : 1;
             const size_t need = wavefront_bytes(npaths, s->sampled_lights, maxd);
+            {
+                const int rc = ensure_partial(s, a);
+                if (rc != RPTB_OK) return rc;
+            }
             if (need > s->wf_bytes) {
                 if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
                 s->wf_mem = nullptr;
@@ -663,12 +674,12 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
                 blo[r] = (float)s->wlo[r];
                 binv[r] = (float)(ext > 0 && std::isfinite(ext) ? 1.0 / ext : 0.0);
             }
-            wavefront_carve(s->wf_mem, npaths, s->sampled_lights, maxd, blo, binv, (WfBuffers*)bufs.data());
+            wavefront_carve(s->wf_mem, npix, G, s->sampled_lights, maxd, blo, binv, (WfBuffers*)bufs.data());
             CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, stream, s->wf_pinned, launches));
         } else {
             const int rc = ensure_partial(s, a);
             if (rc != RPTB_OK) return rc;
-            CU(launch_render_f32(s->view32, a, p->collect_stats != 0, stream, launches));
+            CU(launch_render_f32(s->view32, a, p->collect_stats != 0, s->features, stream, launches));
         }
     } else {
         RenderArgs<double> a;
@@ -677,7 +688,7 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         a.counters = want_counters ? s->counters : nullptr;
         const int rc = ensure_partial(s, a);
         if (rc != RPTB_OK) return rc;
-        CU(launch_render_f64(s->view64, a, p->collect_stats != 0, stream, launches));
+        CU(launch_render_f64(s->view64, a, p->collect_stats != 0, F_ALL, stream, launches));
     }
     return RPTB_OK;
 }

@@ -213,9 +213,9 @@ RPTB_D uint32_t node_first_ref(const KdNodeDev64& n) { return n.first_ref; }
 // KdTree::intersect.  `o`,`d` are in the mesh's local space (d not normalised, so
 // t is the world t).  Returns true if some triangle tightened h.t.  `any` = shadow
 // query: return at the first leaf that produced a hit.
-template <class R, bool STATS>
+template <class R, bool STATS, int FEAT = F_ALL>
 RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
-    if (!M<R>::literal && m.root_is_leaf) {
+    if (!M<R>::literal && (m.root_is_leaf || !(FEAT & F_TREE))) {
         // f32 only (the f64 gate keeps the reference's control flow).  A tree that is one leaf (e.g. every `polygon` of the Cornell box): the root cull
         // of kdtree.rs:130-134 can only prune, never change the hit, so all lanes test the
         // few triangles directly -- no divergent slab test.
@@ -230,6 +230,7 @@ RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, bool
         }
         return hit;
     }
+    if constexpr (!(FEAT & F_TREE) && !M<R>::literal) return false;  // (unreachable: compiled for tree-less scenes)
     // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
     R lo, hi;
     Vec3<R> inv;
@@ -314,7 +315,7 @@ RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, bool
 }
 
 // ------------------------------------------------------- object dispatch ------
-template <class R, bool STATS>
+template <class R, bool STATS, int FEAT = F_ALL>
 RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> o, Vec3<R> d, R tmin, bool any,
                              Hit<R>& h, TravStats& ts) {
     if (ob.has_transform) {  // Ray::apply_transform(inverse_transform)
@@ -327,7 +328,7 @@ RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec
         case SHAPE_SPHERE: return sphere_intersect(o, d, tmin, h.t);
         case SHAPE_PLANE: return plane_intersect(ob.plane_n, ob.plane_v, o, d, tmin, h.t);
         case SHAPE_CUBE: return cube_intersect(o, d, tmin, h.t, h.aux);
-        default: return kd_intersect<R, STATS>(sv.meshes[ob.mesh], o, d, tmin, any, h, ts);
+        default: return kd_intersect<R, STATS, FEAT>(sv.meshes[ob.mesh], o, d, tmin, any, h, ts);
     }
 }
 

@@ -59,7 +59,7 @@ struct PathCounters {
 // get_closest_hit: linear scan of scene.objects.  `any` = shadow query (the first
 // object with a hit at t < h.t ends the scan; the caller preloads h.t with the light
 // distance).
-template <class R, bool STATS>
+template <class R, bool STATS, int FEAT = F_ALL>
 RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
     h.obj = -1;
     h.aux = 0;
@@ -67,7 +67,7 @@ RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bo
     const uint32_t n = sv.nobjects;
     for (uint32_t i = 0; i < n; i++) {
         if (STATS) ts.object_tests++;
-        if (object_intersect<R, STATS>(sv, sv.objects[i], o, d, tmin, any, h, ts)) {
+        if (object_intersect<R, STATS, FEAT>(sv, sv.objects[i], o, d, tmin, any, h, ts)) {
             h.obj = (int)i;
             if (any) return;
         }
@@ -102,7 +102,7 @@ enum : int {
 // at the single get_closest_hit site; a lane with nothing to do in a slot (light sample
 // with provably zero contribution, path just ended) sits that trace out.  Per lane the
 // order of operations -- and of random draws -- is exactly trace_ray's.
-template <class R, int MAXD, bool STATS>
+template <class R, int MAXD, bool STATS, int FEAT = F_ALL>
 __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
     const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
                     skip = zero_i || (!mat.transparent && M<R>::signbit(dot(n, wi)));
                 }
                 if (!skip) {
-                    const Vec3<R> f = bsdf(mat, n, wo, wi);
+                    const Vec3<R> f = bsdf<R, FEAT>(mat, n, wo, wi);
                     contrib = cmul(f, intensity) * dot(wi, n);  // renderer.rs:198-199 (signed cosine)
                     tmax = M<R>::next_up(dist);  // occluded iff some hit has t <= dist (renderer.rs:197)
                     ro = offset_origin(pos, ng, wi, err_scale);
@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
                 Vec3<R> wi = rd;
                 R pdf = (R)1;
                 bool bounce = false;
-                if ((uint32_t)depth < a.max_bounces && !dead) bounce = sample_f(mat, n, wo, rng, wi, pdf);
+                if ((uint32_t)depth < a.max_bounces && !dead) bounce = sample_f<R, FEAT>(mat, n, wo, rng, wi, pdf);
                 if (bounce) {  // renderer.rs:157-164
-                    const Vec3<R> f = bsdf(mat, n, wo, wi);
+                    const Vec3<R> f = bsdf<R, FEAT>(mat, n, wo, wi);
                     const R abscos = M<R>::abs(dot(wi, n));
                     Level<R>& lv = stack[depth];
                     lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
         h.obj = -1;
         if (active) {
             pc.rays++;
-            closest_hit<R, STATS>(sv, ro, rd, tmin, light_slot, h, pc.ts);
+            closest_hit<R, STATS, FEAT>(sv, ro, rd, tmin, light_slot, h, pc.ts);
         }
 
         // ================= consume the answer ============================================
@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel
             } else {
                 pc.segments++;  // one trace_ray invocation
                 if (h.obj < 0) {
-                    if (sv.env.kind != 0) pc.env_lookups++;
-                    Lterm = env_color(sv.env, rd);
+                    if ((FEAT & F_HDRI) && sv.env.kind != 0) pc.env_lookups++;
+                    Lterm = env_color<R, FEAT>(sv.env, rd);
                     status = ST_FINISH;
                 } else {
                     const ObjectRec<R>& ob = sv.objects[h.obj];

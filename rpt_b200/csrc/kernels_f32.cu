@@ -20,6 +20,14 @@ static size_t sort_temp_bytes(size_t slots) {
     return bytes;
 }
 
+// paths in flight per owned pixel slot: enough to keep ~2M paths alive, never more than there are chunks
+uint32_t wavefront_groups(uint32_t npix, uint32_t nchunks) {
+    if (npix == 0) return 1;
+    uint32_t g = (2000000u + npix - 1u) / npix;
+    if (g > nchunks) g = nchunks;
+    return g < 1u ? 1u : g;
+}
+
 size_t wavefront_bytes(uint32_t npaths, uint32_t Ks, uint32_t maxd) {
     const size_t n = npaths, slots = n * (Ks + 1);
     return align256(n * sizeof(WfPath)) + align256(n * Ks * 3 * sizeof(float) + 16) + align256(n * maxd * 6 * sizeof(float) + 16) +
@@ -27,8 +35,11 @@ size_t wavefront_bytes(uint32_t npaths, uint32_t Ks, uint32_t maxd) {
            align256(sort_temp_bytes(slots)) + 256;
 }
 
-void wavefront_carve(void* mem, uint32_t npaths, uint32_t Ks, uint32_t maxd, const float* bounds_lo,
+void wavefront_carve(void* mem, uint32_t npix, uint32_t G, uint32_t Ks, uint32_t maxd, const float* bounds_lo,
                      const float* bounds_inv_extent, WfBuffers* out) {
+    const uint32_t npaths = npix * G;
+    out->npix = npix;
+    out->G = G;
     char* p = (char*)mem;
     const size_t n = npaths, slots = n * (Ks + 1);
     out->paths = (WfPath*)p; p += align256(n * sizeof(WfPath));
@@ -84,8 +95,10 @@ cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float
     if (e != cudaSuccess) return e;
     const unsigned tgrid = (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
     // a sample with n <= max_bounces + 1 segments takes n + 1 steps (camera ray, one per vertex,
-    // and the step that consumes the last vertex's shadow rays and emits the next camera ray)
-    const unsigned long long max_steps = (unsigned long long)args.iterations * (args.max_bounces + 2ull) + 2ull;
+    // and the step that consumes the last vertex's shadow rays and emits the next camera ray); a path
+    // runs ceil(nchunks / G) chunks of `chunk` samples
+    const unsigned long long per_path = (unsigned long long)((args.nchunks + b.G - 1) / b.G) * args.chunk;
+    const unsigned long long max_steps = (per_path < args.iterations ? per_path : args.iterations) * (args.max_bounces + 2ull) + 2ull;
     for (unsigned long long step = 0; step < max_steps; step++) {
         e = cudaMemsetAsync(b.count, 0, 2 * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return e;
@@ -112,7 +125,8 @@ cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float
             if (*pinned == 0) break;
         }
     }
-    wf_finish_kernel<<<pgrid, WF_THREADS, 0, stream>>>(args, b);
+    if (args.nchunks > 1) resolve_chunks_kernel<float><<<args.ntiles_mine, RENDER_THREADS, 0, stream>>>(args);
+    else wf_finish_kernel<<<pgrid, WF_THREADS, 0, stream>>>(args, b);
     nl++;
     if (launches) *launches = nl;
     return cudaGetLastError();

@@ -7,7 +7,7 @@ namespace rptb {
 
 #define RPTB_DECLARE_LAUNCHERS(SUFFIX, R)                                                                          \
     cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats,              \
-                                       cudaStream_t stream, uint32_t* launches);                                   \
+                                       int features, cudaStream_t stream, uint32_t* launches);                     \
     cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,   \
                                             double* out_t, int32_t* out_obj, double* out_n,                        \
                                             DeviceCounters* counters, bool stats, cudaStream_t stream);            \
@@ -24,8 +24,9 @@ struct WfBuffers;
 // bytes of device memory the engine needs for (npaths, Ks sampled lights, maxd levels)
 size_t wavefront_bytes(uint32_t npaths, uint32_t Ks, uint32_t maxd);
 // carve `mem` (wavefront_bytes big, 256-byte aligned) into the engine's arrays
-void wavefront_carve(void* mem, uint32_t npaths, uint32_t Ks, uint32_t maxd, const float* bounds_lo,
+void wavefront_carve(void* mem, uint32_t npix, uint32_t G, uint32_t Ks, uint32_t maxd, const float* bounds_lo,
                      const float* bounds_inv_extent, WfBuffers* out);
+uint32_t wavefront_groups(uint32_t npix, uint32_t nchunks);
 size_t wavefront_struct_size();
 // run Renderer::sample with the wavefront schedule; blocks until the image is in args.out
 // (the step loop is driven from the host).  `pinned` = 4 bytes of page-locked host memory.

@@ -6,8 +6,8 @@
 namespace rptb {
 
 template <class R>
-cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats, cudaStream_t stream,
-                               uint32_t* launches) {
+cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats, int features,
+                               cudaStream_t stream, uint32_t* launches) {
     uint32_t nl = 0;
     const size_t nvals = (size_t)args.width * args.height * 3;
     if (args.shard_count > 1) {  // other shards' pixels must read as zero
@@ -18,6 +18,7 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
         const dim3 grid(args.ntiles_mine, args.ngroups), block(RENDER_THREADS);
         if (args.max_bounces <= 16) {
             if (stats) render_kernel<R, 16, true><<<grid, block, 0, stream>>>(sv, args);
+            else if (!M<R>::literal && features == 0) render_kernel<R, 16, false, 0><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
         } else {
             if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true><<<grid, block, 0, stream>>>(sv, args);
@@ -61,8 +62,8 @@ cudaError_t launch_sample_f_impl(const MaterialRec<R>& m, const double* dirs, ui
 
 #define RPTB_DEFINE_LAUNCHERS(SUFFIX, R)                                                                            \
     cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats,               \
-                                       cudaStream_t stream, uint32_t* launches) {                                   \
-        return launch_render_impl<R>(sv, args, stats, stream, launches);                                            \
+                                       int features, cudaStream_t stream, uint32_t* launches) {                     \
+        return launch_render_impl<R>(sv, args, stats, features, stream, launches);                                  \
     }                                                                                                               \
     cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,    \
                                             double* out_t, int32_t* out_obj, double* out_n,                         \

@@ -30,6 +30,11 @@ namespace rptb {
 enum : uint32_t { SHAPE_SPHERE = 0, SHAPE_PLANE = 1, SHAPE_CUBE = 2, SHAPE_MESH = 3 };
 enum : uint32_t { LIGHT_POINT = 0, LIGHT_AMBIENT = 1, LIGHT_DIRECTIONAL = 2, LIGHT_OBJECT = 3 };
 
+// Scene features a render kernel instantiation is compiled for.  The megakernel's hot loop is bound
+// by instruction issue and its instruction cache (ncu: `no_instruction` is the #2 stall), so scenes
+// that provably lack a feature run a variant with that code compiled out.
+enum : int { F_TREE = 1 /* kd-trees beyond one leaf */, F_TRANSP = 2 /* transparent materials */, F_HDRI = 4, F_ALL = 7 };
+
 constexpr int KD_STACK = 64;          // max kd-tree depth the traversal stack holds
 constexpr int MAX_CONST_OBJECTS = 96;  // tables up to this size live in __constant__ memory
 constexpr int MAX_CONST_LIGHTS = 16;

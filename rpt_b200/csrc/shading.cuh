@@ -58,22 +58,23 @@ RPTB_D Vec3<R> fresnel_f0(const MaterialRec<R>& m) {
 }
 
 // Material::bsdf (material.rs:125-210)
-template <class R>
+template <class R, int FEAT = F_ALL>
 RPTB_D Vec3<R> bsdf(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Vec3<R> wi) {
     const R n_dot_wi = dot(n, wi);
     const R n_dot_wo = dot(n, wo);
     const bool wi_outside = !M<R>::signbit(n_dot_wi);
     const bool wo_outside = !M<R>::signbit(n_dot_wo);
     const Vec3<R> one = mk((R)1, (R)1, (R)1);
-    if (!m.transparent && (!wi_outside || !wo_outside)) return mk((R)0, (R)0, (R)0);
+    constexpr bool TR = (FEAT & F_TRANSP) != 0;  // false: every material of the scene is opaque
+    if ((!TR || !m.transparent) && (!wi_outside || !wo_outside)) return mk((R)0, (R)0, (R)0);
     const R m2 = m.roughness * m.roughness;
-    if (wi_outside == wo_outside) {
+    if (!TR || wi_outside == wo_outside) {
         const Vec3<R> h = M<R>::normalize(wi + wo);
         const R wo_dot_h = dot(wo, h);
         const R n_dot_h = dot(n, h);
         const R d = beckmann_d(m2, n, h);
         Vec3<R> f;
-        if (!wi_outside && M<R>::sqrt((R)1 - wo_dot_h * wo_dot_h) * m.index > (R)1) {
+        if (TR && !wi_outside && M<R>::sqrt((R)1 - wo_dot_h * wo_dot_h) * m.index > (R)1) {
             f = one;  // total internal reflection
         } else {
             const Vec3<R> f0 = fresnel_f0(m);
@@ -83,7 +84,7 @@ RPTB_D Vec3<R> bsdf(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Vec3<R> wi) 
         g = ((R)2 * g) / wo_dot_h;
         g = M<R>::min(g, (R)1);
         const Vec3<R> specular = (d * f) * g / ((R)4 * n_dot_wo * n_dot_wi);
-        if (m.transparent) return specular;
+        if (TR && m.transparent) return specular;
         const Vec3<R> diffuse = cmul(one - f, mat_color(m)) / M<R>::pi();
         return specular + diffuse;
     } else {
@@ -155,8 +156,9 @@ RPTB_D R beckmann_pdf(R m2, Vec3<R> n, Vec3<R> h) {
 }
 
 // Material::sample_f (material.rs:224-313).  Returns false for `None` (TIR ends the path).
-template <class R>
+template <class R, int FEAT = F_ALL>
 RPTB_D bool sample_f(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Rng<R>& rng, Vec3<R>& wi_out, R& pdf_out) {
+    constexpr bool TR = (FEAT & F_TRANSP) != 0;
     const R m2 = m.roughness * m.roughness;
     const R r0 = (m.index - (R)1) / (m.index + (R)1);
     const R f0 = r0 * r0;
@@ -169,7 +171,7 @@ RPTB_D bool sample_f(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Rng<R>& rng
     if (gen_bool(rng, f)) {
         const Vec3<R> h = beckmann_sample(m2, n, rng);
         wi = -(wo - ((R)2 * dot(h, wo)) * h);  // -glm::reflect_vec(wo, h)
-    } else if (!m.transparent) {
+    } else if (!TR || !m.transparent) {
         R x, y;
         unit_disc(rng, x, y);
         const R z = M<R>::sqrt(M<R>::literal ? ((R)1 - x * x - y * y) : M<R>::max((R)1 - x * x - y * y, (R)0));
@@ -192,7 +194,7 @@ RPTB_D bool sample_f(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Rng<R>& rng
         p += f * p_h / ((R)4 * M<R>::abs(dot(h, wo)));
     }
     const R wi_dot_n = dot(wi, n);
-    if (!m.transparent) {
+    if (!TR || !m.transparent) {
         p += ((R)1 - f) * M<R>::max(wi_dot_n, (R)0) * ((R)1 / M<R>::pi());
     } else if (M<R>::signbit(wo_dot_n) != M<R>::signbit(wi_dot_n)) {
         const Vec3<R> h = M<R>::normalize(wi * eta_t + wo);
@@ -324,9 +326,9 @@ RPTB_D Vec3<R> env_texel(const EnvRec<R>& e, uint32_t x, uint32_t y) {
     const float4 t = __ldg(e.texels_f4 + (size_t)y * e.width + x);
     return mk((R)t.x, (R)t.y, (R)t.z);
 }
-template <class R>
+template <class R, int FEAT = F_ALL>
 RPTB_D Vec3<R> env_color(const EnvRec<R>& e, Vec3<R> dir_in) {
-    if (e.kind == 0) return mk(e.color[0], e.color[1], e.color[2]);
+    if (!(FEAT & F_HDRI) || e.kind == 0) return mk(e.color[0], e.color[1], e.color[2]);
     const Vec3<R> dir = M<R>::normalize(dir_in);
     R azimuth, polar;
     if (M<R>::literal) {

@@ -70,7 +70,8 @@ struct __align__(16) WfPath {
     uint32_t flags;  // bit0 dead, bit1 sample_f returned a direction, bit2 bounce ray emitted, bit3 fwd_ok, bits 8.. shadow mask
     float fwdA[3], fwdT0;
     float fwdT12[2], fwdTmin[2];
-    float fwdTmin2, _pad0;
+    float fwdTmin2;
+    uint32_t chunk_id;  // sample chunk this path is summing (scene_dev.cuh: RenderArgs::chunk)
     uint32_t rng_block, rng_avail;
     uint32_t rng_q[4];
     double acc[3];
@@ -92,7 +93,10 @@ struct WfBuffers {
     void* sort_tmp;
     size_t sort_tmp_bytes;
     float bounds_lo[3], bounds_inv[3];  // world bounds of the kd-tree meshes (key quantisation)
-    uint32_t npaths, Ks, maxd;
+    // npaths = npix * G: every owned pixel slot has G paths in flight, path (slot, g) sums the sample
+    // chunks g, g + G, g + 2G, ... one after the other (the chunk sums are resolved in chunk order, so
+    // the image does not depend on G -- which is chosen per launch to keep ~2M paths in flight)
+    uint32_t npaths, npix, G, Ks, maxd;
 };
 
 // Sort key of a ray: [shadow?:1][Morton code of the origin, 9 bits per axis, with the direction octant
@@ -123,8 +127,8 @@ __global__ void wf_key_kernel(const WfBuffers b, uint32_t capacity) {
     b.keys[i] = key;
 }
 
-RPTB_D void wf_pixel_of(const RenderArgs<float>& a, uint32_t p, uint32_t& x, uint32_t& y) {
-    const uint32_t k = p / RENDER_THREADS, tid = p % RENDER_THREADS;
+RPTB_D void wf_pixel_of(const RenderArgs<float>& a, uint32_t slot, uint32_t& x, uint32_t& y) {
+    const uint32_t k = slot / RENDER_THREADS, tid = slot % RENDER_THREADS;
     const uint32_t tile = a.shard_index + k * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const uint32_t warp = tid >> 5, lane = tid & 31u;
@@ -136,10 +140,12 @@ __global__ void wf_init_kernel(const RenderArgs<float> a, const WfBuffers b) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= b.npaths) return;
     uint32_t x, y;
-    wf_pixel_of(a, p, x, y);
+    wf_pixel_of(a, p % b.npix, x, y);
     WfPath st;
     memset(&st, 0, sizeof(st));
-    st.status = (x < a.width && y < a.height) ? WF_FRESH : WF_DONE;
+    st.chunk_id = p / b.npix;
+    st.s = st.chunk_id * a.chunk;
+    st.status = (x < a.width && y < a.height && st.s < a.iterations) ? WF_FRESH : WF_DONE;
     st.fwdT0 = 1.0f;
     st.fwdT12[0] = st.fwdT12[1] = 1.0f;
     st.fwdTmin[0] = st.fwdTmin[1] = st.fwdTmin2 = 1.0f;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade_kernel(const SceneView<fl
     const bool live = st.status != WF_DONE;
 
     uint32_t x = 0, y = 0;
-    if (in_range) wf_pixel_of(a, p, x, y);
+    if (in_range) wf_pixel_of(a, p % b.npix, x, y);
     const uint32_t pix = y * a.width + x;
     Rng<R> rng;
     rng.init(a.seed, pix, a.first_sample + st.s);
@@ -277,6 +283,16 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade_kernel(const SceneView<fl
             st.acc[1] += (double)L.y;
             st.acc[2] += (double)L.z;
             st.s++;
+            if (a.nchunks > 1) {
+                const uint32_t cend = min((st.chunk_id + 1u) * a.chunk, a.iterations);
+                if (st.s >= cend) {  // chunk complete: publish its sum, move on to this path's next chunk
+                    double* o = a.partial + ((size_t)st.chunk_id * b.npix + (p % b.npix)) * 3;
+                    o[0] = st.acc[0]; o[1] = st.acc[1]; o[2] = st.acc[2];
+                    st.acc[0] = st.acc[1] = st.acc[2] = 0.0;
+                    st.chunk_id += b.G;
+                    st.s = st.chunk_id * a.chunk;  // >= iterations when no chunk is left
+                }
+            }
             st.status = WF_FRESH;
         }
     }
@@ -630,7 +646,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kern
 
 __global__ void wf_finish_kernel(const RenderArgs<float> a, const WfBuffers b) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= b.npaths) return;
+    if (p >= b.npaths) return;  // (nchunks == 1 only: npaths == npix; otherwise resolve_chunks_kernel)
     uint32_t x, y;
     wf_pixel_of(a, p, x, y);
     if (x >= a.width || y >= a.height) return;

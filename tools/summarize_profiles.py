@@ -74,8 +74,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     traffic = {}
     obj = os.path.join(ROOT, "build", "obj", "kernels_f32.o")
-    jobs = [("%s_render_kernel_cornell" % R, "Cornell 800x800 (32 spp capture) -- rptb::render_kernel<float,16,false>",
-             "_ZN4rptb13render_kernelIfLi16ELb0EEEvNS_9SceneViewIT_EENS_10RenderArgsIS2_EE", "cornell",
+    jobs = [("%s_render_kernel_cornell" % R, "Cornell 800x800 (32 spp capture) -- rptb::render_kernel<float,16,false,0>",
+             "_ZN4rptb13render_kernelIfLi16ELb0ELi0EEEvNS_9SceneViewIT_EENS_10RenderArgsIS2_EE", "cornell",
              "Dominant kernel of the bench workload (BASELINE configs[1]); one launch per step per GPU."),
             ("%s_wf_trace_dragon" % R, "dragon-proxy 1920x1080 (4 spp capture) -- rptb::wf_trace_kernel<false>",
              "_ZN4rptb15wf_trace_kernelILb0EEEvNS_9SceneViewIfEENS_9WfBuffersEPKjPNS_14DeviceCountersE", "dragon-proxy",
