@@ -24,8 +24,14 @@
 namespace rptb {
 
 constexpr int RENDER_THREADS = 128;  // 4 warps: a 16x8 pixel tile
+// Resident CTAs/SM each instantiation is compiled for (register cap = 65536 / (128 * blocks)).
+// Measured, Msamples/s: full-feature kernel (glass) 5 -> 20.1 G, 6 -> 19.1 G;
+// feature-free kernel (Cornell) 4 -> 4060, 5 -> 4586, 6 -> 4784, 7 -> 4838, 8 -> 4927.
 #ifndef RPTB_MIN_BLOCKS
-#define RPTB_MIN_BLOCKS 5  // <= 102 registers: 20 warps/SM (measured +5 % over 4)
+#define RPTB_MIN_BLOCKS 5
+#endif
+#ifndef RPTB_MIN_BLOCKS_LITE
+#define RPTB_MIN_BLOCKS_LITE 8
 #endif
 constexpr int TILE_W = 16, TILE_H = 8;
 
@@ -103,7 +109,7 @@ enum : int {
 // with provably zero contribution, path just ended) sits that trace out.  Per lane the
 // order of operations -- and of random draws -- is exactly trace_ray's.
 template <class R, int MAXD, bool STATS, int FEAT = F_ALL>
-__global__ void __launch_bounds__(RENDER_THREADS, RPTB_MIN_BLOCKS) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
+__global__ void __launch_bounds__(RENDER_THREADS, FEAT == 0 ? RPTB_MIN_BLOCKS_LITE : RPTB_MIN_BLOCKS) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
     const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
