@@ -33,6 +33,15 @@ constexpr int RENDER_THREADS = 128;  // 4 warps: a 16x8 pixel tile
 #ifndef RPTB_MIN_BLOCKS_LITE
 #define RPTB_MIN_BLOCKS_LITE 8
 #endif
+#ifndef RPTB_MIN_BLOCKS_TREE
+#define RPTB_MIN_BLOCKS_TREE 8   // F_TREE only (teapot: 5 -> 5230, 6 -> 5426, 8 -> 5816 Msamples/s)
+#endif
+#ifndef RPTB_MIN_BLOCKS_GLASS
+#define RPTB_MIN_BLOCKS_GLASS 5  // F_TRANSP | F_HDRI, no trees (glass: flat, 19.2-19.4 G for 5/6/8)
+#endif
+constexpr int render_min_blocks(int feat) {
+    return feat == 0 ? RPTB_MIN_BLOCKS_LITE : feat == F_TREE ? RPTB_MIN_BLOCKS_TREE : feat == (F_TRANSP | F_HDRI) ? RPTB_MIN_BLOCKS_GLASS : RPTB_MIN_BLOCKS;
+}
 constexpr int TILE_W = 16, TILE_H = 8;
 
 template <class R>
@@ -109,7 +118,7 @@ enum : int {
 // with provably zero contribution, path just ended) sits that trace out.  Per lane the
 // order of operations -- and of random draws -- is exactly trace_ray's.
 template <class R, int MAXD, bool STATS, int FEAT = F_ALL>
-__global__ void __launch_bounds__(RENDER_THREADS, FEAT == 0 ? RPTB_MIN_BLOCKS_LITE : RPTB_MIN_BLOCKS) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
+__global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
     const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;

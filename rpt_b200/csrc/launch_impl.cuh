@@ -19,6 +19,8 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
         if (args.max_bounces <= 16) {
             if (stats) render_kernel<R, 16, true><<<grid, block, 0, stream>>>(sv, args);
             else if (!M<R>::literal && features == 0) render_kernel<R, 16, false, 0><<<grid, block, 0, stream>>>(sv, args);
+            else if (!M<R>::literal && features == F_TREE) render_kernel<R, 16, false, F_TREE><<<grid, block, 0, stream>>>(sv, args);
+            else if (!M<R>::literal && features == (F_TRANSP | F_HDRI)) render_kernel<R, 16, false, F_TRANSP | F_HDRI><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
         } else {
             if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true><<<grid, block, 0, stream>>>(sv, args);
