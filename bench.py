@@ -152,15 +152,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload_name: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture."""
+def ncu_traffic(workload_name: str, spp: int, engine: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed ncu capture (profiles/ncu_traffic.json); megakernel launches are scaled from the
+    capture's spp to the workload's (their DRAM traffic is per-sample local-memory traffic)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get(workload_name)
-        except Exception:
+    try:
+        rec = json.load(open(path)).get(workload_name)
+        if not isinstance(rec, dict):
             return None
-    return None
+        b = float(rec["dram_bytes_per_launch"])
+        return b if engine == 2 else b * spp / float(rec["capture_spp"])
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------ CPU arm -----------
@@ -406,7 +410,7 @@ def run_native(args):
                 "kernel": "rptb::render_kernel<float,16,false,FEAT> (megakernel: one launch per step, + chunk resolve)" if engine != 2 else
                           "rptb::wf_trace_kernel<false> (+ wf_shade_kernel; wavefront engine: the duration is the whole step's kernels)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(cfg.name), "peak_source": peak_src,
+                "traffic": ncu_traffic(cfg.name, spp_total, engine), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_all / world,
                 "bytes_model": "64*object_tests + 8*node_visits + 52*tri_tests + 36*mesh_hits + 32*segments + 64*env_lookups + 12*pixels",
                 "counters_per_step": total,

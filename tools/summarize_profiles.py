@@ -98,9 +98,13 @@ def main():
     tpath = os.path.join(OUT, "ncu_traffic.json")
     old = json.load(open(tpath)) if os.path.exists(tpath) else {}
     note = old.get("_note", {})
+    spp = {"cornell": 32, "dragon-proxy": 4}
     for k, v in traffic.items():
-        old[k] = v
-        note[k] = "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch in the %s capture (reduced spp: Cornell traffic is launch overhead + film write, independent of spp)" % R
+        old[k] = {"dram_bytes_per_launch": v, "capture_spp": spp[k]}
+        note[k] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel in the %s capture, "
+                   "taken at capture_spp samples per pixel (ncu replays a launch ~40 times).  The megakernel's traffic is "
+                   "its local-memory level stack and register spills and scales with spp; bench.py scales it to the "
+                   "workload's spp.  A wavefront trace launch covers one path-vertex step and does not depend on spp." % R)
     old["_note"] = note
     json.dump(old, open(tpath, "w"), indent=1)
 
