@@ -34,8 +34,11 @@ $(OBJDIR)/api.o: $(CSRC)/api.cu $(HDRS)
 $(OBJDIR)/kdbuild.o: $(CSRC)/kdbuild.cpp include/rpt_b200.h
 	@mkdir -p $(OBJDIR)
 	$(CXX) -std=c++17 -O3 -fPIC -fopenmp -Wall -c $< -o $@
+$(OBJDIR)/objparse.o: $(CSRC)/objparse.cpp
+	@mkdir -p $(OBJDIR)
+	$(CXX) -std=c++17 -O3 -fPIC -Wall -c $< -o $@
 
-$(LIB): $(OBJDIR)/kernels_f32.o $(OBJDIR)/kernels_f64.o $(OBJDIR)/film.o $(OBJDIR)/api.o $(OBJDIR)/kdbuild.o
+$(LIB): $(OBJDIR)/kernels_f32.o $(OBJDIR)/kernels_f64.o $(OBJDIR)/film.o $(OBJDIR)/api.o $(OBJDIR)/kdbuild.o $(OBJDIR)/objparse.o
 	@mkdir -p rpt_b200/lib
 	$(NVCC) -shared $(ARCH) -o $@ $^ -Xcompiler -fopenmp -lgomp -cudart shared
 

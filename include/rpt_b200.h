@@ -272,6 +272,17 @@ typedef struct rptb_kdtree_out {
 int rptb_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out);
 void rptb_free_kdtree(rptb_kdtree_out* out);
 
+/* Replaces: load_obj -> parse_obj_point / parse_obj_face (src/io.rs:27-73,151-200) on an in-memory
+ * .OBJ text.  *out_tris receives ntris x 18 doubles (v1 v2 v3 n1 n2 n3), the input Mesh::new takes;
+ * free with rptb_free_triangles.  Host side.                                              */
+int rptb_parse_obj(const char* text, uint64_t len, double** out_tris, uint64_t* out_ntris);
+void rptb_free_triangles(double* tris);
+
+/* Replaces: Buffer::variance (src/buffer.rs:59-73) for nbatches >= 2 equally weighted entries per
+ * pixel: batches = nbatches x npixels x 3 doubles; the mean over pixels of the per-pixel sample
+ * variance (n - 1 degrees of freedom) of the entries, summed over the three channels.   */
+int rptb_film_variance(const double* batches, uint32_t nbatches, uint64_t npixels, int device, double* out);
+
 /* Replaces: Buffer::image -> get_filtered_color -> color_bytes
  * (src/buffer.rs:43-56,75-93, src/color.rs:17-23) for a buffer holding
  * `nbatches` equally weighted entries per pixel (sums[] = per-pixel sum over

@@ -185,6 +185,9 @@ SYMBOLS = [
      [C.POINTER(Material), c_double_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, c_double_p, c_double_p]),
     ("rptb_build_kdtree", C.c_int, [c_double_p, C.c_uint64, C.POINTER(KdTreeOut)]),
     ("rptb_free_kdtree", None, [C.POINTER(KdTreeOut)]),
+    ("rptb_parse_obj", C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(c_double_p), C.POINTER(C.c_uint64)]),
+    ("rptb_free_triangles", None, [c_double_p]),
+    ("rptb_film_variance", C.c_int, [c_double_p, C.c_uint32, C.c_uint64, C.c_int, c_double_p]),
     ("rptb_film_resolve", C.c_int,
      [c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_u8_p]),
 ]

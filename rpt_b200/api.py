@@ -275,12 +275,27 @@ def parse_obj(lines) -> np.ndarray:
     return np.stack(tris) if tris else np.zeros((0, 18))
 
 
+def parse_obj_native(text) -> np.ndarray:
+    """The same parse through the library's C++ implementation (rptb_parse_obj): what load_obj uses."""
+    data = text.encode() if isinstance(text, str) else bytes(text)
+    lib = capi.lib()
+    out = capi.c_double_p()
+    n = C.c_uint64(0)
+    capi.check(lib.rptb_parse_obj(data, len(data), C.byref(out), C.byref(n)), "rptb_parse_obj")
+    try:
+        if n.value == 0:
+            return np.zeros((0, 18))
+        return np.ctypeslib.as_array(out, shape=(int(n.value), 18)).copy()
+    finally:
+        lib.rptb_free_triangles(out)
+
+
 def load_obj(path_or_file) -> Mesh:
     """src/io.rs:27-73."""
     if hasattr(path_or_file, "read"):
-        return Mesh(parse_obj(path_or_file))
-    with open(path_or_file, "r") as f:
-        return Mesh(parse_obj(f))
+        return Mesh(parse_obj_native(path_or_file.read()))
+    with open(path_or_file, "rb") as f:
+        return Mesh(parse_obj_native(f.read()))
 
 
 # ---------------------------------------------------------------- material ----
@@ -630,12 +645,16 @@ class Buffer:
         )
         return out
 
-    def variance(self) -> float:  # :59-73
-        b = np.stack(self.batches)  # (nb, npix, 3)
-        mean = b.mean(axis=0)
-        ss = ((b - mean) ** 2).sum(axis=2).sum(axis=0)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            return float(np.mean(ss / (len(self.batches) - 1.0)))
+    def variance(self) -> float:
+        """:59-73, on the device (rptb_film_variance).  With a single entry per pixel the reference
+        divides by n - 1 = 0 and returns NaN; so does this."""
+        if len(self.batches) < 2:
+            return float("nan")
+        b = np.ascontiguousarray(np.stack(self.batches))  # (nb, npix, 3)
+        out = C.c_double(0.0)
+        capi.check(capi.lib().rptb_film_variance(b.ctypes.data_as(capi.c_double_p), b.shape[0], b.shape[1],
+                                                 self.device, C.byref(out)), "rptb_film_variance")
+        return float(out.value)
 
 
 # ---------------------------------------------------------------- renderer ----

@@ -30,6 +30,8 @@ int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnod
 cudaError_t launch_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height,
                                 uint32_t radius, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_convert_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t stream);
+cudaError_t launch_film_variance(const double* batches, uint32_t nbatches, uint64_t npixels, double* out_sum, cudaStream_t stream);
+int parse_obj_text(const char* text, size_t len, std::vector<double>& tris, std::string& err);
 }  // namespace rptb
 
 using namespace rptb;
@@ -999,6 +1001,54 @@ void rptb_free_kdtree(rptb_kdtree_out* out) {
     std::free(out->nodes);
     std::free(out->refs);
     std::memset(out, 0, sizeof(*out));
+}
+
+int rptb_parse_obj(const char* text, uint64_t len, double** out_tris, uint64_t* out_ntris) {
+    if (!text || !out_tris || !out_ntris) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    *out_tris = nullptr;
+    *out_ntris = 0;
+    try {
+        std::vector<double> tris;
+        std::string err;
+        if (parse_obj_text(text, (size_t)len, tris, err) != 0) return fail(RPTB_ERR_BAD_ARG, "%s", err.c_str());
+        const size_t n = tris.size();
+        double* p = (double*)std::malloc(sizeof(double) * (n ? n : 1));
+        if (!p) return fail(RPTB_ERR_OOM, "host allocation failed");
+        std::memcpy(p, tris.data(), sizeof(double) * n);
+        *out_tris = p;
+        *out_ntris = n / 18;
+    } catch (const std::bad_alloc&) {
+        return fail(RPTB_ERR_OOM, "host allocation failed");
+    }
+    return RPTB_OK;
+}
+
+void rptb_free_triangles(double* tris) { std::free(tris); }
+
+int rptb_film_variance(const double* batches, uint32_t nbatches, uint64_t npixels, int device, double* out) {
+    if (!batches || !out) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    if (nbatches < 2) return fail(RPTB_ERR_BAD_ARG, "variance needs at least two entries per pixel");
+    if (npixels == 0) return fail(RPTB_ERR_BAD_ARG, "empty image");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RPTB_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RPTB_ERR_BAD_ARG, "device %d of %d", device, ndev);
+    DeviceGuard g(device);
+    const size_t n = (size_t)nbatches * npixels * 3;
+    double *d_in = nullptr, *d_out = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_in);
+        cudaFree(d_out);
+    };
+    CUC(cudaMalloc(&d_in, n * sizeof(double)));
+    CUC(cudaMalloc(&d_out, sizeof(double)));
+    CUC(cudaMemcpy(d_in, batches, n * sizeof(double), cudaMemcpyHostToDevice));
+    CUC(cudaMemset(d_out, 0, sizeof(double)));
+    CUC(launch_film_variance(d_in, nbatches, npixels, d_out, 0));
+    double sum = 0.0;
+    CUC(cudaMemcpy(&sum, d_out, sizeof(double), cudaMemcpyDeviceToHost));
+    cleanup();
+    *out = sum / (double)npixels;
+    return RPTB_OK;
 }
 
 int rptb_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height, uint32_t box_radius,

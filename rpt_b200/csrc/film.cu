@@ -44,6 +44,43 @@ __global__ void convert_f64_f32_kernel(const double* __restrict__ in, float* __r
     if (i < n) out[i] = (float)in[i];
 }
 
+// Buffer::variance (src/buffer.rs:59-73): per pixel, the sample variance (n - 1) of its `nbatches`
+// entries summed over the three channels; block-reduced and added to *out_sum (the caller divides by
+// the pixel count).  The block partials are added with atomics, so the last bits depend on the order.
+__global__ void film_variance_kernel(const double* __restrict__ batches, uint32_t nbatches, uint64_t npixels,
+                                     double* __restrict__ out_sum) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (p < npixels) {
+        double mean[3] = {0.0, 0.0, 0.0};
+        for (uint32_t b = 0; b < nbatches; b++)
+            for (int k = 0; k < 3; k++) mean[k] += batches[((size_t)b * npixels + p) * 3 + k];
+        for (int k = 0; k < 3; k++) mean[k] /= (double)nbatches;
+        double ss = 0.0;
+        for (uint32_t b = 0; b < nbatches; b++)
+            for (int k = 0; k < 3; k++) {
+                const double d = batches[((size_t)b * npixels + p) * 3 + k] - mean[k];
+                ss += d * d;
+            }
+        v = ss / ((double)nbatches - 1.0);
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __shared__ double warp_sum[8];
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (unsigned w = 0; w < blockDim.x / 32; w++) s += warp_sum[w];
+        atomicAdd(out_sum, s);
+    }
+}
+
+cudaError_t launch_film_variance(const double* batches, uint32_t nbatches, uint64_t npixels, double* out_sum,
+                                 cudaStream_t stream) {
+    film_variance_kernel<<<(unsigned)((npixels + 255) / 256), 256, 0, stream>>>(batches, nbatches, npixels, out_sum);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height,
                                 uint32_t radius, uint8_t* out, cudaStream_t stream) {
     const dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);

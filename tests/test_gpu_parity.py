@@ -488,3 +488,18 @@ def test_sample_chunks_keep_shards_bit_identical(cfgs):
     lo, _ = _gpu_render(cfg, ds, w, h, 64, mb, 5, F64, first_sample=0)
     hi, _ = _gpu_render(cfg, ds, w, h, 64, mb, 5, F64, first_sample=64)
     np.testing.assert_allclose((lo + hi) / 2, a, rtol=1e-12)
+
+
+def test_film_variance_matches_oracle(orc, gpu_ok):
+    """Buffer::variance (src/buffer.rs:59-73) on the device vs the CPU restatement."""
+    rng = np.random.default_rng(29)
+    batches = rng.uniform(0, 2, (5, 70 * 41, 3))
+    out = C.c_double(0.0)
+    capi.check(capi.lib().rptb_film_variance(batches.ctypes.data_as(capi.c_double_p), 5, 70 * 41, 0, C.byref(out)),
+               "rptb_film_variance")
+    np.testing.assert_allclose(out.value, orc.variance(batches), rtol=1e-12)
+    buf = api.Buffer(70, 41)
+    for b in batches:
+        buf.add_samples(b)
+    np.testing.assert_allclose(buf.variance(), orc.variance(batches), rtol=1e-12)
+    assert math.isnan(api.Buffer(2, 2).variance())  # fewer than two entries: n - 1 = 0 in the reference
