@@ -584,6 +584,13 @@ void fill_args(const rptb_camera* cam, const rptb_render_params* p, RenderArgs<R
     a.ntiles_mine = ntiles > a.shard_index ? (ntiles - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
     sample_chunks(p->iterations, a.nchunks, a.chunk);
     sample_groups(a.ntiles_mine, a.nchunks, a.ngroups, a.chunks_per_group);
+    if (const char* g = getenv("RPTB_GROUPS")) {  // tuning aid: force the number of sample groups
+        uint32_t want = (uint32_t)atoi(g);
+        if (want < 1) want = 1;
+        if (want > a.nchunks) want = a.nchunks;
+        a.chunks_per_group = (a.nchunks + want - 1) / want;
+        a.ngroups = (a.nchunks + a.chunks_per_group - 1) / a.chunks_per_group;
+    }
     a.partial = nullptr;
 }
 

@@ -159,11 +159,11 @@ inline void sample_chunks(uint32_t iterations, uint32_t& nchunks, uint32_t& chun
     nchunks = (iterations + chunk - 1u) / chunk;
     if (nchunks < 1u) nchunks = 1u;
 }
-// groups so that tiles * groups is at least ~4 waves of resident CTAs (148 SMs x 5 CTAs); measured on
-// Cornell 800x800x512: 1 group 4295, 2 groups 4177, 16 groups 4115 Msamples/s -- long runs per thread
-// have the smaller tail, so split no further than the machine needs
+// groups so that tiles * groups is about 10 waves of resident CTAs (148 SMs x 8 CTAs).  Measured on
+// Cornell 800x800x512 (5 000 tiles, 8 CTAs/SM): 1 group 4964, 2 -> 5047, 3 -> 5075, 4 -> 5036,
+// 8 -> 4931 Msamples/s: more CTAs shorten the grid's tail, longer runs per thread shorten the warp's.
 inline void sample_groups(uint32_t ntiles, uint32_t nchunks, uint32_t& ngroups, uint32_t& chunks_per_group) {
-    const uint32_t want = ntiles ? (3000u + ntiles - 1u) / ntiles : 1u;
+    const uint32_t want = ntiles ? (12000u + ntiles - 1u) / ntiles : 1u;
     ngroups = want < 1u ? 1u : (want > nchunks ? nchunks : want);
     chunks_per_group = (nchunks + ngroups - 1u) / ngroups;
     ngroups = (nchunks + chunks_per_group - 1u) / chunks_per_group;
