@@ -214,7 +214,36 @@ RPTB_D uint32_t node_first_ref(const KdNodeDev64& n) { return n.first_ref; }
 // t is the world t).  Returns true if some triangle tightened h.t.  `any` = shadow
 // query: return at the first leaf that produced a hit.
 template <class R, bool STATS, int FEAT = F_ALL>
-RPTB_D bool kd_intersect(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
+RPTB_D bool kd_intersect(const SceneView<R>& sv, const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h,
+                         TravStats& ts) {
+    if constexpr ((FEAT & F_SMALL) != 0 && !M<R>::literal) if (m.root_is_leaf) {
+        // one-leaf mesh, triangles in parameter space: Triangle::intersect as in tri_intersect(float)
+        bool hit = false;
+        if (STATS) ts.node_visits++;
+        const uint32_t base = m.small_tri_base;
+        for (uint32_t tri = 0; tri < m.ntris; tri++) {
+            if (STATS) ts.tri_tests++;
+            const float4 q0 = sv.small.tri48[3 * (base + tri)];
+            const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+            if (fabsf(cosine) < 1e-8f) continue;
+            const float time = __fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+            if (time < tmin || time >= h.t) continue;
+            const float4 q1 = sv.small.tri48[3 * (base + tri) + 1];
+            const float4 q2 = sv.small.tri48[3 * (base + tri) + 2];
+            const float px = fmaf(time, d.x, o.x), py = fmaf(time, d.y, o.y), pz = fmaf(time, d.z, o.z);
+            const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
+            const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
+            const float u = 1.0f - v - w;
+            if (u >= 0.0f && v >= 0.0f && w >= 0.0f) {
+                h.t = time;
+                h.bv = v;
+                h.bw = w;
+                h.aux = tri;
+                hit = true;
+            }
+        }
+        return hit;
+    }
     if (!M<R>::literal && (m.root_is_leaf || !(FEAT & F_TREE))) {
         // f32 only (the f64 gate keeps the reference's control flow).  A tree that is one leaf (e.g. every `polygon` of the Cornell box): the root cull
         // of kdtree.rs:130-134 can only prune, never change the hit, so all lanes test the
@@ -328,7 +357,9 @@ RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec
         case SHAPE_SPHERE: return sphere_intersect(o, d, tmin, h.t);
         case SHAPE_PLANE: return plane_intersect(ob.plane_n, ob.plane_v, o, d, tmin, h.t);
         case SHAPE_CUBE: return cube_intersect(o, d, tmin, h.t, h.aux);
-        default: return kd_intersect<R, STATS, FEAT>(sv.meshes[ob.mesh], o, d, tmin, any, h, ts);
+        default:
+            if constexpr ((FEAT & F_SMALL) != 0 && !M<R>::literal) return kd_intersect<R, STATS, FEAT>(sv, sv.small.meshes[ob.mesh], o, d, tmin, any, h, ts);
+            else return kd_intersect<R, STATS, FEAT>(sv, sv.meshes[ob.mesh], o, d, tmin, any, h, ts);
     }
 }
 

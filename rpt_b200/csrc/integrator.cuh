@@ -40,7 +40,8 @@ constexpr int RENDER_THREADS = 128;  // 4 warps: a 16x8 pixel tile
 #define RPTB_MIN_BLOCKS_GLASS 5  // F_TRANSP | F_HDRI, no trees (glass: flat, 19.2-19.4 G for 5/6/8)
 #endif
 constexpr int render_min_blocks(int feat) {
-    return feat == 0 ? RPTB_MIN_BLOCKS_LITE : feat == F_TREE ? RPTB_MIN_BLOCKS_TREE : feat == (F_TRANSP | F_HDRI) ? RPTB_MIN_BLOCKS_GLASS : RPTB_MIN_BLOCKS;
+    const int base = feat & F_ALL;  // F_SMALL does not change the register budget
+    return base == 0 ? RPTB_MIN_BLOCKS_LITE : base == F_TREE ? RPTB_MIN_BLOCKS_TREE : base == (F_TRANSP | F_HDRI) ? RPTB_MIN_BLOCKS_GLASS : RPTB_MIN_BLOCKS;
 }
 constexpr int TILE_W = 16, TILE_H = 8;
 
@@ -82,7 +83,10 @@ RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bo
     const uint32_t n = sv.nobjects;
     for (uint32_t i = 0; i < n; i++) {
         if (STATS) ts.object_tests++;
-        if (object_intersect<R, STATS, FEAT>(sv, sv.objects[i], o, d, tmin, any, h, ts)) {
+        bool hit;
+        if constexpr ((FEAT & F_SMALL) != 0 && !M<R>::literal) hit = object_intersect<R, STATS, FEAT>(sv, sv.small.objects[i], o, d, tmin, any, h, ts);
+        else hit = object_intersect<R, STATS, FEAT>(sv, sv.objects[i], o, d, tmin, any, h, ts);
+        if (hit) {
             h.obj = (int)i;
             if (any) return;
         }
@@ -102,6 +106,13 @@ RPTB_D Vec3<double> offset_origin(Vec3<double> p, Vec3<double>, Vec3<double>, do
 template <class R>
 RPTB_D R max_abs3(Vec3<R> a) { return M<R>::max(M<R>::max(M<R>::abs(a.x), M<R>::abs(a.y)), M<R>::abs(a.z)); }
 
+// scene.lights[i]: from parameter space when the scene's tables ride in the kernel parameters
+template <int FEAT, class R>
+RPTB_D const LightRec<R>& scene_light(const SceneView<R>& sv, uint32_t i) {
+    if constexpr ((FEAT & F_SMALL) != 0 && !M<R>::literal) return sv.small.lights[i];
+    else return sv.lights[i];
+}
+
 // Per-lane status in the flattened trace_ray recursion.
 enum : int {
     ST_FRESH = 0,   // needs a camera ray (start of get_color's next sample)
@@ -118,7 +129,7 @@ enum : int {
 // with provably zero contribution, path just ended) sits that trace out.  Per lane the
 // order of operations -- and of random draws -- is exactly trace_ray's.
 template <class R, int MAXD, bool STATS, int FEAT = F_ALL>
-__global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) render_kernel(const SceneView<R> sv, const RenderArgs<R> a) {
+__global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) render_kernel(const __grid_constant__ SceneView<R> sv, const __grid_constant__ RenderArgs<R> a) {
     const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
     const R yn = ((R)(2u * (a.height - y) - 1u) - (R)a.height) / dim;
 
     uint32_t Ks = 0;  // lights that need a shadow ray (warp-uniform)
-    for (uint32_t i = 0; i < sv.nlights; i++) Ks += sv.lights[i].kind != LIGHT_AMBIENT ? 1u : 0u;
+    for (uint32_t i = 0; i < sv.nlights; i++) Ks += scene_light<FEAT>(sv, i).kind != LIGHT_AMBIENT ? 1u : 0u;
 
     PathCounters pc = {0, 0, 0, 0, {0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -178,12 +189,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
             // ================= sample_lights, one sampled light per slot ==================
             if (status == ST_VERTEX && !dead) {
                 const MaterialRec<R> mat = sv.materials[mat_id];
-                while (sv.lights[li].kind == LIGHT_AMBIENT) {  // ambient lights listed before it
-                    const LightRec<R>& l = sv.lights[li];
+                while (scene_light<FEAT>(sv, li).kind == LIGHT_AMBIENT) {  // ambient lights listed before it
+                    const LightRec<R>& l = scene_light<FEAT>(sv, li);
                     color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
                     li++;
                 }
-                const LightRec<R>& l = sv.lights[li];
+                const LightRec<R>& l = scene_light<FEAT>(sv, li);
                 li++;
                 Vec3<R> intensity, wi;
                 R dist;
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
             if (status == ST_VERTEX) {
                 const MaterialRec<R> mat = sv.materials[mat_id];
                 while (li < sv.nlights) {  // trailing ambient lights (and, for a dead vertex, all of them)
-                    const LightRec<R>& l = sv.lights[li];
+                    const LightRec<R>& l = scene_light<FEAT>(sv, li);
                     if (l.kind == LIGHT_AMBIENT) color = color + cmul(mk(l.color[0], l.color[1], l.color[2]), mat_color(mat));
                     li++;
                 }

@@ -33,7 +33,10 @@ enum : uint32_t { LIGHT_POINT = 0, LIGHT_AMBIENT = 1, LIGHT_DIRECTIONAL = 2, LIG
 // Scene features a render kernel instantiation is compiled for.  The megakernel's hot loop is bound
 // by instruction issue and its instruction cache (ncu: `no_instruction` is the #2 stall), so scenes
 // that provably lack a feature run a variant with that code compiled out.
-enum : int { F_TREE = 1 /* kd-trees beyond one leaf */, F_TRANSP = 2 /* transparent materials */, F_HDRI = 4, F_ALL = 7 };
+enum : int {
+    F_TREE = 1 /* kd-trees beyond one leaf */, F_TRANSP = 2 /* transparent materials */, F_HDRI = 4, F_ALL = 7,
+    F_SMALL = 8 /* the scene tables fit SmallTables: read them from kernel-parameter (constant) space */
+};
 
 constexpr int KD_STACK = 64;          // max kd-tree depth the traversal stack holds
 constexpr int MAX_CONST_OBJECTS = 96;  // tables up to this size live in __constant__ memory
@@ -69,6 +72,8 @@ struct MeshRec {
     R bmin[3], bmax[3];   // KdTree::bounds
     uint32_t ntris;
     uint32_t root_is_leaf;
+    uint32_t small_tri_base;  // first triangle of this mesh in SmallTables::tri48 (one-leaf meshes, F_SMALL)
+    uint32_t _pad;
 };
 
 template <class R>
@@ -108,6 +113,22 @@ struct EnvRec {
     const double* texels_f64; // f64: packed rgb
 };
 
+// A small scene's warp-uniform tables, carried IN the kernel parameters (constant bank, up to 32 KB per
+// launch on sm_100): every lane of a warp walks scene.objects / scene.lights in lock step and tests
+// the same few triangles of one-leaf meshes, so these reads are uniform -- from parameter space they
+// are constant-cache broadcasts that need no LSU slot, no L1 tag look-up and no address registers.
+// Divergent accesses (the object / material of a lane's own hit) keep using the global copies.
+constexpr int SMALL_OBJECTS = 16, SMALL_LIGHTS = 4, SMALL_MESHES = 16, SMALL_TRIS = 64;
+template <class R>
+struct SmallTables {};  // f64 parity gate: not used
+template <>
+struct SmallTables<float> {
+    ObjectRec<float> objects[SMALL_OBJECTS];
+    LightRec<float> lights[SMALL_LIGHTS];
+    MeshRec<float> meshes[SMALL_MESHES];
+    float4 tri48[3 * SMALL_TRIS];  // one-leaf meshes only; MeshRec::small_tri_base indexes it
+};
+
 template <class R>
 struct SceneView {
     const ObjectRec<R>* objects;  // global copies (always valid)
@@ -115,8 +136,9 @@ struct SceneView {
     const MaterialRec<R>* materials;
     const MeshRec<R>* meshes;
     uint32_t nobjects, nlights, nmaterials, nmeshes;
-    uint32_t tables_in_const;  // objects+lights also staged in __constant__
+    uint32_t tables_in_const;  // F_SMALL: `small` is filled
     EnvRec<R> env;
+    SmallTables<R> small;
 };
 
 // Camera with the per-render invariants hoisted (src/camera.rs:64-81 recomputes
