@@ -13,8 +13,10 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <fstream>
 #include <functional>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -121,6 +123,59 @@ struct Object {  // Object::new(shape).material(m)
     Object material(Material m) && { mat = m; return std::move(*this); }
     Object material(Material m) const& { Object o = *this; o.mat = m; return o; }
 };
+
+// ---- mesh ingestion (src/io.rs:27-360); the parsing itself is the library's ----------------------
+namespace detail {
+inline std::string slurp(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("rpt: cannot open " + path);
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+inline Shape mesh_shape(const double* tris, uint64_t first, uint64_t n) {
+    Shape s;
+    s.kind = RPTB_SHAPE_MESH;
+    s.mesh = std::make_shared<Mesh>();
+    s.mesh->tris.assign(tris + 18 * first, tris + 18 * (first + n));
+    return s;
+}
+}  // namespace detail
+
+inline Shape load_obj(const std::string& path) {  // src/io.rs:27-73
+    const std::string text = detail::slurp(path);
+    double* tris = nullptr;
+    uint64_t n = 0;
+    if (rptb_parse_obj(text.data(), text.size(), &tris, &n) != 0) throw std::runtime_error(rptb_last_error());
+    Shape s = detail::mesh_shape(tris, 0, n);
+    rptb_free_triangles(tris);
+    return s;
+}
+
+inline Shape load_stl(const std::string& path) {  // src/io.rs:260-287
+    const std::string data = detail::slurp(path);
+    double* tris = nullptr;
+    uint64_t n = 0;
+    if (rptb_parse_stl(data.data(), data.size(), &tris, &n) != 0) throw std::runtime_error(rptb_last_error());
+    Shape s = detail::mesh_shape(tris, 0, n);
+    rptb_free_triangles(tris);
+    return s;
+}
+
+inline std::vector<Object> load_obj_with_mtl(const std::string& obj_path, const std::string& mtl_path) {  // src/io.rs:83-149
+    const std::string obj = detail::slurp(obj_path), mtl = detail::slurp(mtl_path);
+    rptb_obj_groups_out out;
+    if (rptb_parse_obj_mtl(obj.data(), obj.size(), mtl.data(), mtl.size(), &out) != 0) throw std::runtime_error(rptb_last_error());
+    std::vector<Object> objects;
+    for (uint64_t g = 0; g < out.ngroups; g++) {
+        const rptb_material& m = out.groups[g].material;
+        Object o(detail::mesh_shape(out.tris, out.groups[g].first_tri, out.groups[g].ntris));
+        o.mat = Material{{m.color[0], m.color[1], m.color[2]}, m.index, m.roughness, m.metallic, m.emittance, m.transparent != 0};
+        objects.push_back(std::move(o));
+    }
+    rptb_free_obj_groups(&out);
+    return objects;
+}
 
 struct Light {  // src/light.rs:7-19
     uint32_t kind;

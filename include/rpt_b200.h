@@ -278,6 +278,33 @@ void rptb_free_kdtree(rptb_kdtree_out* out);
 int rptb_parse_obj(const char* text, uint64_t len, double** out_tris, uint64_t* out_ntris);
 void rptb_free_triangles(double* tris);
 
+/* Replaces: load_obj_with_mtl + load_mtl (src/io.rs:83-149,202-258) on in-memory .OBJ and .MTL
+ * texts.  The reference returns Vec<Object>, one Mesh per run of faces between `usemtl` switches;
+ * here all triangles come back in file order (18 doubles each) and groups[g] names the run
+ * [first_tri, first_tri + ntris) with the Material load_mtl derived for it (Material::default(),
+ * src/material.rs:28-32, before the first `usemtl`).  Free with rptb_free_obj_groups.  Host side. */
+typedef struct rptb_obj_group {
+    rptb_material material;
+    uint64_t first_tri;
+    uint64_t ntris;
+} rptb_obj_group;
+typedef struct rptb_obj_groups_out {
+    double* tris;
+    uint64_t ntris;
+    rptb_obj_group* groups;
+    uint64_t ngroups;
+} rptb_obj_groups_out;
+int rptb_parse_obj_mtl(const char* obj_text, uint64_t obj_len, const char* mtl_text, uint64_t mtl_len,
+                       rptb_obj_groups_out* out);
+void rptb_free_obj_groups(rptb_obj_groups_out* out);
+
+/* Replaces: load_stl -> load_stl_ascii / load_stl_binary (src/io.rs:260-360) on the bytes of an .STL
+ * file: binary when len == 84 + 50 n (n = the u32 at byte 80), else ASCII when it starts with
+ * "solid ".  Each facet's stored normal is used for all three corners, unnormalised, as the
+ * reference does.  Unlike the reference's ASCII loop, a closing `endsolid` line is accepted.
+ * Free with rptb_free_triangles.  Host side.                                              */
+int rptb_parse_stl(const void* data, uint64_t len, double** out_tris, uint64_t* out_ntris);
+
 /* Replaces: Buffer::variance (src/buffer.rs:59-73) for nbatches >= 2 equally weighted entries per
  * pixel: batches = nbatches x npixels x 3 doubles; the mean over pixels of the per-pixel sample
  * variance (n - 1 degrees of freedom) of the entries, summed over the three channels.   */

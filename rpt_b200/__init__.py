@@ -6,12 +6,12 @@ rpt_b200/lib/librpt_b200.so (CUDA, sm_100a) behind the C ABI of include/rpt_b200
 """
 from .api import (Buffer, Camera, Cube, DeviceScene, Environment, Filter, FlatScene, Hdri, Light, Material, Mesh,
                   Object, Plane, Renderer, Scene, Shape, Sphere, Transformed, Triangle, color_bytes, cube, hex_color,
-                  load_obj, parse_obj, plane, polygon, sphere, vec3)
+                  load_mtl, load_obj, load_obj_with_mtl, load_stl, parse_obj, plane, polygon, sphere, vec3)
 from ._capi import PRECISION_F32, PRECISION_F64, RptbError
 
 __all__ = [
     "Buffer", "Camera", "Cube", "DeviceScene", "Environment", "Filter", "FlatScene", "Hdri", "Light", "Material",
     "Mesh", "Object", "Plane", "Renderer", "Scene", "Shape", "Sphere", "Transformed", "Triangle", "color_bytes",
-    "cube", "hex_color", "load_obj", "parse_obj", "plane", "polygon", "sphere", "vec3", "PRECISION_F32",
+    "cube", "hex_color", "load_mtl", "load_obj", "load_obj_with_mtl", "load_stl", "parse_obj", "plane", "polygon", "sphere", "vec3", "PRECISION_F32",
     "PRECISION_F64", "RptbError",
 ]

@@ -166,6 +166,19 @@ class KdTreeOut(C.Structure):
     ]
 
 
+class ObjGroup(C.Structure):
+    _fields_ = [("material", Material), ("first_tri", C.c_uint64), ("ntris", C.c_uint64)]
+
+
+class ObjGroupsOut(C.Structure):
+    _fields_ = [
+        ("tris", c_double_p),
+        ("ntris", C.c_uint64),
+        ("groups", C.POINTER(ObjGroup)),
+        ("ngroups", C.c_uint64),
+    ]
+
+
 # Every symbol include/rpt_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("rptb_last_error", C.c_char_p, []),
@@ -187,6 +200,9 @@ SYMBOLS = [
     ("rptb_free_kdtree", None, [C.POINTER(KdTreeOut)]),
     ("rptb_parse_obj", C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(c_double_p), C.POINTER(C.c_uint64)]),
     ("rptb_free_triangles", None, [c_double_p]),
+    ("rptb_parse_obj_mtl", C.c_int, [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(ObjGroupsOut)]),
+    ("rptb_free_obj_groups", None, [C.POINTER(ObjGroupsOut)]),
+    ("rptb_parse_stl", C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(c_double_p), C.POINTER(C.c_uint64)]),
     ("rptb_film_variance", C.c_int, [c_double_p, C.c_uint32, C.c_uint64, C.c_int, c_double_p]),
     ("rptb_film_resolve", C.c_int,
      [c_double_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, c_u8_p]),

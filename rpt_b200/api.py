@@ -298,6 +298,131 @@ def load_obj(path_or_file) -> Mesh:
         return Mesh(parse_obj_native(f.read()))
 
 
+def _read_bytes(path_or_file) -> bytes:
+    if hasattr(path_or_file, "read"):
+        data = path_or_file.read()
+        return data.encode() if isinstance(data, str) else bytes(data)
+    with open(path_or_file, "rb") as f:
+        return f.read()
+
+
+def _take_triangles(out, n) -> np.ndarray:
+    if n == 0:
+        return np.zeros((0, 18))
+    return np.ctypeslib.as_array(out, shape=(int(n), 18)).copy()
+
+
+def load_mtl(path_or_file) -> dict:
+    """src/io.rs:202-258: `newmtl` starts from Material.default(); Kd -> color, Ns -> roughness =
+    (2/(Ns+2))^(1/4), Ni -> index = max(Ni, 1+1e-4), d < 0.8 -> transparent; everything else is
+    ignored.  Pure-Python restatement (the native path is rptb_parse_obj_mtl); returns name -> Material."""
+    materials: dict = {}
+    current = None
+    for raw in _read_bytes(path_or_file).decode().split("\n"):
+        line = raw.strip()
+        if not line or line.startswith("#"):
+            continue
+        tok = line.split()
+        if tok[0] == "newmtl":
+            current = tok[1]
+            materials.setdefault(current, Material.default())
+            continue
+        if current is None:
+            raise ValueError("Material was not specified with `newmtl` before properties were added")
+        mat = materials[current]
+        if tok[0] == "Kd":
+            mat.color = vec3(float(tok[1]), float(tok[2]), float(tok[3]))
+        elif tok[0] == "Ns":
+            mat.roughness = math.sqrt(math.sqrt(2.0 / (float(tok[1]) + 2.0)))
+        elif tok[0] == "Ni":
+            mat.index = max(float(tok[1]), 1.0 + 1e-4)
+        elif tok[0] == "d":
+            if float(tok[1]) < 0.8:
+                mat.transparent = True
+    return materials
+
+
+def parse_obj_with_mtl(lines, materials: dict):
+    """Pure-Python restatement of the body of load_obj_with_mtl (src/io.rs:83-149), used to check
+    the native parser: returns [(Material, (n, 18) triangles)] in file order."""
+    groups = []
+    # `replay` holds every v / vn record seen so far, in place, plus the faces of the open run only, so
+    # parse_obj(replay) resolves relative indices exactly as the reference does at each face.
+    replay: List[str] = []
+    open_faces = 0
+    current_material = Material.default()
+    last_usemtl = None
+
+    def flush():
+        nonlocal replay, open_faces
+        if open_faces:
+            tris = parse_obj(replay)
+            if len(tris):  # a run whose faces produced no triangle is not an Object
+                groups.append((current_material, tris))
+            replay = [ln for ln in replay if ln.split()[0] != "f"]
+            open_faces = 0
+
+    for raw in lines:
+        line = raw.strip()
+        if not line or line.startswith("#"):
+            continue
+        tok = line.split()
+        if tok[0] in ("v", "vn"):
+            replay.append(line)
+        elif tok[0] == "f":
+            replay.append(line)
+            open_faces += 1
+        elif tok[0] == "usemtl":
+            if last_usemtl is None or last_usemtl != tok[1]:
+                flush()
+                if tok[1] not in materials:
+                    raise ValueError(f"Could not found `usemtl {tok[1]}` in library")
+                current_material = materials[tok[1]]
+                last_usemtl = tok[1]
+    flush()
+    return groups
+
+
+def load_obj_with_mtl(obj_file, mtl_file, build: bool = True) -> List["Object"]:
+    """src/io.rs:83-149: one Object(Mesh) per run of faces between `usemtl` switches, each carrying
+    the material load_mtl derived; `mtllib` lines are ignored (the .mtl is passed explicitly).
+    Parsed by the library (rptb_parse_obj_mtl)."""
+    obj, mtl = _read_bytes(obj_file), _read_bytes(mtl_file)
+    lib = capi.lib()
+    out = capi.ObjGroupsOut()
+    capi.check(lib.rptb_parse_obj_mtl(obj, len(obj), mtl, len(mtl), C.byref(out)), "rptb_parse_obj_mtl")
+    try:
+        tris = _take_triangles(out.tris, out.ntris)
+        objects = []
+        for g in range(int(out.ngroups)):
+            grp = out.groups[g]
+            m = grp.material
+            mat = Material(list(m.color), m.index, m.roughness, m.metallic, m.emittance, bool(m.transparent))
+            first, n = int(grp.first_tri), int(grp.ntris)
+            objects.append(Object(Mesh(tris[first:first + n], build=build)).material(mat))
+        return objects
+    finally:
+        lib.rptb_free_obj_groups(C.byref(out))
+
+
+def parse_stl_native(data: bytes) -> np.ndarray:
+    """src/io.rs:260-360 through the library (rptb_parse_stl): (n, 18) triangles, every corner
+    carrying its facet's stored normal."""
+    lib = capi.lib()
+    out = capi.c_double_p()
+    n = C.c_uint64(0)
+    capi.check(lib.rptb_parse_stl(data, len(data), C.byref(out), C.byref(n)), "rptb_parse_stl")
+    try:
+        return _take_triangles(out, n.value)
+    finally:
+        lib.rptb_free_triangles(out)
+
+
+def load_stl(path_or_file) -> Mesh:
+    """src/io.rs:260-287: binary or ASCII .STL -> Mesh."""
+    return Mesh(parse_stl_native(_read_bytes(path_or_file)))
+
+
 # ---------------------------------------------------------------- material ----
 class Material:
     """src/material.rs:7-26."""

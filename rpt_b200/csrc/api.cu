@@ -32,6 +32,13 @@ cudaError_t launch_film_resolve(const double* sums, uint32_t nbatches, uint32_t 
 cudaError_t launch_convert_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t stream);
 cudaError_t launch_film_variance(const double* batches, uint32_t nbatches, uint64_t npixels, double* out_sum, cudaStream_t stream);
 int parse_obj_text(const char* text, size_t len, std::vector<double>& tris, std::string& err);
+struct ObjGroup {
+    rptb_material material;
+    uint64_t first_tri, ntris;
+};
+int parse_obj_mtl_text(const char* obj, size_t obj_len, const char* mtl, size_t mtl_len, std::vector<double>& tris,
+                       std::vector<ObjGroup>& groups, std::string& err);
+int parse_stl_bytes(const void* data, size_t len, std::vector<double>& tris, std::string& err);
 }  // namespace rptb
 
 using namespace rptb;
@@ -1052,6 +1059,71 @@ int rptb_parse_obj(const char* text, uint64_t len, double** out_tris, uint64_t* 
 }
 
 void rptb_free_triangles(double* tris) { std::free(tris); }
+
+// Copies a triangle vector into a malloc'd block the caller frees with rptb_free_triangles.
+static double* export_triangles(const std::vector<double>& tris) {
+    const size_t n = tris.size();
+    double* p = (double*)std::malloc(sizeof(double) * (n ? n : 1));
+    if (p && n) std::memcpy(p, tris.data(), sizeof(double) * n);
+    return p;
+}
+
+int rptb_parse_obj_mtl(const char* obj_text, uint64_t obj_len, const char* mtl_text, uint64_t mtl_len,
+                       rptb_obj_groups_out* out) {
+    if (!obj_text || !mtl_text || !out) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    try {
+        std::vector<double> tris;
+        std::vector<ObjGroup> groups;
+        std::string err;
+        if (parse_obj_mtl_text(obj_text, (size_t)obj_len, mtl_text, (size_t)mtl_len, tris, groups, err) != 0)
+            return fail(RPTB_ERR_BAD_ARG, "%s", err.c_str());
+        double* t = export_triangles(tris);
+        rptb_obj_group* g = (rptb_obj_group*)std::malloc(sizeof(rptb_obj_group) * (groups.empty() ? 1 : groups.size()));
+        if (!t || !g) {
+            std::free(t);
+            std::free(g);
+            return fail(RPTB_ERR_OOM, "host allocation failed");
+        }
+        for (size_t i = 0; i < groups.size(); i++) {
+            g[i].material = groups[i].material;
+            g[i].first_tri = groups[i].first_tri;
+            g[i].ntris = groups[i].ntris;
+        }
+        out->tris = t;
+        out->ntris = tris.size() / 18;
+        out->groups = g;
+        out->ngroups = groups.size();
+    } catch (const std::bad_alloc&) {
+        return fail(RPTB_ERR_OOM, "host allocation failed");
+    }
+    return RPTB_OK;
+}
+
+void rptb_free_obj_groups(rptb_obj_groups_out* out) {
+    if (!out) return;
+    std::free(out->tris);
+    std::free(out->groups);
+    std::memset(out, 0, sizeof(*out));
+}
+
+int rptb_parse_stl(const void* data, uint64_t len, double** out_tris, uint64_t* out_ntris) {
+    if (!data || !out_tris || !out_ntris) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    *out_tris = nullptr;
+    *out_ntris = 0;
+    try {
+        std::vector<double> tris;
+        std::string err;
+        if (parse_stl_bytes(data, (size_t)len, tris, err) != 0) return fail(RPTB_ERR_BAD_ARG, "%s", err.c_str());
+        double* p = export_triangles(tris);
+        if (!p) return fail(RPTB_ERR_OOM, "host allocation failed");
+        *out_tris = p;
+        *out_ntris = tris.size() / 18;
+    } catch (const std::bad_alloc&) {
+        return fail(RPTB_ERR_OOM, "host allocation failed");
+    }
+    return RPTB_OK;
+}
 
 int rptb_film_variance(const double* batches, uint32_t nbatches, uint64_t npixels, int device, double* out) {
     if (!batches || !out) return fail(RPTB_ERR_BAD_ARG, "null argument");
