@@ -97,18 +97,41 @@ typedef enum rptb_shape_kind {
     RPTB_SHAPE_SPHERE = 0, /* src/shape/sphere.rs:13-64 */
     RPTB_SHAPE_PLANE = 1,  /* src/shape/plane.rs:17-32  */
     RPTB_SHAPE_CUBE = 2,   /* src/shape/cube.rs:20-87   */
-    RPTB_SHAPE_MESH = 3    /* src/kdtree.rs:129-143 + src/shape/mesh.rs:49-98 */
+    RPTB_SHAPE_MESH = 3,   /* src/kdtree.rs:129-143 + src/shape/mesh.rs:49-98 */
+    RPTB_SHAPE_MONOMIAL = 4, /* MonomialSurface{height, exp}: src/shape/monomial_surface.rs:13-123 */
+    RPTB_SHAPE_GROUP = 5   /* KdTree<Box<dyn Bounded>> over shapes: src/kdtree.rs:99-223 as used by
+                              examples/fractal_spheres.rs:43-47 and examples/fractal_teapots.rs:53-59 */
 } rptb_shape_kind;
 
 typedef struct rptb_object {
     uint32_t kind;          /* rptb_shape_kind */
     uint32_t material;      /* index into rptb_scene_desc.materials */
-    uint32_t mesh;          /* index into rptb_scene_desc.meshes (MESH only) */
+    uint32_t mesh;          /* MESH: index into rptb_scene_desc.meshes; GROUP: index into .groups */
     uint32_t has_transform; /* 0 = bare shape, 1 = Transformed<T> */
     double transform[16];   /* column-major */
     double plane_normal[3]; /* PLANE only: x . normal = value */
     double plane_value;
+    double monomial_height; /* MONOMIAL only: y = height * (x^2 + z^2)^(exp/2), x^2 + z^2 <= 1 */
+    double monomial_exp;    /* MONOMIAL only; the reference's intersect/normal assume 4       */
 } rptb_object;
+
+/* ---- KdTree<T: Bounded> over whole shapes (two-level instancing) -----------
+ * `children` are the tree's `objects` (src/kdtree.rs:100-104): Bounded shapes only -- SPHERE, CUBE,
+ * MESH, MONOMIAL, bare or Transformed (Plane has no bounding box; a GROUP inside a GROUP is
+ * RPTB_ERR_UNSUPPORTED).  Their `material` is ignored: the tree is ONE shape of ONE Object.  Many
+ * children may name the same mesh (the reference shares it through Arc<Mesh>).  `nodes`/`refs` are
+ * the tree serialised as in rptb_kdnode, refs = child indices; if `nodes` is NULL the library
+ * builds it with the reference's `construct` over the children's bounding boxes
+ * (Sphere [-1,1]^3, Cube [-.5,.5]^3, MonomialSurface (-1,0,-1)..(1,height,1), KdTree::bounds,
+ * Transformed = box of the 8 transformed corners, src/shape.rs:153-175).                      */
+typedef struct rptb_group {
+    const struct rptb_object* children;
+    uint64_t nchildren;
+    const rptb_kdnode* nodes;
+    uint64_t nnodes;
+    const uint32_t* refs;
+    uint64_t nrefs;
+} rptb_group;
 
 /* ---- Light: src/light.rs:7-19 -------------------------------------------- */
 typedef enum rptb_light_kind {
@@ -148,6 +171,9 @@ typedef struct rptb_scene_desc {
     const rptb_light* lights;   /* scene.lights, in order */
     uint32_t nlights;
     rptb_env environment;
+    const rptb_group* groups;   /* targets of GROUP objects (may be NULL when ngroups == 0) */
+    uint32_t ngroups;
+    uint32_t _pad;
 } rptb_scene_desc;
 
 /* ---- Camera: src/camera.rs:8-26 (same six fields) -------------------------- */
@@ -270,6 +296,9 @@ typedef struct rptb_kdtree_out {
     uint32_t max_leaf;
 } rptb_kdtree_out;
 int rptb_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out);
+/* The same `construct`, over arbitrary bounding boxes (6 doubles each: p_min, p_max): the tree of a
+ * KdTree<Box<dyn Bounded>> (rptb_group).  Host side.                                          */
+int rptb_build_kdtree_boxes(const double* boxes, uint64_t nboxes, rptb_kdtree_out* out);
 void rptb_free_kdtree(rptb_kdtree_out* out);
 
 /* Replaces: load_obj -> parse_obj_point / parse_obj_face (src/io.rs:27-73,151-200) on an in-memory

@@ -225,6 +225,8 @@ struct Rng {
         const uint64_t p_int = (uint64_t)(prob * 18446744073709551616.0);
         return p.next_u64() < p_int;
     }
+    // Rng::gen::<bool>() -> Standard: the sign bit of one 32-bit word; here the top bit of one u64 draw
+    bool gen_bool_std() { return (p.next_u64() >> 63) != 0; }
     // Uniform::from(0..n) for usize (widening-multiply rejection)
     uint64_t uniform_usize(uint64_t n) {
         const uint64_t ints_to_reject = (UINT64_MAX - n + 1) % n;
@@ -284,10 +286,41 @@ struct HitRecord {
     bool on_mesh = false;  // oracle-only bookkeeping for counters
 };
 
+// ------------------------------------------------- src/kdtree.rs:27-87 -----
+struct BoundingBox {
+    V3 p_min = {INF, INF, INF};
+    V3 p_max = {-INF, -INF, -INF};
+    BoundingBox merge(const BoundingBox& o) const { return BoundingBox{vmin(p_min, o.p_min), vmax(p_max, o.p_max)}; }
+    void intersect(const Ray& ray, double& t0, double& t1) const {  // :54-68
+        double x1 = (p_min.x - ray.origin.x) / ray.dir.x;
+        double x2 = (p_max.x - ray.origin.x) / ray.dir.x;
+        double a = std::fmin(x1, x2), b = std::fmax(x1, x2);
+        x1 = a; x2 = b;
+        double y1 = (p_min.y - ray.origin.y) / ray.dir.y;
+        double y2 = (p_max.y - ray.origin.y) / ray.dir.y;
+        a = std::fmin(y1, y2); b = std::fmax(y1, y2);
+        y1 = a; y2 = b;
+        double z1 = (p_min.z - ray.origin.z) / ray.dir.z;
+        double z2 = (p_max.z - ray.origin.z) / ray.dir.z;
+        a = std::fmin(z1, z2); b = std::fmax(z1, z2);
+        z1 = a; z2 = b;
+        t0 = std::fmax(std::fmax(x1, y1), z1);
+        t1 = std::fmin(std::fmin(x2, y2), z2);
+    }
+    void split(int axis, double value, BoundingBox& l, BoundingBox& r) const {  // :71-86
+        V3 mid_max = p_max; mid_max.at(axis) = value;
+        V3 mid_min = p_min; mid_min.at(axis) = value;
+        l = BoundingBox{p_min, mid_max};
+        r = BoundingBox{mid_min, p_max};
+    }
+};
+
 struct Shape {  // src/shape.rs:18-25
     virtual ~Shape() {}
     virtual bool intersect(const Ray& ray, double t_min, HitRecord& rec, Counters& c) const = 0;
     virtual void sample(const V3& target, Rng& rng, V3& v, V3& n, double& p) const = 0;
+    // trait Bounded (src/kdtree.rs:8-12); false = the shape does not implement it (Plane)
+    virtual bool bounding_box(BoundingBox&) const { return false; }
 };
 
 // ------------------------------------------- src/shape/sphere.rs:13-64 -----
@@ -327,6 +360,10 @@ struct Sphere : Shape {
         v = pt;
         nn = pt;
         p = z * (1.0 / PI);  // z * FRAC_1_PI
+    }
+    bool bounding_box(BoundingBox& b) const override {  // :67-74
+        b = BoundingBox{v3(-1.0, -1.0, -1.0), v3(1.0, 1.0, 1.0)};
+        return true;
     }
 };
 
@@ -404,34 +441,92 @@ struct Cube : Shape {
         }
         p = 1.0 / 6.0;
     }
+    bool bounding_box(BoundingBox& b) const override {  // :10-17
+        b = BoundingBox{v3(-0.5, -0.5, -0.5), v3(0.5, 0.5, 0.5)};
+        return true;
+    }
 };
 
-// ------------------------------------------------- src/kdtree.rs:27-87 -----
-struct BoundingBox {
-    V3 p_min = {INF, INF, INF};
-    V3 p_max = {-INF, -INF, -INF};
-    BoundingBox merge(const BoundingBox& o) const { return BoundingBox{vmin(p_min, o.p_min), vmax(p_max, o.p_max)}; }
-    void intersect(const Ray& ray, double& t0, double& t1) const {  // :54-68
-        double x1 = (p_min.x - ray.origin.x) / ray.dir.x;
-        double x2 = (p_max.x - ray.origin.x) / ray.dir.x;
-        double a = std::fmin(x1, x2), b = std::fmax(x1, x2);
-        x1 = a; x2 = b;
-        double y1 = (p_min.y - ray.origin.y) / ray.dir.y;
-        double y2 = (p_max.y - ray.origin.y) / ray.dir.y;
-        a = std::fmin(y1, y2); b = std::fmax(y1, y2);
-        y1 = a; y2 = b;
-        double z1 = (p_min.z - ray.origin.z) / ray.dir.z;
-        double z2 = (p_max.z - ray.origin.z) / ray.dir.z;
-        a = std::fmin(z1, z2); b = std::fmax(z1, z2);
-        z1 = a; z2 = b;
-        t0 = std::fmax(std::fmax(x1, y1), z1);
-        t1 = std::fmin(std::fmin(x2, y2), z2);
+// ------------------------------------ src/shape/monomial_surface.rs:13-187 --
+// y = height * (x^2 + z^2)^(exp/2) over the unit disc; intersect and the normals hard-code exp = 4,
+// as the reference does ("Normals and other things ... work only for exp=4 for now", :11).
+struct MonomialSurface : Shape {
+    double height = 1.0, exp = 4.0;
+    bool bounding_box(BoundingBox& b) const override {  // :179-186
+        b = BoundingBox{v3(-1.0, 0.0, -1.0), v3(1.0, height, 1.0)};
+        return true;
     }
-    void split(int axis, double value, BoundingBox& l, BoundingBox& r) const {  // :71-86
-        V3 mid_max = p_max; mid_max.at(axis) = value;
-        V3 mid_min = p_min; mid_min.at(axis) = value;
-        l = BoundingBox{p_min, mid_max};
-        r = BoundingBox{mid_min, p_max};
+    bool intersect(const Ray& ray, double t_min, HitRecord& rec, Counters&) const override {  // :21-105
+        BoundingBox bb;
+        bounding_box(bb);
+        double b_min, b_max;
+        bb.intersect(ray, b_min, b_max);
+        if (std::fmax(b_min, t_min) > std::fmin(b_max, rec.time)) return false;
+        auto dist = [&](double t) {
+            const double x = ray.origin.x + t * ray.dir.x;
+            const double y = ray.origin.y + t * ray.dir.y;
+            const double z = ray.origin.z + t * ray.dir.z;
+            return y - height * powi(x * x + z * z, 2);
+        };
+        const double coef0 = powi(ray.origin.x, 2) + powi(ray.origin.z, 2);
+        const double coef1 = 2. * (ray.origin.x * ray.dir.x + ray.origin.z * ray.dir.z);
+        const double coef2 = powi(ray.dir.x, 2) + powi(ray.dir.z, 2);
+        auto deriv = [&](double t) {
+            const double dy = 2. * coef0 * coef1 + 2. * t * (coef1 * coef1 + 2. * coef0 * coef2) +
+                              3. * powi(t, 2) * 2. * coef1 * coef2 + 4. * powi(t, 3) * coef2 * coef2;
+            return ray.dir.y - height * dy;
+        };
+        auto deriv2 = [&](double t) {
+            const double dy = 2. * (coef1 * coef1 + 2. * coef0 * coef2) + 3. * 2. * t * 2. * coef1 * coef2 +
+                              4. * 3. * powi(t, 2) * coef2 * coef2;
+            return -height * dy;
+        };
+        double t_max;
+        const bool maximize = dist(t_min) < 0.0;
+        if (maximize) {  // below the surface: Newton towards the maximum of dist along the ray
+            double cur_x = (b_min + b_max) / 2.;
+            for (int it = 0; it < 10; it++) {
+                const double f = dist(cur_x);
+                if (f > 0.) break;
+                const double der = deriv(cur_x);
+                const double der2 = deriv2(cur_x);
+                cur_x -= der / der2;
+            }
+            // (:62-64 prints a diagnostic here; no effect on the result)
+            t_max = cur_x;
+            if (t_max < t_min) return false;
+        } else {
+            t_max = 10000.;
+        }
+        if ((dist(t_min) < 0.0) == (dist(t_max) < 0.0)) return false;
+        double l = t_min, r = t_max;
+        for (int it = 0; it < 60; it++) {  // bisection :75-84
+            const double m = (l + r) / 2.0;
+            if ((dist(m) >= 0.0) == maximize) r = m;
+            else l = m;
+        }
+        if (r > rec.time) return false;
+        const V3 pos = ray.at(r);
+        if (pos.x * pos.x + pos.z * pos.z > 1.0) return false;  // outside the rim
+        rec.time = r;
+        rec.normal = normalize(v3(height * 4.0 * pos.x * (pos.x * pos.x + pos.z * pos.z), -1.0,
+                                  height * 4.0 * pos.z * (pos.x * pos.x + pos.z * pos.z)));
+        if (dot(rec.normal, ray.dir) > 0.0) rec.normal = -rec.normal;  // two-sided
+        rec.on_mesh = false;
+        return true;
+    }
+    void sample(const V3&, Rng& rng, V3& v, V3& n, double& p) const override {  // :107-122
+        // NB: UnitCircle -- the reference samples the RIM of the surface only (a quirk, kept)
+        double x, z;
+        rng.unit_circle(x, z);
+        const V3 pos = v3(x, height * std::pow(x * x + z * z, exp / 2.), z);
+        V3 normal = normalize(v3(height * 4. * pos.x * (pos.x * pos.x + pos.z * pos.z), -1.,
+                                 height * 4. * pos.z * (pos.x * pos.x + pos.z * pos.z)));
+        const double AREA = 6.3406654362;
+        if (rng.gen_bool_std()) normal = -normal;
+        v = pos;
+        n = normal;
+        p = 1. / (2. * AREA);
     }
 };
 
@@ -494,7 +589,8 @@ double median(const std::vector<double>& s) {  // :347-355
     return (s[mid] + s[mid - 1]) / 2.0;
 }
 
-std::unique_ptr<KdNode> construct(const std::vector<Triangle>& objects, std::vector<size_t> indices) {  // :235-345
+// `boxes[i]` = objects[i].bounding_box(): the reference recomputes it at every node, the value is the same.
+std::unique_ptr<KdNode> construct(const std::vector<BoundingBox>& boxes, std::vector<size_t> indices) {  // :235-345
     auto node = std::make_unique<KdNode>();
     if (indices.size() < 16) {
         node->indices = std::move(indices);
@@ -503,7 +599,7 @@ std::unique_ptr<KdNode> construct(const std::vector<Triangle>& objects, std::vec
     std::vector<double> xs, ys, zs;
     std::vector<BoundingBox> bboxs;
     for (size_t index : indices) {
-        const BoundingBox bb = objects[index].bounding_box();
+        const BoundingBox bb = boxes[index];
         xs.push_back(bb.p_min.x); xs.push_back(bb.p_max.x);
         ys.push_back(bb.p_min.y); ys.push_back(bb.p_max.y);
         zs.push_back(bb.p_min.z); zs.push_back(bb.p_max.z);
@@ -550,26 +646,65 @@ std::unique_ptr<KdNode> construct(const std::vector<Triangle>& objects, std::vec
     }
     node->kind = split_dir;
     node->value = m[split_dir];
-    node->left = construct(objects, std::move(left));
-    node->right = construct(objects, std::move(right));
+    node->left = construct(boxes, std::move(left));
+    node->right = construct(boxes, std::move(right));
     return node;
 }
 
-struct KdTree : Shape {  // KdTree<Triangle> = Mesh
+// What KdTree<T> needs from T (T: Bounded, src/kdtree.rs:106): Triangle, or any Bounded shape
+// behind a pointer (Box<dyn Bounded> / Arc<Mesh>, src/kdtree.rs:14-24).
+typedef std::shared_ptr<const Shape> ShapePtr;
+inline BoundingBox elem_box(const Triangle& t) { return t.bounding_box(); }
+inline bool elem_intersect(const Triangle& t, const Ray& ray, double t_min, HitRecord& rec, Counters& c) {
+    return t.intersect(ray, t_min, rec, c);
+}
+inline void elem_sample(const Triangle& t, const V3&, Rng& rng, V3& v, V3& n, double& p) { t.sample(rng, v, n, p); }
+inline BoundingBox elem_box(const ShapePtr& s) {
+    BoundingBox b;
+    const bool bounded = s->bounding_box(b);
+    assert(bounded);
+    (void)bounded;
+    return b;
+}
+inline bool elem_intersect(const ShapePtr& s, const Ray& ray, double t_min, HitRecord& rec, Counters& c) {
+    c.object_tests++;
+    return s->intersect(ray, t_min, rec, c);
+}
+inline void elem_sample(const ShapePtr& s, const V3& target, Rng& rng, V3& v, V3& n, double& p) {
+    s->sample(target, rng, v, n, p);
+}
+
+template <class T>
+struct KdTreeT : Shape {  // KdTree<T>; KdTree<Triangle> = Mesh
     std::unique_ptr<KdNode> root;
-    std::vector<Triangle> objects;
+    std::vector<T> objects;
     BoundingBox bounds;
     bool brute_force = false;  // oracle self-check mode: ignore the tree
 
+    std::vector<BoundingBox> boxes() const {
+        std::vector<BoundingBox> b;
+        b.reserve(objects.size());
+        for (const T& t : objects) b.push_back(elem_box(t));
+        return b;
+    }
     void init_bounds() {  // :108-119
         bounds = BoundingBox();
-        for (const Triangle& t : objects) bounds = bounds.merge(t.bounding_box());
+        for (const T& t : objects) bounds = bounds.merge(elem_box(t));
+    }
+    void build() {  // KdTree::new
+        std::vector<size_t> idx(objects.size());
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
+        root = construct(boxes(), std::move(idx));
+    }
+    bool bounding_box(BoundingBox& b) const override {  // :122-126
+        b = bounds;
+        return true;
     }
     bool intersect(const Ray& ray, double t_min, HitRecord& rec, Counters& c) const override {  // :129-136
         if (brute_force) {
             bool result = false;
-            for (const Triangle& t : objects)
-                if (t.intersect(ray, t_min, rec, c)) result = true;
+            for (const T& t : objects)
+                if (elem_intersect(t, ray, t_min, rec, c)) result = true;
             return result;
         }
         double b_min, b_max;
@@ -577,10 +712,10 @@ struct KdTree : Shape {  // KdTree<Triangle> = Mesh
         if (std::fmax(b_min, t_min) > std::fmin(b_max, rec.time)) return false;
         return intersect_subtree(*root, bounds, ray, t_min, rec, c);
     }
-    void sample(const V3&, Rng& rng, V3& v, V3& n, double& p) const override {  // :138-143
+    void sample(const V3& target, Rng& rng, V3& v, V3& n, double& p) const override {  // :138-143
         const size_t num = objects.size();
         const size_t index = (size_t)rng.uniform_usize(num);
-        objects[index].sample(rng, v, n, p);
+        elem_sample(objects[index], target, rng, v, n, p);
         p = p / (double)num;
     }
     bool intersect_subtree(const KdNode& node, const BoundingBox& bbox, const Ray& ray, double t_min,
@@ -591,7 +726,7 @@ struct KdTree : Shape {  // KdTree<Triangle> = Mesh
         if (node.kind == 3) {
             bool result = false;
             for (size_t index : node.indices)
-                if (objects[index].intersect(ray, t_min, rec, c)) result = true;
+                if (elem_intersect(objects[index], ray, t_min, rec, c)) result = true;
             return result;
         }
         const int ax = node.kind;
@@ -616,14 +751,16 @@ struct KdTree : Shape {  // KdTree<Triangle> = Mesh
         }
     }
 };
+typedef KdTreeT<Triangle> KdTree;      // Mesh (src/shape/mesh.rs:102)
+typedef KdTreeT<ShapePtr> ShapeTree;   // KdTree<Box<dyn Bounded>> (examples/fractal_*.rs)
 
 // ----------------------------------------------- src/shape.rs:99-150 -------
 struct Transformed : Shape {
-    std::unique_ptr<Shape> shape;
+    ShapePtr shape;
     M4 transform, inverse_transform;
     M3 linear, normal_transform;
     double scale;
-    Transformed(std::unique_ptr<Shape> s, const M4& t) : shape(std::move(s)), transform(t) {  // :111-124
+    Transformed(ShapePtr s, const M4& t) : shape(std::move(s)), transform(t) {  // :111-124
         inverse_transform = inverse4(t);
         linear = mat4_to_mat3(t);
         scale = det3(linear);
@@ -648,6 +785,17 @@ struct Transformed : Shape {
         v = mul_point(transform, lv);
         n = new_normal;
         p = lp / parallelepiped_base;
+    }
+    bool bounding_box(BoundingBox& out) const override {  // :153-175: box of the 8 transformed corners
+        BoundingBox b;
+        if (!shape->bounding_box(b)) return false;
+        out = BoundingBox();
+        for (int i = 0; i < 8; i++) {
+            const V3 corner = v3((i & 4) ? b.p_max.x : b.p_min.x, (i & 2) ? b.p_max.y : b.p_min.y, (i & 1) ? b.p_max.z : b.p_min.z);
+            const V3 v = mul_point(transform, corner);
+            out = BoundingBox{vmin(out.p_min, v), vmax(out.p_max, v)};
+        }
+        return true;
     }
 };
 
@@ -815,7 +963,7 @@ struct Environment {
 
 // ----------------------------------------- src/object.rs, src/light.rs -----
 struct Object {
-    std::unique_ptr<Shape> shape;
+    ShapePtr shape;
     Material material;
 };
 struct Light {
@@ -1014,49 +1162,76 @@ std::vector<Triangle> to_triangles(const double* tris, uint64_t n) {
     return out;
 }
 
-std::unique_ptr<Shape> to_shape(const rptb_scene_desc& d, const rptb_object& o, bool brute_force) {
-    std::unique_ptr<Shape> s;
-    switch (o.kind) {
-        case RPTB_SHAPE_SPHERE: s = std::make_unique<Sphere>(); break;
-        case RPTB_SHAPE_PLANE: {
-            auto p = std::make_unique<Plane>();
-            p->normal = v3(o.plane_normal[0], o.plane_normal[1], o.plane_normal[2]);
-            p->value = o.plane_value;
-            s = std::move(p);
-            break;
+// Meshes are built once per scene and shared (Arc<Mesh>, examples/fractal_teapots.rs:48-49).
+struct ShapeFactory {
+    const rptb_scene_desc& d;
+    bool brute_force;
+    std::vector<ShapePtr> meshes;
+    ShapeFactory(const rptb_scene_desc& desc, bool bf) : d(desc), brute_force(bf), meshes(desc.nmeshes) {}
+
+    ShapePtr mesh(uint32_t index) {
+        if (meshes[index]) return meshes[index];
+        const rptb_mesh& m = d.meshes[index];
+        auto k = std::make_shared<KdTree>();
+        k->objects = to_triangles(m.tris, m.ntris);
+        k->init_bounds();
+        k->brute_force = brute_force;
+        if (!brute_force) {
+            if (m.nodes != nullptr) k->root = unflatten_tree(m.nodes, m.refs, 0);
+            else k->build();
         }
-        case RPTB_SHAPE_CUBE: s = std::make_unique<Cube>(); break;
-        default: {
-            const rptb_mesh& m = d.meshes[o.mesh];
-            auto k = std::make_unique<KdTree>();
-            k->objects = to_triangles(m.tris, m.ntris);
-            k->init_bounds();
-            k->brute_force = brute_force;
-            if (!brute_force) {
-                if (m.nodes != nullptr) {
-                    k->root = unflatten_tree(m.nodes, m.refs, 0);
-                } else {
-                    std::vector<size_t> idx(m.ntris);
-                    for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
-                    k->root = construct(k->objects, std::move(idx));
-                }
+        meshes[index] = k;
+        return k;
+    }
+    ShapePtr group(uint32_t index) {  // KdTree::new(Vec<Box<dyn Bounded>>)
+        const rptb_group& g = d.groups[index];
+        auto k = std::make_shared<ShapeTree>();
+        for (uint64_t i = 0; i < g.nchildren; i++) k->objects.push_back(shape(g.children[i]));
+        k->init_bounds();
+        k->brute_force = brute_force;
+        if (!brute_force) {
+            if (g.nodes != nullptr) k->root = unflatten_tree(g.nodes, g.refs, 0);
+            else k->build();
+        }
+        return k;
+    }
+    ShapePtr shape(const rptb_object& o) {
+        ShapePtr s;
+        switch (o.kind) {
+            case RPTB_SHAPE_SPHERE: s = std::make_shared<Sphere>(); break;
+            case RPTB_SHAPE_PLANE: {
+                auto p = std::make_shared<Plane>();
+                p->normal = v3(o.plane_normal[0], o.plane_normal[1], o.plane_normal[2]);
+                p->value = o.plane_value;
+                s = p;
+                break;
             }
-            s = std::move(k);
+            case RPTB_SHAPE_CUBE: s = std::make_shared<Cube>(); break;
+            case RPTB_SHAPE_MONOMIAL: {
+                auto p = std::make_shared<MonomialSurface>();
+                p->height = o.monomial_height;
+                p->exp = o.monomial_exp;
+                s = p;
+                break;
+            }
+            case RPTB_SHAPE_GROUP: s = group(o.mesh); break;
+            default: s = mesh(o.mesh);
         }
+        if (o.has_transform) {
+            M4 t;
+            std::memcpy(t.m, o.transform, sizeof(t.m));
+            s = std::make_shared<Transformed>(s, t);
+        }
+        return s;
     }
-    if (o.has_transform) {
-        M4 t;
-        std::memcpy(t.m, o.transform, sizeof(t.m));
-        s = std::make_unique<Transformed>(std::move(s), t);
-    }
-    return s;
-}
+};
 
 std::unique_ptr<Scene> to_scene(const rptb_scene_desc& d, bool brute_force) {
     auto sc = std::make_unique<Scene>();
+    ShapeFactory factory(d, brute_force);
     for (uint32_t i = 0; i < d.nobjects; i++) {
         Object o;
-        o.shape = to_shape(d, d.objects[i], brute_force);
+        o.shape = factory.shape(d.objects[i]);
         o.material = to_material(d.materials[d.objects[i].material]);
         sc->objects.push_back(std::move(o));
     }
@@ -1067,7 +1242,7 @@ std::unique_ptr<Scene> to_scene(const rptb_scene_desc& d, bool brute_force) {
         li.color = v3(l.color[0], l.color[1], l.color[2]);
         li.vec = v3(l.vec[0], l.vec[1], l.vec[2]);
         if (l.kind == RPTB_LIGHT_OBJECT) {
-            li.object.shape = to_shape(d, l.object, brute_force);
+            li.object.shape = factory.shape(l.object);
             li.object.material = to_material(d.materials[l.object.material]);
         }
         sc->lights.push_back(std::move(li));
@@ -1223,11 +1398,37 @@ void oracle_illuminate(const oracle_scene* s, uint32_t index, const double* pos,
 }
 
 // KdTree::new -> construct (src/kdtree.rs:108-119,235-355), serialised in DFS pre-order.
+static int export_tree(const std::vector<BoundingBox>& boxes, rptb_kdtree_out* out);
+
 int oracle_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out) {
     const std::vector<Triangle> objects = to_triangles(tris, ntris);
-    std::vector<size_t> idx(ntris);
+    std::vector<BoundingBox> boxes;
+    for (const Triangle& t : objects) boxes.push_back(t.bounding_box());
+    return export_tree(boxes, out);
+}
+
+// construct over caller-supplied boxes (6 doubles each: p_min, p_max)
+int oracle_build_kdtree_boxes(const double* in, uint64_t n, rptb_kdtree_out* out) {
+    std::vector<BoundingBox> boxes(n);
+    for (uint64_t i = 0; i < n; i++)
+        boxes[i] = BoundingBox{v3(in[6 * i], in[6 * i + 1], in[6 * i + 2]), v3(in[6 * i + 3], in[6 * i + 4], in[6 * i + 5])};
+    return export_tree(boxes, out);
+}
+
+// Bounded::bounding_box of a described shape (out: p_min, p_max); returns 0 if it has none (Plane)
+int oracle_shape_bounds(const rptb_scene_desc* desc, const rptb_object* o, double* out) {
+    ShapeFactory factory(*desc, true);
+    BoundingBox b;
+    if (!factory.shape(*o)->bounding_box(b)) return 0;
+    out[0] = b.p_min.x; out[1] = b.p_min.y; out[2] = b.p_min.z;
+    out[3] = b.p_max.x; out[4] = b.p_max.y; out[5] = b.p_max.z;
+    return 1;
+}
+
+static int export_tree(const std::vector<BoundingBox>& boxes, rptb_kdtree_out* out) {
+    std::vector<size_t> idx(boxes.size());
     for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
-    const std::unique_ptr<KdNode> root = construct(objects, std::move(idx));
+    const std::unique_ptr<KdNode> root = construct(boxes, std::move(idx));
     std::vector<rptb_kdnode> nodes;
     std::vector<uint32_t> refs;
     uint32_t depth = 0, max_leaf = 0;

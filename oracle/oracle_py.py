@@ -49,6 +49,10 @@ def lib() -> C.CDLL:
     L.oracle_illuminate.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_uint64, dp, dp, dp]
     L.oracle_build_kdtree.restype = C.c_int
     L.oracle_build_kdtree.argtypes = [dp, C.c_uint64, C.POINTER(capi.KdTreeOut)]
+    L.oracle_build_kdtree_boxes.restype = C.c_int
+    L.oracle_build_kdtree_boxes.argtypes = [dp, C.c_uint64, C.POINTER(capi.KdTreeOut)]
+    L.oracle_shape_bounds.restype = C.c_int
+    L.oracle_shape_bounds.argtypes = [C.POINTER(capi.SceneDesc), C.POINTER(capi.Object), dp]
     L.oracle_free_kdtree.argtypes = [C.POINTER(capi.KdTreeOut)]
     L.oracle_hex_color.argtypes = [C.c_uint32, dp]
     L.oracle_color_bytes.argtypes = [dp, capi.c_u8_p]
@@ -130,11 +134,23 @@ def sample_f(material, dirs: np.ndarray, seed: int = 0):
     return wi, pdf
 
 
-def build_kdtree(tris: np.ndarray):
-    """KdTree::new restated literally -> (nodes structured array view, refs, depth, max_leaf)."""
-    tris = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 18)
+def shape_bounds(flat, obj_index: int):
+    """Bounded::bounding_box of scene object `obj_index` -> (p_min, p_max), or None (Plane)."""
+    out = np.empty(6)
+    if not lib().oracle_shape_bounds(C.byref(flat.desc), C.byref(flat.objects[obj_index]), _p(out)):
+        return None
+    return out[:3].copy(), out[3:].copy()
+
+
+def build_kdtree(tris: np.ndarray, boxes: bool = False):
+    """KdTree::new restated literally -> (nodes structured array view, refs, depth, max_leaf).
+    boxes=True: `tris` is an (n, 6) array of bounding boxes (p_min, p_max) instead of triangles."""
+    tris = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 6 if boxes else 18)
     out = capi.KdTreeOut()
-    lib().oracle_build_kdtree(_p(tris), tris.shape[0], C.byref(out))
+    if boxes:
+        lib().oracle_build_kdtree_boxes(_p(tris), tris.shape[0], C.byref(out))
+    else:
+        lib().oracle_build_kdtree(_p(tris), tris.shape[0], C.byref(out))
     try:
         n = int(out.nnodes)
         nodes = np.frombuffer(C.string_at(out.nodes, C.sizeof(capi.KdNode) * n), dtype=KDNODE_DTYPE).copy()

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("RPTB_LIB") or os.path.join(_HERE, "lib", "librpt_b200
 
 # ---- enums (include/rpt_b200.h) ------------------------------------------------
 OK = 0
-SHAPE_SPHERE, SHAPE_PLANE, SHAPE_CUBE, SHAPE_MESH = 0, 1, 2, 3
+SHAPE_SPHERE, SHAPE_PLANE, SHAPE_CUBE, SHAPE_MESH, SHAPE_MONOMIAL, SHAPE_GROUP = 0, 1, 2, 3, 4, 5
 LIGHT_POINT, LIGHT_AMBIENT, LIGHT_DIRECTIONAL, LIGHT_OBJECT = 0, 1, 2, 3
 ENV_COLOR, ENV_HDRI = 0, 1
 PRECISION_F32, PRECISION_F64 = 0, 1
@@ -70,6 +70,19 @@ class Object(C.Structure):
         ("transform", C.c_double * 16),
         ("plane_normal", C.c_double * 3),
         ("plane_value", C.c_double),
+        ("monomial_height", C.c_double),
+        ("monomial_exp", C.c_double),
+    ]
+
+
+class Group(C.Structure):
+    _fields_ = [
+        ("children", C.POINTER(Object)),
+        ("nchildren", C.c_uint64),
+        ("nodes", C.POINTER(KdNode)),
+        ("nnodes", C.c_uint64),
+        ("refs", c_u32_p),
+        ("nrefs", C.c_uint64),
     ]
 
 
@@ -105,6 +118,9 @@ class SceneDesc(C.Structure):
         ("lights", C.POINTER(Light)),
         ("nlights", C.c_uint32),
         ("environment", Env),
+        ("groups", C.POINTER(Group)),
+        ("ngroups", C.c_uint32),
+        ("_pad", C.c_uint32),
     ]
 
 
@@ -197,6 +213,7 @@ SYMBOLS = [
     ("rptb_sample_f", C.c_int,
      [C.POINTER(Material), c_double_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, c_double_p, c_double_p]),
     ("rptb_build_kdtree", C.c_int, [c_double_p, C.c_uint64, C.POINTER(KdTreeOut)]),
+    ("rptb_build_kdtree_boxes", C.c_int, [c_double_p, C.c_uint64, C.POINTER(KdTreeOut)]),
     ("rptb_free_kdtree", None, [C.POINTER(KdTreeOut)]),
     ("rptb_parse_obj", C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(c_double_p), C.POINTER(C.c_uint64)]),
     ("rptb_free_triangles", None, [c_double_p]),

@@ -181,6 +181,41 @@ class Mesh(Shape):
         return self.triangles.shape[0]
 
 
+class MonomialSurface(Shape):
+    """y = height * (x^2 + z^2)^(exp/2) over the unit disc, src/shape/monomial_surface.rs:13-18.
+    As in the reference, intersection and normals are only right for exp = 4."""
+
+    kind = capi.SHAPE_MONOMIAL
+
+    def __init__(self, height: float, exp: float = 4.0):
+        self.height = float(height)
+        self.exp = float(exp)
+
+
+class KdTree(Shape):
+    """KdTree::new(objects) over whole Bounded shapes (src/kdtree.rs:99-119): the kd-tree of
+    kd-trees of examples/fractal_teapots.rs:53-59 and the sphere clouds of fractal_spheres.rs.
+    `objects` are spheres, cubes, monomial surfaces and meshes, bare or transformed; a Mesh may
+    appear many times (the reference shares it through Arc<Mesh>).  The tree over the children's
+    bounding boxes is built by the library when the scene is created."""
+
+    kind = capi.SHAPE_GROUP
+
+    def __init__(self, objects):
+        self.objects = list(objects)
+        for o in self.objects:
+            base = o.shape if isinstance(o, Transformed) else o
+            if isinstance(base, Plane):
+                raise TypeError("Plane is not Bounded (no bounding_box): it cannot go into a KdTree")
+            if isinstance(base, KdTree):
+                raise TypeError("a KdTree inside a KdTree is not supported by the device scene")
+            if not isinstance(base, (Sphere, Cube, Mesh, MonomialSurface)):
+                raise TypeError(f"not a Bounded shape: {type(base).__name__}")
+
+    def __len__(self) -> int:
+        return len(self.objects)
+
+
 class Transformed(Shape):
     """src/shape.rs:99-125; chaining composes instead of nesting (:234-284)."""
 
@@ -225,6 +260,10 @@ def plane(normal, value: float) -> Plane:  # :297-299
 
 def cube() -> Cube:  # :302-304
     return Cube()
+
+
+def monomial_surface(height: float, exp: float) -> MonomialSurface:  # :292-294
+    return MonomialSurface(height, exp)
 
 
 def polygon(verts) -> Mesh:  # :307-313 (triangle fan)
@@ -621,9 +660,18 @@ class FlatScene:
             mesh_index[key] = len(meshes) - 1
             return mesh_index[key]
 
-        def to_object(o: Object) -> capi.Object:
+        groups: List[capi.Group] = []
+
+        def add_group(tree: KdTree) -> int:
+            children = (capi.Object * max(len(tree.objects), 1))(*[to_shape(c) for c in tree.objects])
+            self._keep.append(children)
+            g = capi.Group()
+            g.children, g.nchildren = children, len(tree.objects)
+            groups.append(g)  # nodes stay NULL: the library runs `construct` over the children's boxes
+            return len(groups) - 1
+
+        def to_shape(shape: Shape) -> capi.Object:
             co = capi.Object()
-            shape = o.shape
             if isinstance(shape, Transformed):
                 co.has_transform = 1
                 co.transform[:] = list(shape.matrix.T.reshape(-1))  # column-major
@@ -632,12 +680,20 @@ class FlatScene:
                 co.has_transform = 0
                 co.transform[:] = list(np.eye(4).reshape(-1))
             co.kind = shape.kind
-            co.material = add_material(o.mat)
             if isinstance(shape, Plane):
                 co.plane_normal[:] = list(shape.normal)
                 co.plane_value = shape.value
+            if isinstance(shape, MonomialSurface):
+                co.monomial_height, co.monomial_exp = shape.height, shape.exp
             if isinstance(shape, Mesh):
                 co.mesh = add_mesh(shape)
+            if isinstance(shape, KdTree):
+                co.mesh = add_group(shape)
+            return co
+
+        def to_object(o: Object) -> capi.Object:
+            co = to_shape(o.shape)
+            co.material = add_material(o.mat)
             return co
 
         objs = [to_object(o) for o in scene.objects]
@@ -658,6 +714,8 @@ class FlatScene:
         d = capi.SceneDesc()
         d.materials, d.nmaterials = self.materials, len(mats)
         d.meshes, d.nmeshes = self.meshes, len(meshes)
+        self.groups = (capi.Group * max(len(groups), 1))(*groups)
+        d.groups, d.ngroups = self.groups, len(groups)
         d.objects, d.nobjects = self.objects, len(objs)
         d.lights, d.nlights = self.lights, len(lights)
         env = scene.environment
@@ -677,6 +735,8 @@ class FlatScene:
         for i in range(self.desc.nmeshes):
             m = self.meshes[i]
             n += m.ntris * 18 * 8 + m.nnodes * C.sizeof(capi.KdNode) + m.nrefs * 4
+        for i in range(self.desc.ngroups):
+            n += self.groups[i].nchildren * C.sizeof(capi.Object)
         if self.desc.environment.kind == capi.ENV_HDRI:
             n += self.desc.environment.width * self.desc.environment.height * 24
         return int(n)

@@ -27,6 +27,8 @@
 namespace rptb {
 int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
                       uint32_t& depth, uint32_t& max_leaf);
+int build_kdtree_boxes_host(const double* boxes, uint64_t nboxes, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
+                            uint32_t& depth, uint32_t& max_leaf);
 cudaError_t launch_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height,
                                 uint32_t radius, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_convert_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t stream);
@@ -1001,16 +1003,17 @@ int rptb_sample_f(const rptb_material* m, const double* dirs, uint64_t n, uint64
     return point_eval(m, dirs, n, 6, seed, precision, device, out_wi, 3, out_pdf, true);
 }
 
-int rptb_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out) {
+static int build_kdtree_common(const double* data, uint64_t n, bool boxes, rptb_kdtree_out* out) {
     if (!out) return fail(RPTB_ERR_BAD_ARG, "null argument");
     std::memset(out, 0, sizeof(*out));
-    if (ntris == 0 || !tris) return fail(RPTB_ERR_BAD_ARG, "no triangles");
-    if (ntris >= (1ull << 31)) return fail(RPTB_ERR_UNSUPPORTED, "mesh too large");
+    if (n == 0 || !data) return fail(RPTB_ERR_BAD_ARG, boxes ? "no boxes" : "no triangles");
+    if (n >= (1ull << 31)) return fail(RPTB_ERR_UNSUPPORTED, "too many objects for one kd-tree");
     try {
         std::vector<rptb_kdnode> nodes;
         std::vector<uint32_t> refs;
         uint32_t depth = 0, max_leaf = 0;
-        build_kdtree_host(tris, ntris, nodes, refs, depth, max_leaf);
+        if (boxes) build_kdtree_boxes_host(data, n, nodes, refs, depth, max_leaf);
+        else build_kdtree_host(data, n, nodes, refs, depth, max_leaf);
         out->nodes = (rptb_kdnode*)std::malloc(sizeof(rptb_kdnode) * nodes.size());
         out->refs = (uint32_t*)std::malloc(sizeof(uint32_t) * std::max<size_t>(refs.size(), 1));
         if (!out->nodes || !out->refs) {
@@ -1029,6 +1032,14 @@ int rptb_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out) 
         return fail(RPTB_ERR_OOM, "host allocation failed");
     }
     return RPTB_OK;
+}
+
+int rptb_build_kdtree(const double* tris, uint64_t ntris, rptb_kdtree_out* out) {
+    return build_kdtree_common(tris, ntris, false, out);
+}
+
+int rptb_build_kdtree_boxes(const double* boxes, uint64_t nboxes, rptb_kdtree_out* out) {
+    return build_kdtree_common(boxes, nboxes, true, out);
 }
 
 void rptb_free_kdtree(rptb_kdtree_out* out) {

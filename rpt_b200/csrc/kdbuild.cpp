@@ -144,18 +144,10 @@ void emit(const Node& n, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>&
 
 namespace rptb {
 
-int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
-                      uint32_t& depth, uint32_t& max_leaf) {
-    std::vector<Box> boxes(ntris);
-    for (uint64_t i = 0; i < ntris; i++) {  // Triangle::bounding_box, src/shape/mesh.rs:39-46
-        const double* t = tris + 18 * i;
-        for (int a = 0; a < 3; a++) {
-            boxes[i].lo[a] = std::fmin(std::fmin(t[a], t[3 + a]), t[6 + a]);
-            boxes[i].hi[a] = std::fmax(std::fmax(t[a], t[3 + a]), t[6 + a]);
-        }
-    }
-    std::vector<uint32_t> idx(ntris);
-    for (uint64_t i = 0; i < ntris; i++) idx[i] = (uint32_t)i;
+static int build_from_boxes(std::vector<Box>& boxes, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
+                            uint32_t& depth, uint32_t& max_leaf) {
+    std::vector<uint32_t> idx(boxes.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
     std::unique_ptr<Node> root;
 #pragma omp parallel
 #pragma omp single
@@ -166,6 +158,31 @@ int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnod
     max_leaf = 0;
     emit(*root, nodes, refs, 0, depth, max_leaf);
     return 0;
+}
+
+int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
+                      uint32_t& depth, uint32_t& max_leaf) {
+    std::vector<Box> boxes(ntris);
+    for (uint64_t i = 0; i < ntris; i++) {  // Triangle::bounding_box, src/shape/mesh.rs:39-46
+        const double* t = tris + 18 * i;
+        for (int a = 0; a < 3; a++) {
+            boxes[i].lo[a] = std::fmin(std::fmin(t[a], t[3 + a]), t[6 + a]);
+            boxes[i].hi[a] = std::fmax(std::fmax(t[a], t[3 + a]), t[6 + a]);
+        }
+    }
+    return build_from_boxes(boxes, nodes, refs, depth, max_leaf);
+}
+
+// KdTree<T: Bounded>::new over caller-supplied bounding boxes (p_min, p_max per object).
+int build_kdtree_boxes_host(const double* in, uint64_t nboxes, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
+                            uint32_t& depth, uint32_t& max_leaf) {
+    std::vector<Box> boxes(nboxes);
+    for (uint64_t i = 0; i < nboxes; i++)
+        for (int a = 0; a < 3; a++) {
+            boxes[i].lo[a] = in[6 * i + a];
+            boxes[i].hi[a] = in[6 * i + 3 + a];
+        }
+    return build_from_boxes(boxes, nodes, refs, depth, max_leaf);
 }
 
 }  // namespace rptb

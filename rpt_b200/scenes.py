@@ -7,6 +7,12 @@ BASELINE.json; where it is silent, from the example file.
     teapot   examples/teapot.rs:10-34
     dragon   examples/dragon.rs:32-75   (mesh: procedural stand-in, see dragon_proxy)
     glass    examples/glass.rs:27-49    (HDRI: synthetic stand-in, see synthetic_hdri)
+
+and, for the two-level kd-trees and the MonomialSurface, not BASELINE configs:
+
+    fractal_spheres  examples/fractal_spheres.rs:3-77
+    fractal_teapots  examples/fractal_teapots.rs:8-88
+    monomial_glass   examples/monomial_glass.rs:25-88  (synthetic HDRI)
 """
 from __future__ import annotations
 
@@ -16,8 +22,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .api import (Camera, Environment, Hdri, Light, Material, Mesh, Object, Scene, cube, hex_color, plane, polygon,
-                  sphere, vec3)
+from .api import (Camera, Environment, Hdri, KdTree, Light, Material, Mesh, Object, Scene, cube, hex_color,
+                  monomial_surface, plane, polygon, sphere, vec3)
 
 _ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 
@@ -212,6 +218,87 @@ def glass_scene(hdri_width: int = 2048, hdri_height: int = 1024) -> Config:
     return Config("glass", scene, Camera.default(), 1920, 1080, 4096, 12,
                   "examples/glass.rs; synthetic HDRI; 1920x1080x4096 spp, max_bounces 12 per BASELINE.json")
 
+
+FRACTAL_COLORS = [0x264653, 0x2A9D8F, 0xE9C46A, 0xF4A261, 0xE76F51]
+
+
+def _fractal(levels: int, make):
+    """gen() of examples/fractal_spheres.rs:3-32 / fractal_teapots.rs:8-41: one shape at p with radius
+    rad, then five (six at the root) children at distance 7/5 rad with radius 2/5 rad, skipping the
+    direction that leads back; shapes are grouped by depth."""
+    groups = [[] for _ in range(levels)]
+
+    def gen(p, rad, depth, last_dir):
+        groups[depth].append(make(p, rad))
+        if depth == levels - 1:
+            return
+        disp = rad * 7.0 / 5.0
+        dx = [disp, -disp, 0.0, 0.0, 0.0, 0.0]
+        dy = [0.0, 0.0, disp, -disp, 0.0, 0.0]
+        dz = [0.0, 0.0, 0.0, 0.0, disp, -disp]
+        for i in range(6):
+            if last_dir is None or i != (last_dir ^ 1):
+                gen(p + vec3(dx[i], dy[i], dz[i]), rad * 2.0 / 5.0, depth + 1, i)
+
+    gen(vec3(0.0, 0.0, 0.0), 1.0, 0, None)
+    return groups
+
+
+def _fractal_scene(name: str, groups, levels: int, note: str) -> Config:
+    scene = Scene()
+    for i, group in enumerate(groups):
+        scene.add(Object(KdTree(group)).material(Material.specular(hex_color(FRACTAL_COLORS[i]), 0.25)))
+    scene.add(Object(plane(vec3(0.0, 0.0, 1.0), -6.0)).material(Material.diffuse(hex_color(0xFFCCCC))))
+    scene.add(Light.Ambient(vec3(0.02, 0.02, 0.02)))
+    d = vec3(0.0, -0.65, -1.0)
+    scene.add(Light.Directional(vec3(0.6, 0.6, 0.6), d / np.linalg.norm(d)))
+    scene.add(Light.Point(vec3(100.0, 100.0, 100.0), vec3(0.0, 5.0, 5.0)))
+    direction = vec3(-0.285714, -0.5, -1.0)
+    up = vec3(0.0, 1.0, -0.5)
+    camera = Camera(eye=vec3(2.0, 3.5, 7.0), direction=direction / np.linalg.norm(direction),
+                    up=up / np.linalg.norm(up), fov=math.pi / 6)
+    return Config(name, scene, camera, 800, 600, 1, 0, note)
+
+
+def fractal_spheres_scene(levels: int = 5) -> Config:
+    groups = _fractal(levels, lambda p, rad: sphere().scale(vec3(rad, rad, rad)).translate(p))
+    return _fractal_scene("fractal_spheres", groups, levels,
+                          "examples/fractal_spheres.rs: one KdTree<Box<dyn Bounded>> of spheres per level (1, 6, 30, 150, 750)")
+
+
+def fractal_teapots_scene(levels: int = 5) -> Config:
+    teapot = Mesh(teapot_triangles())  # Arc<Mesh>: every instance shares this one kd-tree
+
+    def make(p, rad):
+        return teapot.scale(vec3(0.5, 0.5, 0.5)).scale(vec3(rad, rad, rad)).translate(p)
+
+    return _fractal_scene("fractal_teapots", _fractal(levels, make), levels,
+                          "examples/fractal_teapots.rs: kd-trees of transformed instances of one teapot kd-tree")
+
+
+def monomial_glass_scene(hdri_width: int = 512, hdri_height: int = 256) -> Config:
+    scene = Scene()
+    scene.environment = Environment.Hdri(synthetic_hdri(hdri_width, hdri_height))
+    scene.add(Object(monomial_surface(2.0, 4.0).translate(vec3(0.0, -1.0, 0.0)))
+              .material(Material.metallic_(hex_color(0xFFFFFF), 0.0001)))
+    scene.add(Object(cube().rotate_y(math.pi / 6.0).scale(vec3(0.5, 0.3, 0.4)).translate(vec3(0.4, -0.8, 4.0)))
+              .material(Material.specular(hex_color(0xFF00FF), 0.5)))
+    scene.add(Object(sphere().scale(vec3(0.5, 0.5, 0.5)).translate(vec3(1.5, -0.5, 1.0)))
+              .material(Material.specular(hex_color(0x0000FF), 0.1)))
+    scene.add(Object(sphere().scale(vec3(0.5, 0.5, 0.5)).translate(vec3(-1.5, -0.5, 1.0)))
+              .material(Material.specular(hex_color(0x00FF00), 0.1)))
+    scene.add(Object(plane(vec3(0.0, 1.0, 0.0), -1.0)).material(Material.specular(hex_color(0xAAAAAA), 0.5)))
+    scene.add(Light.Ambient(vec3(0.01, 0.01, 0.01)))
+    scene.add(Light.Point(vec3(100.0, 100.0, 100.0), vec3(0.0, 5.0, 5.0)))
+    return Config("monomial_glass", scene, Camera.default(), 800, 600, 100, 1,
+                  "examples/monomial_glass.rs; synthetic HDRI")
+
+
+EXTRA_CONFIGS = {
+    "fractal_spheres": fractal_spheres_scene,
+    "fractal_teapots": fractal_teapots_scene,
+    "monomial_glass": monomial_glass_scene,
+}
 
 CONFIGS = {
     "sphere": sphere_scene,
