@@ -22,13 +22,10 @@
 #include <vector>
 
 #include "../../include/rpt_b200.h"
+#include "flatten.h"
 #include "launch.h"
 
 namespace rptb {
-int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
-                      uint32_t& depth, uint32_t& max_leaf);
-int build_kdtree_boxes_host(const double* boxes, uint64_t nboxes, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
-                            uint32_t& depth, uint32_t& max_leaf);
 cudaError_t launch_film_resolve(const double* sums, uint32_t nbatches, uint32_t width, uint32_t height,
                                 uint32_t radius, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_convert_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t stream);
@@ -126,250 +123,6 @@ struct Arena {
     }
 };
 
-// ---- small double-precision matrix helpers (column-major 4x4 in) -------------------
-struct Xf {
-    double fwd[12];  // rows of the 3x4
-    double inv[12];
-    double nrm[9];   // rows of (L^-1)^T
-    double det;
-};
-
-bool invert4(const double* m /*col-major*/, double* out /*col-major*/) {
-    double w[4][8];
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) {
-            w[r][c] = m[c * 4 + r];
-            w[r][c + 4] = r == c ? 1.0 : 0.0;
-        }
-    for (int i = 0; i < 4; i++) {
-        int p = i;
-        for (int r = i + 1; r < 4; r++)
-            if (std::fabs(w[r][i]) > std::fabs(w[p][i])) p = r;
-        if (w[p][i] == 0.0) return false;
-        if (p != i)
-            for (int c = 0; c < 8; c++) std::swap(w[i][c], w[p][c]);
-        const double piv = w[i][i];
-        for (int c = 0; c < 8; c++) w[i][c] /= piv;
-        for (int r = 0; r < 4; r++)
-            if (r != i && w[r][i] != 0.0) {
-                const double f = w[r][i];
-                for (int c = 0; c < 8; c++) w[r][c] -= f * w[i][c];
-            }
-    }
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) out[c * 4 + r] = w[r][c + 4];
-    return true;
-}
-
-// Transformed::new (src/shape.rs:111-124)
-bool make_xf(const double* t /*col-major 4x4*/, Xf& x) {
-    double inv[16];
-    if (!invert4(t, inv)) return false;
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 4; c++) {
-            x.fwd[r * 4 + c] = t[c * 4 + r];
-            x.inv[r * 4 + c] = inv[c * 4 + r];
-        }
-    // linear = upper-left 3x3; L(r,c) = t[c*4+r]
-    auto L = [&](int r, int c) { return t[c * 4 + r]; };
-    const double det = L(0, 0) * (L(1, 1) * L(2, 2) - L(1, 2) * L(2, 1)) - L(0, 1) * (L(1, 0) * L(2, 2) - L(1, 2) * L(2, 0)) +
-                       L(0, 2) * (L(1, 0) * L(2, 1) - L(1, 1) * L(2, 0));
-    x.det = det;
-    // inverse transpose = cofactor matrix / det
-    double cof[3][3];
-    cof[0][0] = L(1, 1) * L(2, 2) - L(1, 2) * L(2, 1);
-    cof[0][1] = -(L(1, 0) * L(2, 2) - L(1, 2) * L(2, 0));
-    cof[0][2] = L(1, 0) * L(2, 1) - L(1, 1) * L(2, 0);
-    cof[1][0] = -(L(0, 1) * L(2, 2) - L(0, 2) * L(2, 1));
-    cof[1][1] = L(0, 0) * L(2, 2) - L(0, 2) * L(2, 0);
-    cof[1][2] = -(L(0, 0) * L(2, 1) - L(0, 1) * L(2, 0));
-    cof[2][0] = L(0, 1) * L(1, 2) - L(0, 2) * L(1, 1);
-    cof[2][1] = -(L(0, 0) * L(1, 2) - L(0, 2) * L(1, 0));
-    cof[2][2] = L(0, 0) * L(1, 1) - L(0, 1) * L(1, 0);
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) x.nrm[r * 3 + c] = cof[r][c] / det;
-    return true;
-}
-
-template <class R>
-void fill_object(const rptb_object& o, ObjectRec<R>& rec) {
-    std::memset(&rec, 0, sizeof(rec));
-    rec.kind = o.kind;
-    rec.material = o.material;
-    rec.mesh = o.mesh;
-    rec.has_transform = o.has_transform ? 1u : 0u;
-    Xf x;
-    static const double ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    make_xf(o.has_transform ? o.transform : ident, x);
-    for (int i = 0; i < 12; i++) {
-        rec.inv[i] = (R)x.inv[i];
-        rec.fwd[i] = (R)x.fwd[i];
-    }
-    for (int i = 0; i < 9; i++) rec.nrm[i] = (R)x.nrm[i];
-    rec.det = (R)x.det;
-    const double len = std::sqrt(o.plane_normal[0] * o.plane_normal[0] + o.plane_normal[1] * o.plane_normal[1] +
-                                 o.plane_normal[2] * o.plane_normal[2]);
-    for (int i = 0; i < 3; i++) {
-        rec.plane_n[i] = (R)o.plane_normal[i];
-        rec.plane_unit[i] = (R)(len > 0 ? o.plane_normal[i] / len : 0.0);
-    }
-    rec.plane_v = (R)o.plane_value;
-}
-
-template <class R>
-void fill_material(const rptb_material& m, MaterialRec<R>& rec) {
-    for (int i = 0; i < 3; i++) rec.color[i] = (R)m.color[i];
-    rec.index = (R)m.index;
-    rec.roughness = (R)m.roughness;
-    rec.metallic = (R)m.metallic;
-    rec.emittance = (R)m.emittance;
-    rec.transparent = m.transparent ? 1u : 0u;
-}
-
-// One flattened mesh on the host, before upload.
-struct HostMesh {
-    std::vector<KdNodeDev> nodes32;
-    std::vector<KdNodeDev64> nodes64;
-    std::vector<uint32_t> refs;
-    std::vector<float4> tri48;
-    std::vector<float4> leaf_planes;
-    std::vector<float> verts32, norms32;
-    std::vector<double> verts64, norms64;
-    double bmin[3], bmax[3];
-    uint32_t ntris = 0, depth = 0;
-};
-
-// Re-serialise the boundary tree in DFS pre-order (left child = node + 1) into both node formats.
-int flatten_nodes(const rptb_kdnode* in, uint64_t nnodes, const uint32_t* in_refs, uint64_t nrefs, uint64_t ntris,
-                  HostMesh& hm) {
-    struct Item {
-        uint32_t src;
-        uint32_t depth;
-        int64_t parent;  // dst index of the parent waiting for its right-child index, -1 if none
-    };
-    std::vector<Item> stack;
-    stack.push_back({0, 0, -1});
-    hm.depth = 0;
-    while (!stack.empty()) {
-        const Item it = stack.back();
-        stack.pop_back();
-        if (it.src >= nnodes) return fail(RPTB_ERR_BAD_ARG, "kd node index %u out of range (%llu nodes)", it.src, (unsigned long long)nnodes);
-        if (hm.nodes32.size() > nnodes) return fail(RPTB_ERR_BAD_ARG, "kd tree is not a tree (cycle?)");
-        const rptb_kdnode& s = in[it.src];
-        const uint32_t dst = (uint32_t)hm.nodes32.size();
-        if (it.parent >= 0) {  // we are the right child of `parent`
-            hm.nodes32[it.parent].word |= dst << 2;
-            hm.nodes64[it.parent].word |= dst << 2;
-        }
-        hm.depth = std::max(hm.depth, it.depth);
-        KdNodeDev n32;
-        KdNodeDev64 n64;
-        if (s.kind == 3) {
-            if ((uint64_t)s.first_ref + s.num_refs > nrefs) return fail(RPTB_ERR_BAD_ARG, "kd leaf refs out of range");
-            if (s.num_refs >= (1u << 30)) return fail(RPTB_ERR_UNSUPPORTED, "kd leaf too large");
-            const uint32_t first = (uint32_t)hm.refs.size();
-            for (uint32_t i = 0; i < s.num_refs; i++) {
-                const uint32_t t = in_refs[s.first_ref + i];
-                if (t >= ntris) return fail(RPTB_ERR_BAD_ARG, "kd leaf references triangle %u of %llu", t, (unsigned long long)ntris);
-                hm.refs.push_back(t);
-            }
-            n32.first_ref = first;
-            n32.word = (s.num_refs << 2) | 3u;
-            n64.split = 0.0;
-            n64.first_ref = first;
-            n64.word = n32.word;
-            hm.nodes32.push_back(n32);
-            hm.nodes64.push_back(n64);
-        } else if (s.kind <= 2) {
-            n32.split = (float)s.split;
-            n32.word = s.kind;  // right child patched in when it is emitted
-            n64.split = s.split;
-            n64.first_ref = 0;
-            n64.word = s.kind;
-            hm.nodes32.push_back(n32);
-            hm.nodes64.push_back(n64);
-            // pre-order: left next (pushed last), right later with a back-pointer to us
-            stack.push_back({s.right, it.depth + 1, (int64_t)dst});
-            stack.push_back({s.left, it.depth + 1, -1});
-        } else {
-            return fail(RPTB_ERR_BAD_ARG, "kd node kind %u", s.kind);
-        }
-    }
-    if (hm.nodes32.size() >= (1u << 30)) return fail(RPTB_ERR_UNSUPPORTED, "kd tree has too many nodes");
-    return RPTB_OK;
-}
-
-int flatten_mesh(const rptb_mesh& m, HostMesh& hm) {
-    if (m.ntris == 0 || m.tris == nullptr) return fail(RPTB_ERR_BAD_ARG, "mesh without triangles");
-    if (m.ntris >= (1ull << 31)) return fail(RPTB_ERR_UNSUPPORTED, "mesh too large");
-    hm.ntris = (uint32_t)m.ntris;
-    int rc;
-    if (m.nodes == nullptr) {
-        std::vector<rptb_kdnode> nodes;
-        std::vector<uint32_t> refs;
-        uint32_t depth, max_leaf;
-        build_kdtree_host(m.tris, m.ntris, nodes, refs, depth, max_leaf);
-        rc = flatten_nodes(nodes.data(), nodes.size(), refs.data(), refs.size(), m.ntris, hm);
-    } else {
-        rc = flatten_nodes(m.nodes, m.nnodes, m.refs, m.nrefs, m.ntris, hm);
-    }
-    if (rc != RPTB_OK) return rc;
-    if (hm.depth >= (uint32_t)KD_STACK) return fail(RPTB_ERR_UNSUPPORTED, "kd tree depth %u exceeds the traversal stack (%d)", hm.depth, KD_STACK);
-
-    for (int a = 0; a < 3; a++) {
-        hm.bmin[a] = INFINITY;
-        hm.bmax[a] = -INFINITY;
-    }
-    hm.tri48.resize(3 * (size_t)m.ntris);
-    hm.verts32.resize(9 * (size_t)m.ntris);
-    hm.norms32.resize(9 * (size_t)m.ntris);
-    hm.verts64.resize(9 * (size_t)m.ntris);
-    hm.norms64.resize(9 * (size_t)m.ntris);
-    for (uint64_t i = 0; i < m.ntris; i++) {
-        const double* t = m.tris + 18 * i;
-        for (int k = 0; k < 9; k++) {
-            hm.verts64[9 * i + k] = t[k];
-            hm.verts32[9 * i + k] = (float)t[k];
-            hm.norms64[9 * i + k] = t[9 + k];
-            hm.norms32[9 * i + k] = (float)t[9 + k];
-        }
-        for (int a = 0; a < 3; a++) {  // KdTree::bounds = merge of Triangle::bounding_box
-            hm.bmin[a] = std::fmin(hm.bmin[a], std::fmin(std::fmin(t[a], t[3 + a]), t[6 + a]));
-            hm.bmax[a] = std::fmax(hm.bmax[a], std::fmax(std::fmax(t[a], t[3 + a]), t[6 + a]));
-        }
-        // the per-triangle invariants of Triangle::intersect (mesh.rs:50-72), folded in double
-        const double d0[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]};
-        const double d1[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
-        double pn[3] = {d0[1] * d1[2] - d0[2] * d1[1], d0[2] * d1[0] - d0[0] * d1[2], d0[0] * d1[1] - d0[1] * d1[0]};
-        const double len = std::sqrt(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);
-        for (int a = 0; a < 3; a++) pn[a] /= len;
-        const double d00 = d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2];
-        const double d01 = d0[0] * d1[0] + d0[1] * d1[1] + d0[2] * d1[2];
-        const double d11 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2];
-        const double denom = d00 * d11 - d01 * d01;
-        double A[3], B[3];
-        for (int a = 0; a < 3; a++) {
-            A[a] = (d11 * d0[a] - d01 * d1[a]) / denom;
-            B[a] = (d00 * d1[a] - d01 * d0[a]) / denom;
-        }
-        const double pnv1 = pn[0] * t[0] + pn[1] * t[1] + pn[2] * t[2];
-        const double a0 = -(A[0] * t[0] + A[1] * t[1] + A[2] * t[2]);
-        const double b0 = -(B[0] * t[0] + B[1] * t[1] + B[2] * t[2]);
-        hm.tri48[3 * i + 0] = make_float4((float)pn[0], (float)pn[1], (float)pn[2], (float)pnv1);
-        hm.tri48[3 * i + 1] = make_float4((float)A[0], (float)A[1], (float)A[2], (float)a0);
-        hm.tri48[3 * i + 2] = make_float4((float)B[0], (float)B[1], (float)B[2], (float)b0);
-    }
-    return RPTB_OK;
-}
-
-template <class R>
-struct Tables {
-    std::vector<ObjectRec<R>> objects;
-    std::vector<LightRec<R>> lights;
-    std::vector<MaterialRec<R>> materials;
-    std::vector<MeshRec<R>> meshes;
-};
-
 }  // namespace
 
 struct rptb_scene {
@@ -401,178 +154,36 @@ struct rptb_scene {
 
 namespace {
 
-int validate_object(const rptb_scene_desc* d, const rptb_object& o, const char* what, uint32_t i) {
-    if (o.kind > RPTB_SHAPE_MESH) return fail(RPTB_ERR_BAD_ARG, "%s %u: bad shape kind %u", what, i, o.kind);
-    if (o.material >= d->nmaterials) return fail(RPTB_ERR_BAD_ARG, "%s %u: material %u out of range", what, i, o.material);
-    if (o.kind == RPTB_SHAPE_MESH && o.mesh >= d->nmeshes) return fail(RPTB_ERR_BAD_ARG, "%s %u: mesh %u out of range", what, i, o.mesh);
-    if (o.has_transform) {
-        Xf x;
-        if (!make_xf(o.transform, x)) return fail(RPTB_ERR_BAD_ARG, "%s %u: singular transform", what, i);
+// bind_scene's uploader: every array goes to the device through the scene's arena
+struct ArenaPut {
+    Arena& arena;
+    cudaError_t error = cudaSuccess;
+    template <class T>
+    bool operator()(std::vector<T>& host, const T** where) {
+        error = arena.upload(host, where);
+        return error == cudaSuccess;
     }
-    return RPTB_OK;
-}
-
-template <class R>
-void fill_tables(const rptb_scene_desc* d, Tables<R>& t) {
-    t.objects.resize(d->nobjects);
-    for (uint32_t i = 0; i < d->nobjects; i++) fill_object(d->objects[i], t.objects[i]);
-    t.materials.resize(d->nmaterials);
-    for (uint32_t i = 0; i < d->nmaterials; i++) fill_material(d->materials[i], t.materials[i]);
-    t.lights.resize(d->nlights);
-    for (uint32_t i = 0; i < d->nlights; i++) {
-        const rptb_light& l = d->lights[i];
-        LightRec<R>& r = t.lights[i];
-        std::memset(&r, 0, sizeof(r));
-        r.kind = l.kind;
-        for (int k = 0; k < 3; k++) {
-            r.color[k] = (R)l.color[k];
-            r.vec[k] = (R)l.vec[k];
-        }
-        if (l.kind == RPTB_LIGHT_OBJECT) {
-            fill_object(l.object, r.object);
-            const rptb_material& m = d->materials[l.object.material];
-            for (int k = 0; k < 3; k++) r.radiance[k] = (R)(m.color[k] * m.emittance);  // light.rs:42
-        }
-    }
-}
-
-template <class R>
-int upload_tables(rptb_scene* s, const Tables<R>& t, SceneView<R>& v) {
-    CU(s->arena.upload(t.objects, &v.objects));
-    CU(s->arena.upload(t.lights, &v.lights));
-    CU(s->arena.upload(t.materials, &v.materials));
-    CU(s->arena.upload(t.meshes, &v.meshes));
-    v.nobjects = (uint32_t)t.objects.size();
-    v.nlights = (uint32_t)t.lights.size();
-    v.nmaterials = (uint32_t)t.materials.size();
-    v.nmeshes = (uint32_t)t.meshes.size();
-    v.tables_in_const = 0;
-    return RPTB_OK;
-}
+    uint64_t bytes() const { return arena.bytes; }
+};
 
 int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
+    HostScene hs;
+    std::string err;
+    int rc = flatten_scene(d, hs, err);
+    if (rc != RPTB_OK) return fail(rc, "%s", err.c_str());
+    if (getenv("RPTB_NO_SMALL") != nullptr) hs.small_ok = false;
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->arena.stream = s->stream;
-    Tables<float> t32;
-    Tables<double> t64;
-    fill_tables(d, t32);
-    fill_tables(d, t64);
-    t32.meshes.resize(d->nmeshes);
-    t64.meshes.resize(d->nmeshes);
-    std::vector<float4> small_tris;  // tri48 of the one-leaf meshes, for SmallTables
-    for (uint32_t i = 0; i < d->nmeshes; i++) {
-        HostMesh hm;
-        const int rc = flatten_mesh(d->meshes[i], hm);
-        if (rc != RPTB_OK) return rc;
-        MeshRec<float>& a = t32.meshes[i];
-        MeshRec<double>& b = t64.meshes[i];
-        std::memset(&a, 0, sizeof(a));
-        std::memset(&b, 0, sizeof(b));
-        const uint64_t before = s->arena.bytes;
-        CU(s->arena.upload(hm.nodes32, &a.nodes));
-        CU(s->arena.upload(hm.refs, &a.refs));
-        CU(s->arena.upload(hm.tri48, &a.tri48));
-        if ((hm.nodes32[0].word & 3u) != 3u) {  // a real tree: planes in leaf order for the trace kernel
-            hm.leaf_planes.resize(hm.refs.size());
-            for (size_t k = 0; k < hm.refs.size(); k++) hm.leaf_planes[k] = hm.tri48[3 * (size_t)hm.refs[k]];
-            CU(s->arena.upload(hm.leaf_planes, &a.leaf_planes));
-        }
-        CU(s->arena.upload(hm.verts32, &a.verts));
-        CU(s->arena.upload(hm.norms32, &a.norms));
-        s->f32_bytes += s->arena.bytes - before;
-        CU(s->arena.upload(hm.nodes64, &b.nodes));
-        b.refs = a.refs;
-        b.tri48 = nullptr;
-        CU(s->arena.upload(hm.verts64, &b.verts));
-        CU(s->arena.upload(hm.norms64, &b.norms));
-        for (int k = 0; k < 3; k++) {
-            a.bmin[k] = (float)hm.bmin[k];
-            a.bmax[k] = (float)hm.bmax[k];
-            b.bmin[k] = hm.bmin[k];
-            b.bmax[k] = hm.bmax[k];
-        }
-        // f32 bounds must contain the f32 vertices: widen by one ulp outward
-        for (int k = 0; k < 3; k++) {
-            a.bmin[k] = std::nextafterf(a.bmin[k], -INFINITY);
-            a.bmax[k] = std::nextafterf(a.bmax[k], INFINITY);
-        }
-        a.ntris = b.ntris = hm.ntris;
-        a.root_is_leaf = b.root_is_leaf = (hm.nodes32[0].word & 3u) == 3u;
-        if (a.root_is_leaf) {
-            a.small_tri_base = (uint32_t)(small_tris.size() / 3);
-            small_tris.insert(small_tris.end(), hm.tri48.begin(), hm.tri48.end());
-        }
-        if (!a.root_is_leaf) s->has_tree = true;
-        s->tree_nodes += hm.nodes32.size();
-        // world-space bounds of every object that uses this mesh (8 transformed corners), for the ray sort keys
-        for (uint32_t oi = 0; oi < d->nobjects; oi++) {
-            const rptb_object& o = d->objects[oi];
-            if (o.kind != RPTB_SHAPE_MESH || o.mesh != i) continue;
-            for (int c = 0; c < 8; c++) {
-                const double p[3] = {(c & 1) ? hm.bmax[0] : hm.bmin[0], (c & 2) ? hm.bmax[1] : hm.bmin[1], (c & 4) ? hm.bmax[2] : hm.bmin[2]};
-                for (int r = 0; r < 3; r++) {
-                    double v = p[r];
-                    if (o.has_transform) v = o.transform[0 * 4 + r] * p[0] + o.transform[1 * 4 + r] * p[1] + o.transform[2 * 4 + r] * p[2] + o.transform[3 * 4 + r];
-                    s->wlo[r] = std::fmin(s->wlo[r], v);
-                    s->whi[r] = std::fmax(s->whi[r], v);
-                }
-            }
-        }
-    }
-    {
-        const uint64_t before = s->arena.bytes;
-        int rc = upload_tables(s, t32, s->view32);
-        if (rc != RPTB_OK) return rc;
-        s->f32_bytes += s->arena.bytes - before;
-        rc = upload_tables(s, t64, s->view64);
-        if (rc != RPTB_OK) return rc;
-    }
-    // environment
-    std::memset(&s->view32.env, 0, sizeof(s->view32.env));
-    std::memset(&s->view64.env, 0, sizeof(s->view64.env));
-    s->view32.env.kind = s->view64.env.kind = d->environment.kind;
+    ArenaPut put{s->arena};
+    if (!bind_scene(hs, put, true, s->view32, s->view64, s->f32_bytes)) CU(put.error);
+    s->features = hs.features;
+    s->has_tree = hs.has_tree;
+    s->tree_nodes = hs.tree_nodes;
+    s->sampled_lights = hs.sampled_lights;
     for (int k = 0; k < 3; k++) {
-        s->view32.env.color[k] = (float)d->environment.color[k];
-        s->view64.env.color[k] = d->environment.color[k];
+        s->wlo[k] = hs.wlo[k];
+        s->whi[k] = hs.whi[k];
     }
-    if (d->environment.kind == RPTB_ENV_HDRI) {
-        const uint32_t w = d->environment.width, h = d->environment.height;
-        if (w == 0 || h == 0 || d->environment.texels == nullptr) return fail(RPTB_ERR_BAD_ARG, "HDRI without texels");
-        const size_t n = (size_t)w * h;
-        std::vector<float4> tex(n);
-        for (size_t i = 0; i < n; i++)
-            tex[i] = make_float4((float)d->environment.texels[3 * i], (float)d->environment.texels[3 * i + 1],
-                                 (float)d->environment.texels[3 * i + 2], 0.0f);
-        std::vector<double> tex64(d->environment.texels, d->environment.texels + 3 * n);
-        const uint64_t before = s->arena.bytes;
-        CU(s->arena.upload(tex, &s->view32.env.texels_f4));
-        s->f32_bytes += s->arena.bytes - before;
-        CU(s->arena.upload(tex64, &s->view64.env.texels_f64));
-        s->view32.env.width = s->view64.env.width = w;
-        s->view32.env.height = s->view64.env.height = h;
-    }
-    // small scenes: the uniform tables also ride in the kernel parameters (scene_dev.cuh, SmallTables)
-    // ... but only when what a ray actually walks (objects + lights + one-leaf triangles) stays within
-    // ~1 KB: the constant cache in front of parameter space is tiny.  Measured: sphere scene (0.6 KB)
-    // 9.2 -> 10.6 Gsamples/s; Cornell (2.1 KB walked per ray) 5.08 -> 4.40 -- so Cornell stays on L1.
-    const size_t walked = d->nobjects * sizeof(ObjectRec<float>) + d->nlights * sizeof(LightRec<float>) + small_tris.size() * sizeof(float4);
-    if (d->nobjects <= (uint32_t)SMALL_OBJECTS && d->nlights <= (uint32_t)SMALL_LIGHTS && d->nmeshes <= (uint32_t)SMALL_MESHES &&
-        small_tris.size() <= (size_t)3 * SMALL_TRIS && walked <= 1024 && getenv("RPTB_NO_SMALL") == nullptr) {
-        SmallTables<float>& sm = s->view32.small;
-        std::memset(&sm, 0, sizeof(sm));
-        for (uint32_t i = 0; i < d->nobjects; i++) sm.objects[i] = t32.objects[i];
-        for (uint32_t i = 0; i < d->nlights; i++) sm.lights[i] = t32.lights[i];
-        for (uint32_t i = 0; i < d->nmeshes; i++) sm.meshes[i] = t32.meshes[i];
-        for (size_t i = 0; i < small_tris.size(); i++) sm.tri48[i] = small_tris[i];
-        s->view32.tables_in_const = 1;
-        s->features |= F_SMALL;
-    }
-    for (uint32_t i = 0; i < d->nlights; i++)
-        if (d->lights[i].kind != RPTB_LIGHT_AMBIENT) s->sampled_lights++;
-    if (s->has_tree) s->features |= F_TREE;
-    for (uint32_t i = 0; i < d->nmaterials; i++)
-        if (d->materials[i].transparent) s->features |= F_TRANSP;
-    if (d->environment.kind == RPTB_ENV_HDRI) s->features |= F_HDRI;
     CU(pool_alloc((void**)&s->counters, sizeof(DeviceCounters), s->stream));
     CU(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), s->stream));
     CU(cudaEventCreate(&s->ev0));
@@ -766,20 +377,15 @@ int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out)
     if ((desc->nmaterials && !desc->materials) || (desc->nobjects && !desc->objects) || (desc->nlights && !desc->lights) ||
         (desc->nmeshes && !desc->meshes))
         return fail(RPTB_ERR_BAD_ARG, "null table with non-zero count");
-    for (uint32_t i = 0; i < desc->nobjects; i++) {
-        const int rc = validate_object(desc, desc->objects[i], "object", i);
-        if (rc != RPTB_OK) return rc;
+    if (desc->ngroups && !desc->groups) return fail(RPTB_ERR_BAD_ARG, "null table with non-zero count");
+    for (uint32_t i = 0; i < desc->nlights; i++)
+        if (desc->lights[i].kind == RPTB_LIGHT_OBJECT && desc->lights[i].object.kind == RPTB_SHAPE_PLANE)
+            return fail(RPTB_ERR_UNSUPPORTED, "light %u: a plane cannot be sampled (Plane::sample is unimplemented!() in the reference)", i);
+    {
+        std::string err;
+        const int vrc = validate_scene(desc, err);
+        if (vrc != RPTB_OK) return fail(vrc, "%s", err.c_str());
     }
-    for (uint32_t i = 0; i < desc->nlights; i++) {
-        if (desc->lights[i].kind > RPTB_LIGHT_OBJECT) return fail(RPTB_ERR_BAD_ARG, "light %u: bad kind", i);
-        if (desc->lights[i].kind == RPTB_LIGHT_OBJECT) {
-            const int rc = validate_object(desc, desc->lights[i].object, "light", i);
-            if (rc != RPTB_OK) return rc;
-            if (desc->lights[i].object.kind == RPTB_SHAPE_PLANE)
-                return fail(RPTB_ERR_UNSUPPORTED, "light %u: a plane cannot be sampled (Plane::sample is unimplemented!() in the reference)", i);
-        }
-    }
-    if (desc->environment.kind > RPTB_ENV_HDRI) return fail(RPTB_ERR_BAD_ARG, "bad environment kind");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RPTB_ERR_NO_DEVICE, "no CUDA device");
     if (device < 0 || device >= ndev) return fail(RPTB_ERR_BAD_ARG, "device %d of %d", device, ndev);

@@ -176,13 +176,13 @@ RPTB_D bool tri_intersect(const MeshRec<double>& m, uint32_t tri, Vec3<double> o
 RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, Vec3<float> d, float tmin,
                           float& rec_t, float& bv, float& bw) {
     const float4* q = m.tri48 + 3 * (size_t)tri;
-    const float4 q0 = __ldg(q);
+    const float4 q0 = ldg(q);
     const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
     if (fabsf(cosine) < 1e-8f) return false;
-    const float time = __fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+    const float time = fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
     if (time < tmin || time >= rec_t) return false;
-    const float4 q1 = __ldg(q + 1);
-    const float4 q2 = __ldg(q + 2);
+    const float4 q1 = ldg(q + 1);
+    const float4 q2 = ldg(q + 2);
     const float px = fmaf(time, d.x, o.x), py = fmaf(time, d.y, o.y), pz = fmaf(time, d.z, o.z);
     const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
     const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
@@ -198,7 +198,7 @@ RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, 
 
 // ------------------------------------------------------------ kd traversal -----
 RPTB_D KdNodeDev load_node(const KdNodeDev* p) {
-    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const uint2 v = ldg(reinterpret_cast<const uint2*>(p));
     KdNodeDev n;
     n.first_ref = v.x;
     n.word = v.y;
@@ -226,7 +226,7 @@ RPTB_D bool kd_intersect(const SceneView<R>& sv, const MeshRec<R>& m, Vec3<R> o,
             const float4 q0 = sv.small.tri48[3 * (base + tri)];
             const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
             if (fabsf(cosine) < 1e-8f) continue;
-            const float time = __fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+            const float time = fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
             if (time < tmin || time >= h.t) continue;
             const float4 q1 = sv.small.tri48[3 * (base + tri) + 1];
             const float4 q2 = sv.small.tri48[3 * (base + tri) + 2];
@@ -322,7 +322,7 @@ RPTB_D bool kd_intersect(const SceneView<R>& sv, const MeshRec<R>& m, Vec3<R> o,
             const uint32_t first_ref = node_first_ref(nd);
             const uint32_t count = nd.word >> 2;
             for (uint32_t i = 0; i < count; i++) {
-                const uint32_t tri = __ldg(m.refs + first_ref + i);
+                const uint32_t tri = ldg(m.refs + first_ref + i);
                 if (STATS) ts.tri_tests++;
                 if (tri_intersect(m, tri, o, d, tmin, h.t, h.bv, h.bw)) {
                     h.aux = tri;
@@ -409,7 +409,7 @@ RPTB_D Surface<R> finalize_hit(const SceneView<R>& sv, const ObjectRec<R>& ob, V
             const Vec3<R> n1 = {p[0], p[1], p[2]}, n2 = {p[3], p[4], p[5]}, n3 = {p[6], p[7], p[8]};
             n = M<R>::normalize(u * n1 + h.bv * n2 + h.bw * n3);  // mesh.rs:77
             if (!M<R>::literal) {
-                const float4 q0 = __ldg(m.tri48 + 3 * (size_t)h.aux);
+                const float4 q0 = ldg(m.tri48 + 3 * (size_t)h.aux);
                 ng = mk((R)q0.x, (R)q0.y, (R)q0.z);
             } else {
                 ng = n;
@@ -426,5 +426,39 @@ RPTB_D Surface<R> finalize_hit(const SceneView<R>& sv, const ObjectRec<R>& ob, V
     s.ng = ng;
     return s;
 }
+
+// get_closest_hit: linear scan of scene.objects.  `any` = shadow query (the first
+// object with a hit at t < h.t ends the scan; the caller preloads h.t with the light
+// distance).
+template <class R, bool STATS, int FEAT = F_ALL>
+RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
+    h.obj = -1;
+    h.aux = 0;
+    h.bv = h.bw = (R)0;
+    const uint32_t n = sv.nobjects;
+    for (uint32_t i = 0; i < n; i++) {
+        if (STATS) ts.object_tests++;
+        bool hit;
+        if constexpr ((FEAT & F_SMALL) != 0 && !M<R>::literal) hit = object_intersect<R, STATS, FEAT>(sv, sv.small.objects[i], o, d, tmin, any, h, ts);
+        else hit = object_intersect<R, STATS, FEAT>(sv, sv.objects[i], o, d, tmin, any, h, ts);
+        if (hit) {
+            h.obj = (int)i;
+            if (any) return;
+        }
+    }
+}
+
+// f32 only: start the next ray a few ulps off the surface, on the side it leaves from.
+// The reference restarts exactly at the hit point with t_min = 1e-12, which only works
+// in f64 ("f64 -> f32").
+RPTB_D Vec3<float> offset_origin(Vec3<float> p, Vec3<float> ng, Vec3<float> dir, float scale) {
+    const float delta = 1.9073486e-6f * scale;  // 32 * 2^-24 * max |coordinate| involved
+    const float s = dot(dir, ng) >= 0.0f ? delta : -delta;
+    return {fmaf(s, ng.x, p.x), fmaf(s, ng.y, p.y), fmaf(s, ng.z, p.z)};
+}
+RPTB_D Vec3<double> offset_origin(Vec3<double> p, Vec3<double>, Vec3<double>, double) { return p; }
+
+template <class R>
+RPTB_D R max_abs3(Vec3<R> a) { return M<R>::max(M<R>::max(M<R>::abs(a.x), M<R>::abs(a.y)), M<R>::abs(a.z)); }
 
 }  // namespace rptb

@@ -72,40 +72,6 @@ struct PathCounters {
     TravStats ts;
 };
 
-// get_closest_hit: linear scan of scene.objects.  `any` = shadow query (the first
-// object with a hit at t < h.t ends the scan; the caller preloads h.t with the light
-// distance).
-template <class R, bool STATS, int FEAT = F_ALL>
-RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
-    h.obj = -1;
-    h.aux = 0;
-    h.bv = h.bw = (R)0;
-    const uint32_t n = sv.nobjects;
-    for (uint32_t i = 0; i < n; i++) {
-        if (STATS) ts.object_tests++;
-        bool hit;
-        if constexpr ((FEAT & F_SMALL) != 0 && !M<R>::literal) hit = object_intersect<R, STATS, FEAT>(sv, sv.small.objects[i], o, d, tmin, any, h, ts);
-        else hit = object_intersect<R, STATS, FEAT>(sv, sv.objects[i], o, d, tmin, any, h, ts);
-        if (hit) {
-            h.obj = (int)i;
-            if (any) return;
-        }
-    }
-}
-
-// f32 only: start the next ray a few ulps off the surface, on the side it leaves from.
-// The reference restarts exactly at the hit point with t_min = 1e-12, which only works
-// in f64 ("f64 -> f32").
-RPTB_D Vec3<float> offset_origin(Vec3<float> p, Vec3<float> ng, Vec3<float> dir, float scale) {
-    const float delta = 1.9073486e-6f * scale;  // 32 * 2^-24 * max |coordinate| involved
-    const float s = dot(dir, ng) >= 0.0f ? delta : -delta;
-    return {fmaf(s, ng.x, p.x), fmaf(s, ng.y, p.y), fmaf(s, ng.z, p.z)};
-}
-RPTB_D Vec3<double> offset_origin(Vec3<double> p, Vec3<double>, Vec3<double>, double) { return p; }
-
-template <class R>
-RPTB_D R max_abs3(Vec3<R> a) { return M<R>::max(M<R>::max(M<R>::abs(a.x), M<R>::abs(a.y)), M<R>::abs(a.z)); }
-
 // scene.lights[i]: from parameter space when the scene's tables ride in the kernel parameters
 template <int FEAT, class R>
 RPTB_D const LightRec<R>& scene_light(const SceneView<R>& sv, uint32_t i) {

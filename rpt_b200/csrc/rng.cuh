@@ -110,6 +110,8 @@ struct Rng<double> {
         if (prob >= 1.0) return true;
         return v < (uint64_t)(prob * 18446744073709551616.0);
     }
+    // Rng::gen::<bool>(): the top bit of one draw
+    RPTB_HD bool coin() { return (p.next_u64() >> 63) != 0; }
     // Uniform::from(0..n) for usize: widening multiply with rejection zone
     RPTB_HD uint64_t below(uint64_t n) {
         const uint64_t ints_to_reject = (0xFFFFFFFFFFFFFFFFull - n + 1) % n;
@@ -182,6 +184,7 @@ struct Rng<float> {
         if (prob >= 1.0f) return true;
         return v < (uint32_t)((uint64_t)((double)prob * 18446744073709551616.0) >> 32);
     }
+    RPTB_HD bool coin() { return (next32() >> 31) != 0; }
     RPTB_HD uint64_t below(uint64_t n) {
 #ifdef __CUDA_ARCH__
         return (uint64_t)__umulhi(next32(), (uint32_t)n);

@@ -27,7 +27,7 @@
 
 namespace rptb {
 
-enum : uint32_t { SHAPE_SPHERE = 0, SHAPE_PLANE = 1, SHAPE_CUBE = 2, SHAPE_MESH = 3 };
+enum : uint32_t { SHAPE_SPHERE = 0, SHAPE_PLANE = 1, SHAPE_CUBE = 2, SHAPE_MESH = 3, SHAPE_MONOMIAL = 4, SHAPE_GROUP = 5 };
 enum : uint32_t { LIGHT_POINT = 0, LIGHT_AMBIENT = 1, LIGHT_DIRECTIONAL = 2, LIGHT_OBJECT = 3 };
 
 // Scene features a render kernel instantiation is compiled for.  The megakernel's hot loop is bound
@@ -35,10 +35,13 @@ enum : uint32_t { LIGHT_POINT = 0, LIGHT_AMBIENT = 1, LIGHT_DIRECTIONAL = 2, LIG
 // that provably lack a feature run a variant with that code compiled out.
 enum : int {
     F_TREE = 1 /* kd-trees beyond one leaf */, F_TRANSP = 2 /* transparent materials */, F_HDRI = 4, F_ALL = 7,
-    F_SMALL = 8 /* the scene tables fit SmallTables: read them from kernel-parameter (constant) space */
+    F_SMALL = 8 /* the scene tables fit SmallTables: read them from kernel-parameter (constant) space */,
+    F_GROUP = 16 /* kd-trees over whole shapes (KdTree<Box<dyn Bounded>>) */, F_MONO = 32 /* MonomialSurface */,
+    F_EXT = F_GROUP | F_MONO, F_EVERY = F_ALL | F_EXT /* the one instantiation that knows every shape */
 };
 
 constexpr int KD_STACK = 64;          // max kd-tree depth the traversal stack holds
+constexpr int GROUP_STACK = 32;       // same, for a kd-tree over whole shapes (a few thousand children at most)
 constexpr int MAX_CONST_OBJECTS = 96;  // tables up to this size live in __constant__ memory
 constexpr int MAX_CONST_LIGHTS = 16;
 
@@ -78,15 +81,27 @@ struct MeshRec {
 
 template <class R>
 struct ObjectRec {
-    uint32_t kind, material, mesh, has_transform;
+    uint32_t kind, material, mesh /* MESH: mesh index; GROUP: group index */, has_transform;
     R inv[12];  // rows of inverse_transform (3x4): local = inv * (p,1)
     R nrm[9];   // rows of normal_transform M^-T (3x3)
     R fwd[12];  // rows of transform (3x4), for Transformed::sample
     R det;      // `scale` = det(linear)
-    R plane_n[3];
-    R plane_v;
+    R plane_n[3];     // PLANE: normal.  MONOMIAL: plane_n[0] = exp
+    R plane_v;        // PLANE: value.   MONOMIAL: height
     R plane_unit[3];  // normalize(plane normal), precomputed
     R _pad;
+};
+
+// KdTree<Box<dyn Bounded>> (src/kdtree.rs:99-104 over shapes): the tree's refs index `children`, each a
+// Bounded shape with its own transform (a mesh child = one instance of meshes[child.mesh]).
+template <class R>
+struct GroupRec {
+    const typename NodeOf<R>::type* nodes;
+    const uint32_t* refs;
+    const ObjectRec<R>* children;
+    R bmin[3], bmax[3];  // KdTree::bounds = merge of the children's bounding boxes
+    uint32_t nchildren;
+    uint32_t root_is_leaf;
 };
 
 template <class R>
@@ -137,6 +152,8 @@ struct SceneView {
     const MeshRec<R>* meshes;
     uint32_t nobjects, nlights, nmaterials, nmeshes;
     uint32_t tables_in_const;  // F_SMALL: `small` is filled
+    uint32_t ngroups;
+    const GroupRec<R>* groups;  // F_GROUP
     EnvRec<R> env;
     SmallTables<R> small;
 };

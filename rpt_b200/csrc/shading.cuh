@@ -323,7 +323,7 @@ RPTB_D Vec3<R> env_texel(const EnvRec<R>& e, uint32_t x, uint32_t y) {
         const double* p = e.texels_f64 + 3 * ((size_t)y * e.width + x);
         return mk((R)p[0], (R)p[1], (R)p[2]);
     }
-    const float4 t = __ldg(e.texels_f4 + (size_t)y * e.width + x);
+    const float4 t = ldg(e.texels_f4 + (size_t)y * e.width + x);
     return mk((R)t.x, (R)t.y, (R)t.z);
 }
 template <class R, int FEAT = F_ALL>

@@ -10,7 +10,13 @@
 #include <stdint.h>
 
 #define RPTB_HD __host__ __device__ __forceinline__
+#ifdef RPTB_HOST_EMU
+// tests/hostemu only (test infrastructure, never part of librpt_b200.so): the device functions are
+// also compiled for the host, so their control flow can be checked against the oracle without a GPU.
+#define RPTB_D __host__ __device__ __forceinline__
+#else
 #define RPTB_D __device__ __forceinline__
+#endif
 
 namespace rptb {
 
@@ -98,6 +104,23 @@ struct M<float> {
     static RPTB_HD bool isnormal(float x) { return ::fabsf(x) >= 1.17549435e-38f && ::fabsf(x) < INFINITY; }
     static RPTB_HD float next_up(float x) { return ::nextafterf(x, INFINITY); }
 };
+
+// read-only global load / fast divide (plain equivalents in the host emulation build)
+template <class T>
+RPTB_D T ldg(const T* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+RPTB_D float fdividef(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
 
 // Rust f64::signum: +1 for +0.0, -1 for -0.0
 template <class R>

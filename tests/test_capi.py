@@ -24,16 +24,27 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name)
 
 
-def test_struct_layouts_match_header_sizes():
-    # sizes implied by the header's field lists (natural alignment, explicit pads)
-    assert C.sizeof(capi.Material) == 64
-    assert C.sizeof(capi.KdNode) == 32
-    assert C.sizeof(capi.Mesh) == 48
-    assert C.sizeof(capi.Object) == 16 + 128 + 32
-    assert C.sizeof(capi.Light) == 8 + 48 + C.sizeof(capi.Object)
-    assert C.sizeof(capi.Camera) == 96
-    assert C.sizeof(capi.RenderParams) == 64
-    assert C.sizeof(capi.Stats) == 72
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """The ctypes mirrors against the header itself: a C program compiled from include/rpt_b200.h
+    prints sizeof() of every struct that crosses the boundary."""
+    import subprocess
+    names = {"rptb_material": capi.Material, "rptb_kdnode": capi.KdNode, "rptb_mesh": capi.Mesh,
+             "rptb_object": capi.Object, "rptb_group": capi.Group, "rptb_light": capi.Light, "rptb_env": capi.Env,
+             "rptb_scene_desc": capi.SceneDesc, "rptb_camera": capi.Camera, "rptb_render_params": capi.RenderParams,
+             "rptb_stats": capi.Stats, "rptb_kdtree_out": capi.KdTreeOut, "rptb_obj_group": capi.ObjGroup,
+             "rptb_obj_groups_out": capi.ObjGroupsOut}
+    src = tmp_path / "sizes.c"
+    body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
+    src.write_text('#include <stdio.h>\n#include "rpt_b200.h"\nint main(void){' + body + 'return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    for n, t in names.items():
+        assert int(got[n]) == C.sizeof(t), n
+    # and the sizes the docs quote
+    assert C.sizeof(capi.Material) == 64 and C.sizeof(capi.KdNode) == 32 and C.sizeof(capi.Camera) == 96
+    assert C.sizeof(capi.RenderParams) == 64 and C.sizeof(capi.Stats) == 72
+    assert C.sizeof(capi.Object) == 16 + 128 + 32 + 16
 
 
 def test_build_kdtree_runs_on_host_and_matches_oracle(orc):
