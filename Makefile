@@ -49,10 +49,17 @@ $(ORACLE): oracle/oracle.cpp include/rpt_b200.h
 	$(CXX) -std=c++17 -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp -fPIC -shared -Wall -Wextra -o $@ $<
 
 # C++ host mirror example (needs a GPU to run)
-examples: build/sphere_cpp
-build/sphere_cpp: examples/sphere.cpp include/rpt.hpp include/rpt_b200.h $(LIB)
+examples: build/sphere_cpp build/fractal_spheres_cpp
+build/%_cpp: examples/%.cpp include/rpt.hpp include/rpt_b200.h $(LIB)
 	$(CXX) -std=c++17 -O2 -Wall -o $@ $< -Lrpt_b200/lib -lrpt_b200 -Wl,-rpath,'$$ORIGIN/../rpt_b200/lib'
 
+# test infrastructure: the device geometry functions compiled for the host (tests/hostemu/hostemu.cu)
+HOSTEMU := tests/hostemu/_build/libhostemu.so
+hostemu: $(HOSTEMU)
+$(HOSTEMU): tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp $(HDRS)
+	@mkdir -p $(dir $@)
+	nvcc -std=c++17 -O2 -DRPTB_HOST_EMU -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fopenmp,-ffp-contract=off -shared -o $@ tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp -lgomp
+
 clean:
-	rm -rf build $(LIB) $(ORACLE)
-.PHONY: all lib oracle examples clean
+	rm -rf build $(LIB) $(ORACLE) tests/hostemu/_build
+.PHONY: all lib oracle examples hostemu clean

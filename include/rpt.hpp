@@ -76,7 +76,9 @@ struct Shape {
     uint32_t kind = RPTB_SHAPE_SPHERE;
     Vec3 plane_normal;
     double plane_value = 0;
-    std::shared_ptr<Mesh> mesh;
+    std::shared_ptr<Mesh> mesh;                           // MESH; copies of a Shape share it (Arc<Mesh>)
+    double monomial_height = 0, monomial_exp = 4;           // MONOMIAL
+    std::shared_ptr<std::vector<Shape>> children;           // GROUP: KdTree<Box<dyn Bounded>>::objects
     bool has_transform = false;
     Mat4 matrix;
     // Transformable: chaining composes, new * self.transform (src/shape.rs:234-284)
@@ -91,6 +93,16 @@ struct Shape {
 inline Shape sphere() { return Shape{}; }
 inline Shape cube() { Shape s; s.kind = RPTB_SHAPE_CUBE; return s; }
 inline Shape plane(Vec3 normal, double value) { Shape s; s.kind = RPTB_SHAPE_PLANE; s.plane_normal = normal; s.plane_value = value; return s; }
+inline Shape monomial_surface(double height, double exp) {  // src/shape.rs:292-294
+    Shape s; s.kind = RPTB_SHAPE_MONOMIAL; s.monomial_height = height; s.monomial_exp = exp; return s;
+}
+// KdTree::new(objects) over whole Bounded shapes (src/kdtree.rs:108-119): spheres, cubes, monomial surfaces and
+// meshes, bare or transformed -- the kd-tree of kd-trees of examples/fractal_teapots.rs.  The library builds the tree.
+inline Shape KdTree(std::vector<Shape> objects) {
+    for (const Shape& c : objects)
+        if (c.kind == RPTB_SHAPE_PLANE || c.kind == RPTB_SHAPE_GROUP) throw std::invalid_argument("rpt::KdTree: child is not a supported Bounded shape");
+    Shape s; s.kind = RPTB_SHAPE_GROUP; s.children = std::make_shared<std::vector<Shape>>(std::move(objects)); return s;
+}
 inline Shape polygon(const std::vector<Vec3>& v) {  // triangle fan, src/shape.rs:307-313
     Shape s;
     s.kind = RPTB_SHAPE_MESH;
@@ -303,23 +315,47 @@ private:
         if (handle_) return;
         std::vector<rptb_material> mats;
         std::vector<rptb_mesh> meshes;
-        auto to_object = [&](const Object& o) {
+        std::vector<const Mesh*> mesh_ids;                       // one rptb_mesh per distinct Mesh (instancing)
+        std::vector<rptb_group> groups;
+        std::vector<std::unique_ptr<std::vector<rptb_object>>> group_children;  // owned until rptb_scene_create returns
+        std::function<rptb_object(const Shape&)> to_shape = [&](const Shape& sh) {
             rptb_object r{};
-            r.kind = o.shape.kind;
+            r.kind = sh.kind;
+            r.has_transform = sh.has_transform ? 1u : 0u;
+            const Mat4 m = sh.has_transform ? sh.matrix : Mat4();
+            for (int i = 0; i < 16; i++) r.transform[i] = m.m[i];
+            r.plane_normal[0] = sh.plane_normal.x; r.plane_normal[1] = sh.plane_normal.y; r.plane_normal[2] = sh.plane_normal.z;
+            r.plane_value = sh.plane_value;
+            r.monomial_height = sh.monomial_height;
+            r.monomial_exp = sh.monomial_exp;
+            if (sh.kind == RPTB_SHAPE_MESH) {
+                size_t k = 0;
+                while (k < mesh_ids.size() && mesh_ids[k] != sh.mesh.get()) k++;
+                if (k == mesh_ids.size()) {
+                    rptb_mesh cm{};
+                    cm.tris = sh.mesh->tris.data();
+                    cm.ntris = sh.mesh->tris.size() / 18;
+                    meshes.push_back(cm);
+                    mesh_ids.push_back(sh.mesh.get());
+                }
+                r.mesh = (uint32_t)k;
+            }
+            if (sh.kind == RPTB_SHAPE_GROUP) {
+                auto kids = std::make_unique<std::vector<rptb_object>>();
+                for (const Shape& c : *sh.children) kids->push_back(to_shape(c));
+                rptb_group g{};
+                g.children = kids->data();
+                g.nchildren = kids->size();
+                r.mesh = (uint32_t)groups.size();
+                groups.push_back(g);
+                group_children.push_back(std::move(kids));
+            }
+            return r;
+        };
+        auto to_object = [&](const Object& o) {
+            rptb_object r = to_shape(o.shape);
             r.material = (uint32_t)mats.size();
             mats.push_back(to_c(o.mat));
-            r.has_transform = o.shape.has_transform ? 1u : 0u;
-            const Mat4 m = o.shape.has_transform ? o.shape.matrix : Mat4();
-            for (int i = 0; i < 16; i++) r.transform[i] = m.m[i];
-            r.plane_normal[0] = o.shape.plane_normal.x; r.plane_normal[1] = o.shape.plane_normal.y; r.plane_normal[2] = o.shape.plane_normal.z;
-            r.plane_value = o.shape.plane_value;
-            if (o.shape.kind == RPTB_SHAPE_MESH) {
-                rptb_mesh cm{};
-                cm.tris = o.shape.mesh->tris.data();
-                cm.ntris = o.shape.mesh->tris.size() / 18;
-                r.mesh = (uint32_t)meshes.size();
-                meshes.push_back(cm);
-            }
             return r;
         };
         std::vector<rptb_object> objs;
@@ -338,6 +374,7 @@ private:
         d.meshes = meshes.data(); d.nmeshes = (uint32_t)meshes.size();
         d.objects = objs.data(); d.nobjects = (uint32_t)objs.size();
         d.lights = lights.data(); d.nlights = (uint32_t)lights.size();
+        d.groups = groups.data(); d.ngroups = (uint32_t)groups.size();
         d.environment.kind = RPTB_ENV_COLOR;
         d.environment.color[0] = scene_.environment.x; d.environment.color[1] = scene_.environment.y; d.environment.color[2] = scene_.environment.z;
         if (rptb_scene_create(&d, device_, &handle_) != RPTB_OK) throw std::runtime_error(rptb_last_error());

@@ -255,6 +255,7 @@ int check_params(const rptb_scene* s, const rptb_camera* cam, const rptb_render_
 // Which schedule renders this call (include/rpt_b200.h, rptb_engine).
 bool use_wavefront(const rptb_scene* s, const rptb_render_params* p) {
     if (p->precision != RPTB_PRECISION_F32) return false;
+    if (s->features & F_EXT) return false;  // kd-trees over shapes / MonomialSurface: megakernel only
     if (p->engine == RPTB_ENGINE_WAVEFRONT) return true;
     if (p->engine == RPTB_ENGINE_MEGAKERNEL) return false;
     // measured on one B200: the megakernel wins while traversal is cheap (teapot: 2 487 nodes,

@@ -8,7 +8,8 @@
 //   Cube::intersect                  src/shape/cube.rs:20-72
 //   Triangle::intersect              src/shape/mesh.rs:49-82
 //   BoundingBox::intersect           src/kdtree.rs:54-68
-//   KdTree::intersect/_subtree       src/kdtree.rs:129-136,151-223
+//   KdTree::intersect/_subtree       src/kdtree.rs:129-136,151-223  (over triangles, and over whole shapes)
+//   MonomialSurface::intersect       src/shape/monomial_surface.rs:21-105
 //   Renderer::get_closest_hit        src/renderer.rs:211-220
 //
 // Design (not a port): the reference recurses through a pointer tree carrying a
@@ -32,6 +33,7 @@ struct Hit {
     int obj;       // index into scene.objects, -1 = miss
     uint32_t aux;  // MESH: triangle index; CUBE: axis*2 + (normal positive ? 1 : 0)
     R bv, bw;      // MESH: barycentrics v, w
+    uint32_t child;  // GROUP: which child of the kd-tree of shapes was hit (aux/bv/bw then describe the child's hit)
 };
 
 struct TravStats {
@@ -140,6 +142,67 @@ RPTB_D bool cube_intersect(Vec3<R> o, Vec3<R> d, R tmin, R& rec_t, uint32_t& cod
         return true;
     }
     return false;
+}
+
+// ------------------------------------------------------- monomial surface ------
+// y = height * (x^2 + z^2)^2 over the unit disc, the reference's scheme kept step for step: slab test of
+// the bounding box, Newton towards the maximum of dist(t) when the ray starts below the surface, then 60
+// bisections between t_min and that point (or t = 10000).  Which crossing it returns depends on t_min;
+// callers inside a kd-tree pass the cell's t_min exactly as KdTree::intersect_subtree does.
+template <class R>
+RPTB_D bool monomial_intersect(R height, Vec3<R> o, Vec3<R> d, R tmin, R& rec_t) {
+    R b_min, b_max;
+    {
+        const R x1 = ((R)-1 - o.x) / d.x, x2 = ((R)1 - o.x) / d.x;
+        const R y1 = ((R)0 - o.y) / d.y, y2 = (height - o.y) / d.y;
+        const R z1 = ((R)-1 - o.z) / d.z, z2 = ((R)1 - o.z) / d.z;
+        b_min = M<R>::max(M<R>::max(M<R>::min(x1, x2), M<R>::min(y1, y2)), M<R>::min(z1, z2));
+        b_max = M<R>::min(M<R>::min(M<R>::max(x1, x2), M<R>::max(y1, y2)), M<R>::max(z1, z2));
+    }
+    if (M<R>::max(b_min, tmin) > M<R>::min(b_max, rec_t)) return false;
+    auto dist = [&](R t) {
+        const R x = o.x + t * d.x, y = o.y + t * d.y, z = o.z + t * d.z;
+        const R r2 = x * x + z * z;
+        return y - height * (r2 * r2);
+    };
+    const R coef0 = o.x * o.x + o.z * o.z;
+    const R coef1 = (R)2 * (o.x * d.x + o.z * d.z);
+    const R coef2 = d.x * d.x + d.z * d.z;
+    auto deriv = [&](R t) {
+        const R dy = (R)2 * coef0 * coef1 + (R)2 * t * (coef1 * coef1 + (R)2 * coef0 * coef2) +
+                     (R)3 * (t * t) * (R)2 * coef1 * coef2 + (R)4 * (t * (t * t)) * coef2 * coef2;
+        return d.y - height * dy;
+    };
+    auto deriv2 = [&](R t) {
+        const R dy = (R)2 * (coef1 * coef1 + (R)2 * coef0 * coef2) + (R)3 * (R)2 * t * (R)2 * coef1 * coef2 +
+                     (R)4 * (R)3 * (t * t) * coef2 * coef2;
+        return -height * dy;
+    };
+    const bool maximize = dist(tmin) < (R)0;
+    R t_max;
+    if (maximize) {
+        R cur = (b_min + b_max) / (R)2;
+        for (int it = 0; it < 10; it++) {
+            if (dist(cur) > (R)0) break;
+            cur -= deriv(cur) / deriv2(cur);
+        }
+        t_max = cur;
+        if (t_max < tmin) return false;
+    } else {
+        t_max = (R)10000;
+    }
+    if ((dist(tmin) < (R)0) == (dist(t_max) < (R)0)) return false;
+    R l = tmin, r = t_max;
+    for (int it = 0; it < 60; it++) {
+        const R m = (l + r) / (R)2;
+        if ((dist(m) >= (R)0) == maximize) r = m;
+        else l = m;
+    }
+    if (r > rec_t) return false;
+    const R px = o.x + r * d.x, pz = o.z + r * d.z;
+    if (px * px + pz * pz > (R)1) return false;  // beyond the rim
+    rec_t = r;
+    return true;
 }
 
 // -------------------------------------------------------------- triangle ------
@@ -344,6 +407,10 @@ RPTB_D bool kd_intersect(const SceneView<R>& sv, const MeshRec<R>& m, Vec3<R> o,
 }
 
 // ------------------------------------------------------- object dispatch ------
+template <class R, bool STATS, int FEAT>
+RPTB_D bool group_intersect(const SceneView<R>& sv, const GroupRec<R>& g, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h,
+                            TravStats& ts);
+
 template <class R, bool STATS, int FEAT = F_ALL>
 RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> o, Vec3<R> d, R tmin, bool any,
                              Hit<R>& h, TravStats& ts) {
@@ -353,6 +420,10 @@ RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec
         o = lo;
         d = ld;
     }
+    if constexpr ((FEAT & F_MONO) != 0)
+        if (ob.kind == SHAPE_MONOMIAL) return monomial_intersect(ob.plane_v, o, d, tmin, h.t);
+    if constexpr ((FEAT & F_GROUP) != 0)
+        if (ob.kind == SHAPE_GROUP) return group_intersect<R, STATS, FEAT>(sv, sv.groups[ob.mesh], o, d, tmin, any, h, ts);
     switch (ob.kind) {
         case SHAPE_SPHERE: return sphere_intersect(o, d, tmin, h.t);
         case SHAPE_PLANE: return plane_intersect(ob.plane_n, ob.plane_v, o, d, tmin, h.t);
@@ -360,6 +431,84 @@ RPTB_D bool object_intersect(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec
         default:
             if constexpr ((FEAT & F_SMALL) != 0 && !M<R>::literal) return kd_intersect<R, STATS, FEAT>(sv, sv.small.meshes[ob.mesh], o, d, tmin, any, h, ts);
             else return kd_intersect<R, STATS, FEAT>(sv, sv.meshes[ob.mesh], o, d, tmin, any, h, ts);
+    }
+}
+
+// KdTree<Box<dyn Bounded>>::intersect (src/kdtree.rs:129-136,151-223) over whole shapes: the traversal of
+// kd_intersect, with two differences the reference's recursion implies once the leaves hold arbitrary
+// shapes instead of triangles.  (1) A child is intersected with the t_min its cell received: the far
+// child of a straddled split gets t_min := t_split (kdtree.rs:219), and MonomialSurface::intersect is
+// sensitive to it.  (2) A child is a full shape: its own transform, and for a mesh its own kd-tree
+// (kd_intersect with its own stack) -- the two-level instancing of examples/fractal_teapots.rs.
+template <class R, bool STATS, int FEAT>
+RPTB_D bool group_intersect(const SceneView<R>& sv, const GroupRec<R>& g, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h,
+                            TravStats& ts) {
+    constexpr int CHILD = FEAT & ~F_GROUP;  // children are never groups
+    R lo, hi;
+    {  // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
+        const R x1 = (g.bmin[0] - o.x) / d.x, x2 = (g.bmax[0] - o.x) / d.x;
+        const R y1 = (g.bmin[1] - o.y) / d.y, y2 = (g.bmax[1] - o.y) / d.y;
+        const R z1 = (g.bmin[2] - o.z) / d.z, z2 = (g.bmax[2] - o.z) / d.z;
+        lo = M<R>::max(M<R>::max(M<R>::min(x1, x2), M<R>::min(y1, y2)), M<R>::min(z1, z2));
+        hi = M<R>::min(M<R>::min(M<R>::max(x1, x2), M<R>::max(y1, y2)), M<R>::max(z1, z2));
+        if (M<R>::max(lo, tmin) > M<R>::min(hi, h.t)) return false;
+    }
+    uint32_t st_node[GROUP_STACK];
+    R st_lo[GROUP_STACK], st_hi[GROUP_STACK], st_tmin[GROUP_STACK];
+    int sp = 0;
+    uint32_t node = 0;
+    R cur_tmin = tmin;
+    bool hit = false;
+    while (true) {
+        auto nd = load_node(g.nodes + node);
+        while ((nd.word & 3u) != 3u) {
+            if (STATS) ts.node_visits++;
+            const uint32_t axis = nd.word & 3u;
+            const uint32_t right = nd.word >> 2;
+            const R split = node_split(nd);
+            const R oa = comp(o, (int)axis), da = comp(d, (int)axis);
+            const R t_split = (split - oa) / da;
+            const bool left_first = (oa < split) || (oa == split && da <= (R)0);
+            const uint32_t first = left_first ? node + 1u : right;
+            const uint32_t second = left_first ? right : node + 1u;
+            if (t_split > M<R>::min(hi, h.t) || t_split <= (R)0) {
+                node = first;  // (i) near only
+            } else if (t_split < M<R>::max(lo, cur_tmin)) {
+                node = second;  // (ii) far only
+            } else {  // (iii) near, then far with t_min := t_split
+                st_node[sp] = second;
+                st_lo[sp] = t_split;
+                st_hi[sp] = hi;
+                st_tmin[sp] = t_split;
+                sp++;
+                node = first;
+                hi = t_split;
+            }
+            nd = load_node(g.nodes + node);
+        }
+        if (STATS) ts.node_visits++;
+        {
+            const uint32_t first_ref = node_first_ref(nd);
+            const uint32_t count = nd.word >> 2;
+            for (uint32_t i = 0; i < count; i++) {
+                const uint32_t c = ldg(g.refs + first_ref + i);
+                if (STATS) ts.object_tests++;
+                if (object_intersect<R, STATS, CHILD>(sv, g.children[c], o, d, cur_tmin, any, h, ts)) {
+                    h.child = c;
+                    hit = true;
+                }
+            }
+        }
+        if (any && hit) return true;
+        while (true) {  // pop; a far cell is skipped when the near side hit before its split (kdtree.rs:212-213)
+            if (sp == 0) return hit;
+            sp--;
+            node = st_node[sp];
+            lo = st_lo[sp];
+            hi = st_hi[sp];
+            cur_tmin = st_tmin[sp];
+            if (!(h.t < lo)) break;
+        }
     }
 }
 
@@ -371,7 +520,7 @@ struct Surface {
     bool on_mesh;
 };
 
-template <class R>
+template <class R, int FEAT = F_ALL>
 RPTB_D Surface<R> finalize_hit(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> o, Vec3<R> d, const Hit<R>& h) {
     Surface<R> s;
     if (ob.has_transform) {
@@ -382,6 +531,28 @@ RPTB_D Surface<R> finalize_hit(const SceneView<R>& sv, const ObjectRec<R>& ob, V
     }
     Vec3<R> n, ng;
     s.on_mesh = false;
+    if constexpr ((FEAT & F_GROUP) != 0)
+        if (ob.kind == SHAPE_GROUP) {
+            // the hit child finishes its own normal (its transform included); the group's transform, if
+            // any, is applied on top -- Transformed<KdTree<..>>::intersect wrapping the child's intersect
+            s = finalize_hit<R, FEAT & ~F_GROUP>(sv, sv.groups[ob.mesh].children[h.child], o, d, h);
+            if (ob.has_transform) {
+                s.n = M<R>::normalize(xform3(ob.nrm, s.n));
+                s.ng = M<R>::literal ? s.n : M<R>::normalize(xform3(ob.nrm, s.ng));
+            }
+            return s;
+        }
+    if constexpr ((FEAT & F_MONO) != 0)
+        if (ob.kind == SHAPE_MONOMIAL) {  // monomial_surface.rs:93-103
+            const Vec3<R> pos = o + h.t * d;
+            const R r2 = pos.x * pos.x + pos.z * pos.z;
+            n = M<R>::normalize(mk(ob.plane_v * (R)4 * pos.x * r2, (R)-1, ob.plane_v * (R)4 * pos.z * r2));
+            if (dot(n, d) > (R)0) n = -n;  // two-sided
+            if (ob.has_transform) n = M<R>::normalize(xform3(ob.nrm, n));
+            s.n = n;
+            s.ng = n;
+            return s;
+        }
     switch (ob.kind) {
         case SHAPE_SPHERE:
             n = M<R>::normalize(o + h.t * d);  // sphere.rs:40
@@ -435,6 +606,7 @@ RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bo
     h.obj = -1;
     h.aux = 0;
     h.bv = h.bw = (R)0;
+    if constexpr ((FEAT & F_GROUP) != 0) h.child = 0;
     const uint32_t n = sv.nobjects;
     for (uint32_t i = 0; i < n; i++) {
         if (STATS) ts.object_tests++;

@@ -21,7 +21,11 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             // take the parameter-space tables: teapot 5762 without vs 5181 Msamples/s with)
             const int base = features & F_ALL;
             const bool small = (features & F_SMALL) != 0;
-            if (stats) render_kernel<R, 16, true><<<grid, block, 0, stream>>>(sv, args);
+            // kd-trees over whole shapes and MonomialSurface live in one extra instantiation (F_EVERY), so
+            // the variants tuned for the BASELINE scenes carry none of that code
+            const bool ext = (features & F_EXT) != 0;
+            if (stats) render_kernel<R, 16, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            else if (ext) render_kernel<R, 16, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
             else if (!M<R>::literal && base == 0 && small) render_kernel<R, 16, false, F_SMALL><<<grid, block, 0, stream>>>(sv, args);
             else if (!M<R>::literal && base == 0) render_kernel<R, 16, false, 0><<<grid, block, 0, stream>>>(sv, args);
             else if (!M<R>::literal && base == F_TREE) render_kernel<R, 16, false, F_TREE><<<grid, block, 0, stream>>>(sv, args);
@@ -29,8 +33,8 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             else if (!M<R>::literal && base == (F_TRANSP | F_HDRI)) render_kernel<R, 16, false, F_TRANSP | F_HDRI><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
         } else {
-            if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true><<<grid, block, 0, stream>>>(sv, args);
-            else render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false><<<grid, block, 0, stream>>>(sv, args);
+            if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            else render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
         }
         nl++;
         if (args.nchunks > 1) {

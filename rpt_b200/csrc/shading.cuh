@@ -212,11 +212,32 @@ RPTB_D bool sample_f(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Rng<R>& rng
 
 // ------------------------------------------------------------- light shapes ---
 // Shape::sample of the light's object -> (point, normal, pdf per unit area)
-template <class R>
+template <class R, int FEAT = F_ALL>
 RPTB_D void shape_sample(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> target, Rng<R>& rng, Vec3<R>& v,
                          Vec3<R>& n, R& p) {
     if (ob.has_transform) target = xform_point(ob.inv, target);  // shape.rs:140
-    switch (ob.kind) {
+    bool done = false;
+    if constexpr ((FEAT & F_MONO) != 0)
+        if (ob.kind == SHAPE_MONOMIAL) {  // monomial_surface.rs:107-122: a point of the RIM (UnitCircle), either side
+            R x, z;
+            unit_circle(rng, x, z);
+            const R height = ob.plane_v;
+            const R r2 = x * x + z * z;
+            v = mk(x, height * M<R>::pow(r2, ob.plane_n[0] / (R)2), z);
+            n = M<R>::normalize(mk(height * (R)4 * x * r2, (R)-1, height * (R)4 * z * r2));
+            if (rng.coin()) n = -n;
+            p = (R)1 / ((R)2 * (R)6.3406654362);
+            done = true;
+        }
+    if constexpr ((FEAT & F_GROUP) != 0)
+        if (ob.kind == SHAPE_GROUP) {  // KdTree::sample, kdtree.rs:138-143: uniform child, pdf / num
+            const GroupRec<R>& g = sv.groups[ob.mesh];
+            const uint32_t index = (uint32_t)uniform_usize(rng, (uint64_t)g.nchildren);
+            shape_sample<R, FEAT & ~F_GROUP>(sv, g.children[index], target, rng, v, n, p);
+            p = p / (R)g.nchildren;
+            done = true;
+        }
+    if (!done) switch (ob.kind) {
         case SHAPE_SPHERE: {  // sphere.rs:52-64
             R x, y;
             unit_disc(rng, x, y);
@@ -282,7 +303,7 @@ RPTB_D void shape_sample(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R>
 }
 
 // Light::illuminate (light.rs:23-47) for the non-ambient kinds
-template <class R>
+template <class R, int FEAT = F_ALL>
 RPTB_D void illuminate(const SceneView<R>& sv, const LightRec<R>& l, Vec3<R> pos, Rng<R>& rng, Vec3<R>& intensity,
                        Vec3<R>& wi, R& dist) {
     const Vec3<R> color = {l.color[0], l.color[1], l.color[2]};
@@ -299,7 +320,7 @@ RPTB_D void illuminate(const SceneView<R>& sv, const LightRec<R>& l, Vec3<R> pos
     } else {
         Vec3<R> v, n;
         R p;
-        shape_sample(sv, l.object, pos, rng, v, n, p);
+        shape_sample<R, FEAT>(sv, l.object, pos, rng, v, n, p);
         const Vec3<R> disp = v - pos;
         const R len = M<R>::sqrt(length2(disp));
         const R cosine = M<R>::max(-dot(disp, n), (R)0) / len;

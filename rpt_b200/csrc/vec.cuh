@@ -68,6 +68,7 @@ struct M<double> {
     static RPTB_HD double max(double a, double b) { return ::fmax(a, b); }
     static RPTB_HD double exp(double x) { return ::exp(x); }
     static RPTB_HD double log(double x) { return ::log(x); }
+    static RPTB_HD double pow(double x, double y) { return ::pow(x, y); }
     static RPTB_HD double div(double a, double b) { return a / b; }
     static RPTB_HD double rcp(double a) { return 1.0 / a; }
     static RPTB_HD bool signbit(double x) { return ::signbit(x); }
@@ -99,6 +100,7 @@ struct M<float> {
     static float rcp(float a) { return 1.0f / a; }
     static Vec3<float> normalize(Vec3<float> a) { return a * (1.0f / ::sqrtf(dot(a, a))); }
 #endif
+    static RPTB_HD float pow(float x, float y) { return ::powf(x, y); }
     static RPTB_HD bool signbit(float x) { return ::signbit(x); }
     static RPTB_HD float copysign(float a, float b) { return ::copysignf(a, b); }
     static RPTB_HD bool isnormal(float x) { return ::fabsf(x) >= 1.17549435e-38f && ::fabsf(x) < INFINITY; }

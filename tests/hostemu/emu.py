@@ -1,0 +1,75 @@
+"""ctypes binding of tests/hostemu/_build/libhostemu.so -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+The device geometry functions (rpt_b200/csrc/geometry.cuh, shading.cuh) compiled for the host; see
+hostemu.cu.  Nothing under rpt_b200/ imports this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from rpt_b200 import _capi as capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libhostemu.so")
+_lib = None
+dp = capi.c_double_p
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-s", "hostemu"], cwd=os.path.dirname(os.path.dirname(_HERE)))
+        L = C.CDLL(LIB_PATH)
+        L.hostemu_scene_create.restype = C.c_void_p
+        L.hostemu_scene_create.argtypes = [C.POINTER(capi.SceneDesc), C.c_char_p, C.c_size_t]
+        L.hostemu_scene_destroy.argtypes = [C.c_void_p]
+        L.hostemu_scene_features.argtypes = [C.c_void_p]
+        L.hostemu_closest_hit.argtypes = [C.c_void_p, dp, C.c_uint64, C.c_double, C.c_uint32, dp, capi.c_i32_p, dp,
+                                          C.POINTER(capi.Stats)]
+        L.hostemu_illuminate.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_uint64, C.c_uint32, dp, dp, dp]
+        _lib = L
+    return _lib
+
+
+class EmuScene:
+    def __init__(self, flat):
+        self.flat = flat
+        err = C.create_string_buffer(512)
+        self.handle = C.c_void_p(lib().hostemu_scene_create(C.byref(flat.desc), err, 512))
+        if not self.handle:
+            raise ValueError(err.value.decode())
+
+    def close(self):
+        if self.handle:
+            lib().hostemu_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def features(self) -> int:
+        return int(lib().hostemu_scene_features(self.handle))
+
+    def closest_hit(self, rays, t_min=1e-12, precision=capi.PRECISION_F64):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        n = rays.shape[0]
+        t = np.empty(n)
+        obj = np.empty(n, np.int32)
+        nrm = np.empty((n, 3))
+        st = capi.Stats()
+        lib().hostemu_closest_hit(self.handle, rays.ctypes.data_as(dp), n, t_min, precision, t.ctypes.data_as(dp),
+                                  obj.ctypes.data_as(capi.c_i32_p), nrm.ctypes.data_as(dp), C.byref(st))
+        return t, obj, nrm, st.as_dict()
+
+    def illuminate(self, light, pos, seed=0, precision=capi.PRECISION_F64):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        n = pos.shape[0]
+        inten, wi, dist = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+        lib().hostemu_illuminate(self.handle, light, pos.ctypes.data_as(dp), n, seed, precision, inten.ctypes.data_as(dp),
+                                 wi.ctypes.data_as(dp), dist.ctypes.data_as(dp))
+        return inten, wi, dist
