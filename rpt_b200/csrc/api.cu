@@ -339,7 +339,7 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         a.counters = want_counters ? s->counters : nullptr;
         const int rc = ensure_partial(s, a);
         if (rc != RPTB_OK) return rc;
-        CU(launch_render_f64(s->view64, a, p->collect_stats != 0, F_ALL, stream, launches));
+        CU(launch_render_f64(s->view64, a, p->collect_stats != 0, F_ALL | (s->features & F_EXT), stream, launches));
     }
     return RPTB_OK;
 }

@@ -68,7 +68,8 @@ def test_closest_hit_parity(orc, cfgs, name):
     # f32 product path
     t2, o2, n2, _ = ds.closest_hit(rays, precision=F32, want_stats=True)
     agree = o2 == o0
-    tie = (o2 >= 0) & (o0 >= 0) & (np.abs(t2 - t0) <= 1e-5 * np.abs(t0))
+    with np.errstate(invalid="ignore"):  # inf - inf on rays that miss in both
+        tie = (o2 >= 0) & (o0 >= 0) & (np.abs(t2 - t0) <= 1e-5 * np.abs(t0))
     assert (agree | tie).mean() >= 0.999, (agree | tie).mean()
     assert agree.mean() >= 0.995
     hit = agree & (o0 >= 0)
@@ -95,7 +96,8 @@ def test_render_parity_same_stream(orc, cfgs, name):
     assert (rel.max(axis=1) < 1e-9).mean() >= 0.98
     assert abs(st64["segments"] - st0["segments"]) <= 2e-3 * st0["segments"]
     assert abs(st64["rays"] - st0["rays"]) <= 2e-3 * st0["rays"]
-    assert abs(st64["node_visits"] - st0["node_visits"]) <= 0.01 * max(st0["node_visits"], 1)
+    # (node visits are not compared here: shadow rays are any-hit queries on the device, full closest-hit
+    # queries in the reference -- same answer, fewer nodes; test_closest_hit_parity compares the counters)
     assert util.rmse(cl(g64), cl(ref)) <= 0.05 * noise
     g32, st32 = _gpu_render(cfg, ds, w, h, spp, mb, 1, F32)
     assert np.isfinite(g32).all()

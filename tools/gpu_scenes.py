@@ -1,15 +1,19 @@
-"""Per-config throughput table (all five BASELINE configs) on one GPU, reduced spp."""
+"""Per-config throughput table on one GPU, reduced spp: the five BASELINE configs, or with `extra` as the
+first argument the three row-N4 example scenes (kd-trees over whole shapes, MonomialSurface)."""
 import sys, os, json, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rpt_b200 import scenes, api, _capi as capi
 
 def main():
-    spps = {"sphere": 100, "cornell": 64, "teapot": 64, "dragon": 32, "glass": 64}
+    extra = len(sys.argv) > 1 and sys.argv[1] == "extra"
+    spps = {"sphere": 100, "cornell": 64, "teapot": 64, "dragon": 32, "glass": 64,
+            "fractal_spheres": 64, "fractal_teapots": 32, "monomial_glass": 100}
+    names = ["fractal_spheres", "fractal_teapots", "monomial_glass"] if extra else ["sphere", "cornell", "teapot", "dragon", "glass"]
     rows = []
-    for name in ["sphere", "cornell", "teapot", "dragon", "glass"]:
+    for name in names:
         t0 = time.time()
-        cfg = scenes.CONFIGS[name]()
+        cfg = (scenes.EXTRA_CONFIGS if extra else scenes.CONFIGS)[name]()
         build_s = time.time() - t0
         r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces).seed(1)
         t0 = time.time(); r.device_scene(); upload_s = time.time() - t0
@@ -31,7 +35,7 @@ def main():
         rows.append(row)
         print(json.dumps(row), flush=True)
         r.close()
-    json.dump(rows, open("gpurun_out/scenes_table.json", "w"), indent=1)
+    json.dump(rows, open("gpurun_out/scenes_table_extra.json" if extra else "gpurun_out/scenes_table.json", "w"), indent=1)
 
 if __name__ == "__main__":
     main()
