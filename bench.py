@@ -39,7 +39,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cornell", choices=["sphere", "cornell", "teapot", "dragon", "glass"])
+    ap.add_argument("--workload", default="cornell",
+                    choices=["sphere", "cornell", "teapot", "dragon", "glass",
+                             "fractal_spheres", "fractal_teapots", "monomial_glass"],  # the last three: exploration only
+                    help="default = the BASELINE configs[1] workload; anything else is for exploration / profiling")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (exploration only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -49,7 +52,7 @@ def parse_args():
 def workload(name: str, spp_override: int = 0):
     from rpt_b200 import scenes
 
-    cfg = scenes.CONFIGS[name]()
+    cfg = (scenes.CONFIGS[name] if name in scenes.CONFIGS else scenes.EXTRA_CONFIGS[name])()
     if spp_override:
         cfg.spp = spp_override
     return cfg

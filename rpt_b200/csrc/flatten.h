@@ -287,6 +287,7 @@ inline int flatten_mesh(const rptb_mesh& m, HostMesh& hm, std::string& err) {
 
 // One flattened kd-tree over whole shapes (rptb_group).
 struct HostGroup : FlatTree {
+    std::vector<float4> kid_boxes;  // 2 per child: Bounded::bounding_box in the group's space, widened for f32
     std::vector<ObjectRec<float>> kids32;
     std::vector<ObjectRec<double>> kids64;
     double bmin[3], bmax[3];
@@ -398,6 +399,13 @@ inline int flatten_group(const rptb_scene_desc* d, const rptb_group& g, uint32_t
         }
         fill_object(c, hg.kids32[i]);
         fill_object(c, hg.kids64[i]);
+        // the f32 path culls a child by this box before entering its space; widen it by more than the
+        // f32 rounding of the child's own transform can move a hit point (|x| * 2^-23 per operation)
+        float mag = 1.0f;
+        for (int a = 0; a < 6; a++) mag = std::fmax(mag, std::fabs((float)boxes[6 * i + a]));
+        const float eps = 8e-6f * mag;
+        hg.kid_boxes.push_back(make_float4((float)boxes[6 * i + 0] - eps, (float)boxes[6 * i + 1] - eps, (float)boxes[6 * i + 2] - eps, 0.0f));
+        hg.kid_boxes.push_back(make_float4((float)boxes[6 * i + 3] + eps, (float)boxes[6 * i + 4] + eps, (float)boxes[6 * i + 5] + eps, 0.0f));
     }
     int rc;
     if (g.nodes == nullptr) {
@@ -631,7 +639,7 @@ bool bind_scene(HostScene& hs, Put& put, bool release, SceneView<float>& v32, Sc
         GroupRec<float>& a = hs.t32.groups[i];
         GroupRec<double>& b = hs.t64.groups[i];
         const uint64_t before = put.bytes();
-        if (!put(hg.nodes32, &a.nodes) || !put(hg.refs, &a.refs) || !put(hg.kids32, &a.children)) return false;
+        if (!put(hg.nodes32, &a.nodes) || !put(hg.refs, &a.refs) || !put(hg.kids32, &a.children) || !put(hg.kid_boxes, &a.child_box)) return false;
         f32_bytes += put.bytes() - before;
         if (!put(hg.nodes64, &b.nodes) || !put(hg.kids64, &b.children)) return false;
         b.refs = a.refs;

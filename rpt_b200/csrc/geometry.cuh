@@ -445,6 +445,8 @@ RPTB_D bool group_intersect(const SceneView<R>& sv, const GroupRec<R>& g, Vec3<R
                             TravStats& ts) {
     constexpr int CHILD = FEAT & ~F_GROUP;  // children are never groups
     R lo, hi;
+    Vec3<R> inv = {(R)0, (R)0, (R)0};
+    if (!M<R>::literal) inv = {M<R>::rcp(d.x), M<R>::rcp(d.y), M<R>::rcp(d.z)};
     {  // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
         const R x1 = (g.bmin[0] - o.x) / d.x, x2 = (g.bmax[0] - o.x) / d.x;
         const R y1 = (g.bmin[1] - o.y) / d.y, y2 = (g.bmax[1] - o.y) / d.y;
@@ -492,6 +494,19 @@ RPTB_D bool group_intersect(const SceneView<R>& sv, const GroupRec<R>& g, Vec3<R
             const uint32_t count = nd.word >> 2;
             for (uint32_t i = 0; i < count; i++) {
                 const uint32_t c = ldg(g.refs + first_ref + i);
+                if constexpr (!M<R>::literal) {
+                    // f32 only (the f64 gate calls every child, like the reference): a ray that misses the
+                    // child's bounding box cannot hit the child, so skip the change of space, the three
+                    // reciprocals and the slab test of the instance's own root (profiles/
+                    // r01_render_kernel_fractal_teapots.md: ~40 children tested per ray, most of them missed)
+                    const float4 bl = ldg(g.child_box + 2 * c), bh = ldg(g.child_box + 2 * c + 1);
+                    const R x1 = ((R)bl.x - o.x) * inv.x, x2 = ((R)bh.x - o.x) * inv.x;
+                    const R y1 = ((R)bl.y - o.y) * inv.y, y2 = ((R)bh.y - o.y) * inv.y;
+                    const R z1 = ((R)bl.z - o.z) * inv.z, z2 = ((R)bh.z - o.z) * inv.z;
+                    const R c0 = M<R>::max(M<R>::max(M<R>::min(x1, x2), M<R>::min(y1, y2)), M<R>::min(z1, z2));
+                    const R c1 = M<R>::min(M<R>::min(M<R>::max(x1, x2), M<R>::max(y1, y2)), M<R>::max(z1, z2));
+                    if (M<R>::max(c0, cur_tmin) > M<R>::min(c1, h.t)) continue;
+                }
                 if (STATS) ts.object_tests++;
                 if (object_intersect<R, STATS, CHILD>(sv, g.children[c], o, d, cur_tmin, any, h, ts)) {
                     h.child = c;

@@ -99,6 +99,7 @@ struct GroupRec {
     const typename NodeOf<R>::type* nodes;
     const uint32_t* refs;
     const ObjectRec<R>* children;
+    const float4* child_box;  // f32 only: (lo.xyz, hi.xyz) of every child in the group's space, widened -- see group_intersect
     R bmin[3], bmax[3];  // KdTree::bounds = merge of the children's bounding boxes
     uint32_t nchildren;
     uint32_t root_is_leaf;

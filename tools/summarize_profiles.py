@@ -79,7 +79,10 @@ def main():
              "Dominant kernel of the bench workload (BASELINE configs[1]); one launch per step per GPU."),
             ("%s_wf_trace_dragon" % R, "dragon-proxy 1920x1080 (4 spp capture) -- rptb::wf_trace_kernel<false>",
              "_ZN4rptb15wf_trace_kernelILb0EEEvNS_9SceneViewIfEENS_9WfBuffersEPKjPNS_14DeviceCountersE", "dragon-proxy",
-             "Dominant kernel of the wavefront engine (one launch per path-vertex step).")]
+             "Dominant kernel of the wavefront engine (one launch per path-vertex step)."),
+            ("%s_render_kernel_fractal_teapots" % R, "examples/fractal_teapots 800x600 (8 spp capture) -- rptb::render_kernel<float,16,false,F_EVERY>",
+             "_ZN4rptb13render_kernelIfLi16ELb0ELi55EEEvNS_9SceneViewIT_EENS_10RenderArgsIS2_EE", "fractal_teapots",
+             "Row N4: kd-trees over 781 instances of one teapot kd-tree (tools/ncu_ext.sh); not a BASELINE config.")]
     for stem, title, kern, wl, note in jobs:
         rep = os.path.join(G, stem + ".ncu-rep")
         if not os.path.exists(rep):
@@ -98,7 +101,7 @@ def main():
     tpath = os.path.join(OUT, "ncu_traffic.json")
     old = json.load(open(tpath)) if os.path.exists(tpath) else {}
     note = old.get("_note", {})
-    spp = {"cornell": 32, "dragon-proxy": 4}
+    spp = {"cornell": 32, "dragon-proxy": 4, "fractal_teapots": 8}
     for k, v in traffic.items():
         old[k] = {"dram_bytes_per_launch": v, "capture_spp": spp[k]}
         note[k] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel in the %s capture, "
