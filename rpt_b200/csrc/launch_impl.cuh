@@ -26,11 +26,12 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             const bool ext = (features & F_EXT) != 0;
             if (stats) render_kernel<R, 16, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
             else if (ext) render_kernel<R, 16, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
-            else if (!M<R>::literal && base == 0 && small) render_kernel<R, 16, false, F_SMALL><<<grid, block, 0, stream>>>(sv, args);
-            else if (!M<R>::literal && base == 0) render_kernel<R, 16, false, 0><<<grid, block, 0, stream>>>(sv, args);
-            else if (!M<R>::literal && base == F_TREE) render_kernel<R, 16, false, F_TREE><<<grid, block, 0, stream>>>(sv, args);
-            else if (!M<R>::literal && base == (F_TRANSP | F_HDRI) && small) render_kernel<R, 16, false, F_TRANSP | F_HDRI | F_SMALL><<<grid, block, 0, stream>>>(sv, args);
-            else if (!M<R>::literal && base == (F_TRANSP | F_HDRI)) render_kernel<R, 16, false, F_TRANSP | F_HDRI><<<grid, block, 0, stream>>>(sv, args);
+            else if constexpr (M<R>::literal) render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);  // the f64 gate is not specialised
+            else if (base == 0 && small) render_kernel<R, 16, false, F_SMALL><<<grid, block, 0, stream>>>(sv, args);
+            else if (base == 0) render_kernel<R, 16, false, 0><<<grid, block, 0, stream>>>(sv, args);
+            else if (base == F_TREE) render_kernel<R, 16, false, F_TREE><<<grid, block, 0, stream>>>(sv, args);
+            else if (base == (F_TRANSP | F_HDRI) && small) render_kernel<R, 16, false, F_TRANSP | F_HDRI | F_SMALL><<<grid, block, 0, stream>>>(sv, args);
+            else if (base == (F_TRANSP | F_HDRI)) render_kernel<R, 16, false, F_TRANSP | F_HDRI><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
         } else {
             if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);

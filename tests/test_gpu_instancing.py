@@ -179,3 +179,20 @@ def test_cpp_host_mirror_builds_the_same_kd_trees_of_shapes(gpu_ok, tmp_path):
     img_py = r.render()
     r.close()
     np.testing.assert_array_equal(img_cpp, img_py)
+
+
+@pytest.mark.parametrize("name", ["fractal_spheres", "fractal_teapots", "monomial_glass"])
+def test_gpu_matches_committed_golden(gpu_ok, name):
+    """The f64 gate reproduces the committed oracle fixtures of the row-N4 scenes (tests/golden,
+    tools/make_golden.py) -- this test needs no oracle on the GPU box."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_render.npz"))
+    cfg = util.golden_config(name)
+    with api.DeviceScene(api.FlatScene(cfg.scene)) as ds:
+        img, st = _gpu_render(cfg, ds, int(g["width"]), int(g["height"]), int(g["spp"]), int(g["max_bounces"]), int(g["seed"]), F64)
+        img32, _ = _gpu_render(cfg, ds, int(g["width"]), int(g["height"]), int(g["spp"]), int(g["max_bounces"]), int(g["seed"]), F32)
+    rel = np.abs(img - g["image"]) / np.maximum(np.abs(g["image"]), 1e-6)
+    assert (rel.max(axis=1) < 1e-9).mean() >= 0.98
+    assert abs(st["segments"] - int(g["segments"])) <= 2e-3 * int(g["segments"])
+    cl = lambda a: np.clip(a, 0.0, 1.0)
+    assert abs(cl(img32).mean() - cl(g["image"]).mean()) <= 1e-2 * cl(g["image"]).mean()

@@ -171,3 +171,41 @@ def test_load_obj_builds_the_mesh(tmp_path):
     p.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
     m = api.load_obj(str(p))
     assert len(m) == 2 and len(m.nodes) == 1 and list(m.refs) == [0, 1]
+
+
+def test_cpp_host_mirror_examples_compile_and_fail_loudly_without_a_gpu(tmp_path):
+    """include/rpt.hpp is header-only over the C ABI: both examples build with plain g++ against the library.
+    On a box without a GPU they must stop with the library's NO_DEVICE message (no CPU fallback); with one,
+    the -m gpu tests compare their images with the Python host's."""
+    import os
+    import subprocess
+    from rpt_b200 import _capi as capi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "rpt_b200", "lib")
+    for name in ("sphere", "fractal_spheres"):
+        exe = str(tmp_path / name)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(root, "examples", name + ".cpp"),
+                               "-L" + libdir, "-lrpt_b200", "-Wl,-rpath," + libdir])
+        if capi.lib().rptb_device_count() <= 0:
+            p = subprocess.run([exe, str(tmp_path / "out.ppm"), "small"], capture_output=True, text=True)
+            assert p.returncode != 0 and "no CUDA device" in p.stderr
+
+
+def test_flatten_kdtree_of_shapes_shares_meshes_and_keeps_child_order():
+    tea = api.Mesh(scenes.teapot_triangles(), build=False)
+    kids = [tea.scale(api.vec3(0.5, 0.5, 0.5)).translate(api.vec3(float(i), 0.0, 0.0)) for i in range(20)] + [api.sphere(), api.monomial_surface(2.0, 4.0)]
+    scene = api.Scene()
+    scene.add(api.Object(api.KdTree(kids).rotate_y(0.3)).material(api.Material.diffuse(api.hex_color(0x808080))))
+    scene.add(api.Object(tea))
+    flat = api.FlatScene(scene)
+    assert flat.desc.nmeshes == 1 and flat.desc.ngroups == 1 and flat.desc.nobjects == 2
+    g = flat.groups[0]
+    assert g.nchildren == 22 and not g.nodes                       # the library builds the tree
+    assert [g.children[i].kind for i in (0, 19, 20, 21)] == [3, 3, 0, 4]
+    assert g.children[5].has_transform == 1 and g.children[5].transform[12] == 5.0 and g.children[5].transform[0] == 0.5
+    assert g.children[20].has_transform == 0
+    assert (g.children[21].monomial_height, g.children[21].monomial_exp) == (2.0, 4.0)
+    assert flat.objects[0].kind == 5 and flat.objects[0].has_transform == 1 and flat.objects[0].mesh == 0
+    assert flat.objects[1].kind == 3 and flat.objects[1].mesh == 0   # the same mesh record as the instances
+    assert flat.host_bytes() > 22 * 184

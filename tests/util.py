@@ -108,3 +108,17 @@ def interior_rays(lo, hi, n, rng):
 
 def rmse(a, b):
     return float(np.sqrt(np.mean((np.asarray(a) - np.asarray(b)) ** 2)))
+
+
+def golden_config(name):
+    """The scene behind each committed fixture of tests/golden (tools/make_golden.py builds it the same way)."""
+    from rpt_b200 import scenes
+    if name == "glass":
+        return scenes.glass_scene(256, 128)
+    if name == "fractal_spheres":
+        return scenes.fractal_spheres_scene(4)
+    if name == "fractal_teapots":
+        return scenes.fractal_teapots_scene(3)
+    if name == "monomial_glass":
+        return scenes.monomial_glass_scene(128, 64)
+    return scenes.CONFIGS[name]()

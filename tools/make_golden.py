@@ -24,13 +24,20 @@ RENDERS = {  # name: (width, height, spp, max_bounces)
     "cornell": (32, 32, 8, 6),
     "teapot": (48, 27, 4, 0),
     "glass": (48, 27, 8, 12),
+    # SURVEY 8f row N4 (kd-trees over whole shapes, MonomialSurface)
+    "fractal_spheres": (48, 36, 4, 1),
+    "fractal_teapots": (48, 36, 4, 1),
+    "monomial_glass": (48, 36, 8, 1),
 }
 
 
 def main():
+    only = set(sys.argv[1:])  # e.g. `python tools/make_golden.py fractal_spheres` adds one fixture, leaves the rest
     os.makedirs(OUT, exist_ok=True)
     for name, (w, h, spp, mb) in RENDERS.items():
-        cfg = scenes.CONFIGS[name]() if name != "glass" else scenes.glass_scene(256, 128)
+        if only and name not in only:
+            continue
+        cfg = util.golden_config(name)
         osc = orc.OracleScene(api.FlatScene(cfg.scene))
         r = api.Renderer(cfg.scene, cfg.camera).width(w).height(h).max_bounces(mb).seed(1)
         img, st = osc.render(cfg.camera, r.params(spp))
@@ -39,6 +46,8 @@ def main():
         print(name, img.mean(0), st["segments"], st["rays"])
     rng = np.random.default_rng(42)
     for name in ("cornell", "teapot"):
+        if only:  # regenerating single render fixtures: leave the hit fixtures (and their ray stream) alone
+            continue
         cfg = scenes.CONFIGS[name]()
         osc = orc.OracleScene(api.FlatScene(cfg.scene))
         if name == "cornell":
