@@ -34,11 +34,14 @@ $(OBJDIR)/api.o: $(CSRC)/api.cu $(HDRS)
 $(OBJDIR)/kdbuild.o: $(CSRC)/kdbuild.cpp include/rpt_b200.h
 	@mkdir -p $(OBJDIR)
 	$(CXX) -std=c++17 -O3 -fPIC -fopenmp -Wall -c $< -o $@
+$(OBJDIR)/bvhbuild.o: $(CSRC)/bvhbuild.cpp $(CSRC)/scene_dev.cuh $(CSRC)/vec.cuh
+	@mkdir -p $(OBJDIR)
+	$(CXX) -std=c++17 -O3 -fPIC -fopenmp -Wall -I/usr/local/cuda/include -c $< -o $@
 $(OBJDIR)/objparse.o: $(CSRC)/objparse.cpp
 	@mkdir -p $(OBJDIR)
 	$(CXX) -std=c++17 -O3 -fPIC -Wall -c $< -o $@
 
-$(LIB): $(OBJDIR)/kernels_f32.o $(OBJDIR)/kernels_f64.o $(OBJDIR)/film.o $(OBJDIR)/api.o $(OBJDIR)/kdbuild.o $(OBJDIR)/objparse.o
+$(LIB): $(OBJDIR)/kernels_f32.o $(OBJDIR)/kernels_f64.o $(OBJDIR)/film.o $(OBJDIR)/api.o $(OBJDIR)/kdbuild.o $(OBJDIR)/bvhbuild.o $(OBJDIR)/objparse.o
 	@mkdir -p rpt_b200/lib
 	$(NVCC) -shared $(ARCH) -o $@ $^ -Xcompiler -fopenmp -lgomp -cudart shared
 
@@ -56,9 +59,9 @@ build/%_cpp: examples/%.cpp include/rpt.hpp include/rpt_b200.h $(LIB)
 # test infrastructure: the device geometry functions compiled for the host (tests/hostemu/hostemu.cu)
 HOSTEMU := tests/hostemu/_build/libhostemu.so
 hostemu: $(HOSTEMU)
-$(HOSTEMU): tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp $(HDRS)
+$(HOSTEMU): tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp $(CSRC)/bvhbuild.cpp $(HDRS)
 	@mkdir -p $(dir $@)
-	nvcc -std=c++17 -O2 -DRPTB_HOST_EMU -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fopenmp,-ffp-contract=off -shared -o $@ tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp -lgomp
+	nvcc -std=c++17 -O2 -DRPTB_HOST_EMU -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fopenmp,-ffp-contract=off -shared -o $@ tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp $(CSRC)/bvhbuild.cpp -lgomp
 
 clean:
 	rm -rf build $(LIB) $(ORACLE) tests/hostemu/_build

@@ -160,6 +160,14 @@ typedef struct rptb_env {
     const double* texels;   /* HDRI: width*height*3, row-major, row 0 = +y pole */
 } rptb_env;
 
+/* How the f32 product path finds the closest triangle of a Mesh.  The closest hit of a ray does not depend
+ * on it (up to which of two triangles wins an exact tie in t on a shared edge); the cost does.
+ *   KDTREE  the reference-shaped KdTree<Triangle> (src/kdtree.rs:99-223), node for node -- what the f64
+ *           parity gate, rptb_closest_hit with stats, and the traversal counters of rptb_stats always use
+ *   BVH     a binary SAH BVH built by the library over the same triangles, each in exactly one leaf
+ * AUTO = the library's default (environment variable RPTB_ACCEL=kdtree|bvh overrides it).              */
+typedef enum rptb_accel { RPTB_ACCEL_AUTO = 0, RPTB_ACCEL_KDTREE = 1, RPTB_ACCEL_BVH = 2 } rptb_accel;
+
 /* ---- Scene: src/scene.rs:7-18 ---------------------------------------------- */
 typedef struct rptb_scene_desc {
     const rptb_material* materials;
@@ -173,7 +181,7 @@ typedef struct rptb_scene_desc {
     rptb_env environment;
     const rptb_group* groups;   /* targets of GROUP objects (may be NULL when ngroups == 0) */
     uint32_t ngroups;
-    uint32_t _pad;
+    uint32_t accel;             /* rptb_accel: what the f32 path traverses meshes with */
 } rptb_scene_desc;
 
 /* ---- Camera: src/camera.rs:8-26 (same six fields) -------------------------- */

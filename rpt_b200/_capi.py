@@ -18,6 +18,7 @@ LIGHT_POINT, LIGHT_AMBIENT, LIGHT_DIRECTIONAL, LIGHT_OBJECT = 0, 1, 2, 3
 ENV_COLOR, ENV_HDRI = 0, 1
 PRECISION_F32, PRECISION_F64 = 0, 1
 ENGINE_AUTO, ENGINE_MEGAKERNEL, ENGINE_WAVEFRONT = 0, 1, 2
+ACCEL_AUTO, ACCEL_KDTREE, ACCEL_BVH = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)
@@ -120,7 +121,7 @@ class SceneDesc(C.Structure):
         ("environment", Env),
         ("groups", C.POINTER(Group)),
         ("ngroups", C.c_uint32),
-        ("_pad", C.c_uint32),
+        ("accel", C.c_uint32),
     ]
 
 

@@ -633,7 +633,7 @@ class FlatScene:
     """Owns the ctypes arrays a rptb_scene_desc points into (caller-owned memory
     borrowed by rptb_scene_create for the duration of the call)."""
 
-    def __init__(self, scene: Scene):
+    def __init__(self, scene: Scene, accel: int = capi.ACCEL_AUTO):
         self._keep: list = []
         mats: List[capi.Material] = []
         meshes: List[capi.Mesh] = []
@@ -716,6 +716,7 @@ class FlatScene:
         d.meshes, d.nmeshes = self.meshes, len(meshes)
         self.groups = (capi.Group * max(len(groups), 1))(*groups)
         d.groups, d.ngroups = self.groups, len(groups)
+        d.accel = int(accel)
         d.objects, d.nobjects = self.objects, len(objs)
         d.lights, d.nlights = self.lights, len(lights)
         env = scene.environment
@@ -745,8 +746,8 @@ class FlatScene:
 class DeviceScene:
     """RAII wrapper of the opaque rptb_scene handle."""
 
-    def __init__(self, scene_or_flat, device: int = 0):
-        self.flat = scene_or_flat if isinstance(scene_or_flat, FlatScene) else FlatScene(scene_or_flat)
+    def __init__(self, scene_or_flat, device: int = 0, accel: int = capi.ACCEL_AUTO):
+        self.flat = scene_or_flat if isinstance(scene_or_flat, FlatScene) else FlatScene(scene_or_flat, accel)
         self.handle = C.c_void_p()
         self.device = device
         capi.check(capi.lib().rptb_scene_create(C.byref(self.flat.desc), device, C.byref(self.handle)),
@@ -784,7 +785,7 @@ class DeviceScene:
         capi.check(
             capi.lib().rptb_closest_hit(self.handle, rays.ctypes.data_as(capi.c_double_p), n, t_min, precision,
                                         t.ctypes.data_as(capi.c_double_p), obj.ctypes.data_as(capi.c_i32_p),
-                                        nrm.ctypes.data_as(capi.c_double_p), C.byref(stats)),
+                                        nrm.ctypes.data_as(capi.c_double_p), C.byref(stats) if want_stats else None),
             "rptb_closest_hit",
         )
         return (t, obj, nrm, stats.as_dict()) if want_stats else (t, obj, nrm)
@@ -860,6 +861,7 @@ class Renderer:
         self._device = 0
         self._precision = capi.PRECISION_F32
         self._engine = capi.ENGINE_AUTO
+        self._accel = capi.ACCEL_AUTO
         self._dev_scene: Optional[DeviceScene] = None
         self._next_sample = 0
         self.last_stats: Optional[dict] = None
@@ -904,6 +906,12 @@ class Renderer:
         self._engine = int(engine)
         return self
 
+    def accel(self, accel: int) -> "Renderer":
+        """rptb_accel: what the f32 path traverses meshes with (capi.ACCEL_KDTREE = the reference-shaped tree,
+        capi.ACCEL_BVH = the library's own BVH).  Takes effect when the device scene is created."""
+        self._accel = int(accel)
+        return self
+
     def params(self, iterations: int, first_sample: int = 0, shard_index: int = 0, shard_count: int = 1,
                collect_stats: int = 0) -> capi.RenderParams:
         p = capi.RenderParams()
@@ -919,7 +927,7 @@ class Renderer:
 
     def device_scene(self) -> DeviceScene:
         if self._dev_scene is None:
-            self._dev_scene = DeviceScene(self.scene, self._device)
+            self._dev_scene = DeviceScene(self.scene, self._device, self._accel)
         return self._dev_scene
 
     def close(self) -> None:

@@ -42,6 +42,11 @@ int parse_stl_bytes(const void* data, size_t len, std::vector<double>& tris, std
 
 using namespace rptb;
 
+// What RPTB_ACCEL_AUTO means when the environment does not say.
+#ifndef RPTB_ACCEL_DEFAULT
+#define RPTB_ACCEL_DEFAULT RPTB_ACCEL_KDTREE
+#endif
+
 namespace {
 
 thread_local std::string g_error;
@@ -154,6 +159,16 @@ struct rptb_scene {
 
 namespace {
 
+// rptb_scene_desc::accel: AUTO -> RPTB_ACCEL env (kdtree | bvh) -> the library default
+uint32_t resolve_accel(uint32_t accel) {
+    if (accel == RPTB_ACCEL_KDTREE || accel == RPTB_ACCEL_BVH) return accel;
+    if (const char* e = getenv("RPTB_ACCEL")) {
+        if (std::strcmp(e, "bvh") == 0) return RPTB_ACCEL_BVH;
+        if (std::strcmp(e, "kdtree") == 0) return RPTB_ACCEL_KDTREE;
+    }
+    return RPTB_ACCEL_DEFAULT;
+}
+
 // bind_scene's uploader: every array goes to the device through the scene's arena
 struct ArenaPut {
     Arena& arena;
@@ -169,7 +184,7 @@ struct ArenaPut {
 int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
     HostScene hs;
     std::string err;
-    int rc = flatten_scene(d, hs, err);
+    int rc = flatten_scene(d, hs, err, resolve_accel(d->accel) == RPTB_ACCEL_BVH);
     if (rc != RPTB_OK) return fail(rc, "%s", err.c_str());
     if (getenv("RPTB_NO_SMALL") != nullptr) hs.small_ok = false;
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -326,7 +341,7 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
                 binv[r] = (float)(ext > 0 && std::isfinite(ext) ? 1.0 / ext : 0.0);
             }
             wavefront_carve(s->wf_mem, npix, G, s->sampled_lights, maxd, blo, binv, (WfBuffers*)bufs.data());
-            CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, stream, s->wf_pinned, launches));
+            CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, (s->features & F_BVH) != 0, stream, s->wf_pinned, launches));
         } else {
             const int rc = ensure_partial(s, a);
             if (rc != RPTB_OK) return rc;
@@ -543,9 +558,9 @@ int rptb_closest_hit(rptb_scene* s, const double* rays, uint64_t n, double t_min
     CUC(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), s->stream));
     CUC(cudaEventRecord(s->ev0, s->stream));
     if (precision == RPTB_PRECISION_F32)
-        CUC(launch_closest_hit_f32(s->view32, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->stream));
+        CUC(launch_closest_hit_f32(s->view32, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->features, s->stream));
     else
-        CUC(launch_closest_hit_f64(s->view64, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->stream));
+        CUC(launch_closest_hit_f64(s->view64, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->features, s->stream));
     CUC(cudaEventRecord(s->ev1, s->stream));
     CUC(cudaMemcpyAsync(out_t, d_t, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUC(cudaMemcpyAsync(out_object, d_obj, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));

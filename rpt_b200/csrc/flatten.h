@@ -28,6 +28,7 @@ int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnod
                       uint32_t& depth, uint32_t& max_leaf);
 int build_kdtree_boxes_host(const double* boxes, uint64_t nboxes, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
                             uint32_t& depth, uint32_t& max_leaf);
+int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& nodes, std::vector<uint32_t>& order, uint32_t& depth);
 
 inline int flat_fail(std::string& err, int code, const char* fmt, ...) {
     char buf[512];
@@ -155,6 +156,9 @@ struct FlatTree {
 struct HostMesh : FlatTree {
     std::vector<float4> tri48;
     std::vector<float4> leaf_planes;
+    std::vector<BvhNodeDev> bvh_nodes;  // F_BVH: the f32 path's own structure over the same triangles
+    std::vector<float4> bvh_tri48;
+    std::vector<uint32_t> bvh_ids;
     std::vector<float> verts32, norms32;
     std::vector<double> verts64, norms64;
     double bmin[3], bmax[3];
@@ -492,12 +496,13 @@ inline int validate_scene(const rptb_scene_desc* d, std::string& err) {
         }
     }
     if (d->environment.kind > RPTB_ENV_HDRI) return flat_fail(err, RPTB_ERR_BAD_ARG, "bad environment kind %u", d->environment.kind);
+    if (d->accel > RPTB_ACCEL_BVH) return flat_fail(err, RPTB_ERR_BAD_ARG, "bad accel %u", d->accel);
     return RPTB_OK;
 }
 
 // Validates `d` and fills every host-side array; pointers inside the MeshRec / GroupRec / EnvRec tables
 // stay null until bind_scene.
-inline int flatten_scene(const rptb_scene_desc* d, HostScene& hs, std::string& err) {
+inline int flatten_scene(const rptb_scene_desc* d, HostScene& hs, std::string& err, bool want_bvh = false) {
     {
         const int rc = validate_scene(d, err);
         if (rc != RPTB_OK) return rc;
@@ -520,6 +525,16 @@ inline int flatten_scene(const rptb_scene_desc* d, HostScene& hs, std::string& e
         if (!leaf) {  // a real tree: planes in leaf order for the trace kernel
             hm.leaf_planes.resize(hm.refs.size());
             for (size_t k = 0; k < hm.refs.size(); k++) hm.leaf_planes[k] = hm.tri48[3 * (size_t)hm.refs[k]];
+        }
+        if (!leaf && want_bvh) {  // the f32 path's own BVH over the same triangles (bvhbuild.cpp)
+            uint32_t bvh_depth = 0;
+            if (build_bvh_host(d->meshes[i].tris, d->meshes[i].ntris, hm.bvh_nodes, hm.bvh_ids, bvh_depth) != 0)
+                return flat_fail(err, RPTB_ERR_UNSUPPORTED, "mesh %u: cannot build a BVH over %llu triangles", i, (unsigned long long)d->meshes[i].ntris);
+            if (bvh_depth + 2 >= (uint32_t)BVH_STACK)
+                return flat_fail(err, RPTB_ERR_UNSUPPORTED, "mesh %u: BVH depth %u exceeds the traversal stack (%d)", i, bvh_depth, BVH_STACK);
+            hm.bvh_tri48.resize(3 * (size_t)hm.ntris);
+            for (size_t k = 0; k < hm.ntris; k++)
+                for (int j = 0; j < 3; j++) hm.bvh_tri48[3 * k + j] = hm.tri48[3 * (size_t)hm.bvh_ids[k] + j];
         }
         for (int k = 0; k < 3; k++) {
             b.bmin[k] = hm.bmin[k];
@@ -589,6 +604,7 @@ inline int flatten_scene(const rptb_scene_desc* d, HostScene& hs, std::string& e
     for (uint32_t i = 0; i < d->nlights; i++)
         if (d->lights[i].kind != RPTB_LIGHT_AMBIENT) hs.sampled_lights++;
     if (hs.has_tree) hs.features |= F_TREE;
+    if (hs.has_tree && want_bvh) hs.features |= F_BVH;  // every mesh with a real tree has its BVH
     for (uint32_t i = 0; i < d->nmaterials; i++)
         if (d->materials[i].transparent) hs.features |= F_TRANSP;
     if (d->environment.kind == RPTB_ENV_HDRI) hs.features |= F_HDRI;
@@ -616,7 +632,8 @@ bool bind_scene(HostScene& hs, Put& put, bool release, SceneView<float>& v32, Sc
         MeshRec<double>& b = hs.t64.meshes[i];
         const uint64_t before = put.bytes();
         if (!put(hm.nodes32, &a.nodes) || !put(hm.refs, &a.refs) || !put(hm.tri48, &a.tri48) || !put(hm.leaf_planes, &a.leaf_planes) ||
-            !put(hm.verts32, &a.verts) || !put(hm.norms32, &a.norms))
+            !put(hm.verts32, &a.verts) || !put(hm.norms32, &a.norms) || !put(hm.bvh_nodes, &a.bvh_nodes) ||
+            !put(hm.bvh_tri48, &a.bvh_tri48) || !put(hm.bvh_ids, &a.bvh_ids))
             return false;
         f32_bytes += put.bytes() - before;
         if (!put(hm.nodes64, &b.nodes) || !put(hm.verts64, &b.verts) || !put(hm.norms64, &b.norms)) return false;
@@ -628,6 +645,9 @@ bool bind_scene(HostScene& hs, Put& put, bool release, SceneView<float>& v32, Sc
             std::vector<uint32_t>().swap(hm.refs);
             std::vector<float4>().swap(hm.tri48);
             std::vector<float4>().swap(hm.leaf_planes);
+            std::vector<BvhNodeDev>().swap(hm.bvh_nodes);
+            std::vector<float4>().swap(hm.bvh_tri48);
+            std::vector<uint32_t>().swap(hm.bvh_ids);
             std::vector<float>().swap(hm.verts32);
             std::vector<float>().swap(hm.norms32);
             std::vector<double>().swap(hm.verts64);

@@ -259,6 +259,99 @@ RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, 
     return false;
 }
 
+// ----------------------------------------------------------- BVH traversal -----
+// The f32 path's own structure (bvhbuild.cpp): a binary SAH BVH, both child boxes in the parent's 64-byte
+// node, every triangle in exactly one leaf of <= 4.  Same query as KdTree::intersect -- closest triangle hit
+// in [tmin, h.t), or any hit for a shadow ray -- and the same triangle test (tri48); only the set of
+// triangles a ray has to look at shrinks (dragon proxy: 419 -> ~10 per ray).  Exact ties in t between two
+// triangles (shared edges) may resolve to the other triangle than in the reference's leaf order.
+RPTB_D BvhNodeDev load_bvh_node(const BvhNodeDev* p) {
+    BvhNodeDev n;
+    const float4* q = reinterpret_cast<const float4*>(p);
+    n.c0xy = ldg(q);
+    n.c1xy = ldg(q + 1);
+    n.cz = ldg(q + 2);
+    const int4 w = ldg(reinterpret_cast<const int4*>(q + 3));
+    n.child0 = w.x;
+    n.child1 = w.y;
+    return n;
+}
+
+template <bool STATS>
+RPTB_D bool bvh_intersect(const MeshRec<float>& m, Vec3<float> o, Vec3<float> d, float tmin, bool any, Hit<float>& h,
+                          TravStats& ts) {
+    const Vec3<float> inv = {M<float>::rcp(d.x), M<float>::rcp(d.y), M<float>::rcp(d.z)};
+    // o * inv per axis, so that a slab is one FMA: (b - o) * inv = b * inv - o * inv
+    const Vec3<float> oi = {o.x * inv.x, o.y * inv.y, o.z * inv.z};
+    int32_t stack[BVH_STACK];
+    int sp = 0;
+    int32_t cur = 0;  // the root is always an inner node
+    bool hit = false;
+    while (true) {
+        while (cur >= 0) {  // inner node: test both children
+            if (STATS) ts.node_visits++;
+            const BvhNodeDev n = load_bvh_node(m.bvh_nodes + cur);
+            const float ax0 = fmaf(n.c0xy.x, inv.x, -oi.x), ax1 = fmaf(n.c0xy.y, inv.x, -oi.x);
+            const float ay0 = fmaf(n.c0xy.z, inv.y, -oi.y), ay1 = fmaf(n.c0xy.w, inv.y, -oi.y);
+            const float az0 = fmaf(n.cz.x, inv.z, -oi.z), az1 = fmaf(n.cz.y, inv.z, -oi.z);
+            const float bx0 = fmaf(n.c1xy.x, inv.x, -oi.x), bx1 = fmaf(n.c1xy.y, inv.x, -oi.x);
+            const float by0 = fmaf(n.c1xy.z, inv.y, -oi.y), by1 = fmaf(n.c1xy.w, inv.y, -oi.y);
+            const float bz0 = fmaf(n.cz.z, inv.z, -oi.z), bz1 = fmaf(n.cz.w, inv.z, -oi.z);
+            const float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
+            const float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), h.t));
+            const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
+            const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), h.t));
+            const bool ha = an <= af, hb = bn <= bf;
+            if (ha && hb) {
+                const bool a_first = an <= bn;
+                stack[sp++] = a_first ? n.child1 : n.child0;
+                cur = a_first ? n.child0 : n.child1;
+            } else if (ha) {
+                cur = n.child0;
+            } else if (hb) {
+                cur = n.child1;
+            } else {
+                if (sp == 0) return hit;
+                cur = stack[--sp];
+            }
+        }
+        // leaf: ~cur = (first << 3) | (count - 1)
+        {
+            const uint32_t code = (uint32_t)~cur;
+            const uint32_t first = code >> 3, count = (code & 7u) + 1u;
+            for (uint32_t k = first; k < first + count; k++) {
+                if (STATS) ts.tri_tests++;
+                const float4* q = m.bvh_tri48 + 3 * (size_t)k;
+                const float4 q0 = ldg(q);
+                const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+                if (fabsf(cosine) < 1e-8f) continue;
+                const float time = fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+                if (time < tmin || time >= h.t) continue;
+                const float4 q1 = ldg(q + 1);
+                const float4 q2 = ldg(q + 2);
+                const float px = fmaf(time, d.x, o.x), py = fmaf(time, d.y, o.y), pz = fmaf(time, d.z, o.z);
+                const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
+                const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
+                const float u = 1.0f - v - w;
+                if (u >= 0.0f && v >= 0.0f && w >= 0.0f) {
+                    h.t = time;
+                    h.bv = v;
+                    h.bw = w;
+                    h.aux = ldg(m.bvh_ids + k);
+                    hit = true;
+                }
+            }
+        }
+        if (any && hit) return true;
+        if (sp == 0) return hit;
+        cur = stack[--sp];
+    }
+}
+template <bool STATS>
+RPTB_D bool bvh_intersect(const MeshRec<double>&, Vec3<double>, Vec3<double>, double, bool, Hit<double>&, TravStats&) {
+    return false;  // the f64 gate never uses the BVH
+}
+
 // ------------------------------------------------------------ kd traversal -----
 RPTB_D KdNodeDev load_node(const KdNodeDev* p) {
     const uint2 v = ldg(reinterpret_cast<const uint2*>(p));
@@ -323,6 +416,7 @@ RPTB_D bool kd_intersect(const SceneView<R>& sv, const MeshRec<R>& m, Vec3<R> o,
         return hit;
     }
     if constexpr (!(FEAT & F_TREE) && !M<R>::literal) return false;  // (unreachable: compiled for tree-less scenes)
+    if constexpr ((FEAT & F_BVH) != 0 && !M<R>::literal) return bvh_intersect<STATS>(m, o, d, tmin, any, h, ts);
     // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
     R lo, hi;
     Vec3<R> inv;

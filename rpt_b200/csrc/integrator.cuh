@@ -39,11 +39,15 @@ constexpr int RENDER_THREADS = 128;  // 4 warps: a 16x8 pixel tile
 #ifndef RPTB_MIN_BLOCKS_GLASS
 #define RPTB_MIN_BLOCKS_GLASS 5  // F_TRANSP | F_HDRI, no trees (glass: flat, 19.2-19.4 G for 5/6/8)
 #endif
+#ifndef RPTB_MIN_BLOCKS_BVH
+#define RPTB_MIN_BLOCKS_BVH 6    // F_BVH (the BVH loop keeps 1/d, o/d and a two-box node live): 80 registers; not tuned on hardware yet
+#endif
 #ifndef RPTB_MIN_BLOCKS_EXT
 #define RPTB_MIN_BLOCKS_EXT 4    // F_EVERY (two nested traversal stacks in local memory): not tuned on hardware yet
 #endif
 constexpr int render_min_blocks(int feat) {
     if (feat & F_EXT) return RPTB_MIN_BLOCKS_EXT;
+    if (feat & F_BVH) return RPTB_MIN_BLOCKS_BVH;
     const int base = feat & F_ALL;  // F_SMALL does not change the register budget
     return base == 0 ? RPTB_MIN_BLOCKS_LITE : base == F_TREE ? RPTB_MIN_BLOCKS_TREE : base == (F_TRANSP | F_HDRI) ? RPTB_MIN_BLOCKS_GLASS : RPTB_MIN_BLOCKS;
 }
@@ -408,7 +412,7 @@ __global__ void clear_kernel(R* out, size_t n) {
 }
 
 // ---- K2: Renderer::get_closest_hit for a batch of world rays -----------------------
-template <class R, bool STATS>
+template <class R, bool STATS, int FEAT>
 __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restrict__ rays, uint64_t n, double tmin_d,
                                    double* __restrict__ out_t, int32_t* __restrict__ out_obj,
                                    double* __restrict__ out_n, DeviceCounters* counters) {
@@ -420,12 +424,12 @@ __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restri
         const Vec3<R> d = {(R)r[3], (R)r[4], (R)r[5]};
         Hit<R> h;
         h.t = M<R>::inf();
-        closest_hit<R, STATS, F_EVERY>(sv, o, d, (R)tmin_d, false, h, ts);
+        closest_hit<R, STATS, FEAT>(sv, o, d, (R)tmin_d, false, h, ts);
         out_obj[i] = h.obj;
         out_t[i] = h.obj >= 0 ? (double)h.t : (double)INFINITY;
         if (out_n) {
             Vec3<R> nn = {(R)0, (R)0, (R)0};
-            if (h.obj >= 0) nn = finalize_hit<R, F_EVERY>(sv, sv.objects[h.obj], o, d, h).n;
+            if (h.obj >= 0) nn = finalize_hit<R, FEAT>(sv, sv.objects[h.obj], o, d, h).n;
             out_n[3 * i] = (double)nn.x;
             out_n[3 * i + 1] = (double)nn.y;
             out_n[3 * i + 2] = (double)nn.z;

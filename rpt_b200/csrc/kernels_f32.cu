@@ -65,7 +65,7 @@ void wavefront_carve(void* mem, uint32_t npix, uint32_t G, uint32_t Ks, uint32_t
 }
 
 cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float>& args, const WfBuffers* bufs,
-                              bool stats, cudaStream_t stream, uint32_t* pinned, uint32_t* launches) {
+                              bool stats, bool use_bvh, cudaStream_t stream, uint32_t* pinned, uint32_t* launches) {
     const WfBuffers b = *bufs;
     const uint32_t capacity = b.npaths * (b.Ks + 1);
     // Optional coherence sort of the ray list (Morton key of origin + direction octant).  Measured on
@@ -90,8 +90,11 @@ cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (stats) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<true>, WF_THREADS, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<false>, WF_THREADS, 0);
+    // with counters the trace kernel always walks the reference-shaped kd-trees (their counts are the algorithmic work)
+    const bool bvh = !stats && sv.nmeshes > 0 && use_bvh;
+    if (stats) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<true, false>, WF_THREADS, 0);
+    else if (bvh) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<false, true>, WF_THREADS, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<false, false>, WF_THREADS, 0);
     if (e != cudaSuccess) return e;
     const unsigned tgrid = (unsigned)(sms * (per_sm > 0 ? per_sm : 1));
     // a sample with n <= max_bounces + 1 segments takes n + 1 steps (camera ray, one per vertex,
@@ -114,8 +117,9 @@ cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float
             list = dv.Current();
             nl += 2;
         }
-        if (stats) wf_trace_kernel<true><<<tgrid, WF_THREADS, 0, stream>>>(sv, b, list, args.counters);
-        else wf_trace_kernel<false><<<tgrid, WF_THREADS, 0, stream>>>(sv, b, list, nullptr);
+        if (stats) wf_trace_kernel<true, false><<<tgrid, WF_THREADS, 0, stream>>>(sv, b, list, args.counters);
+        else if (bvh) wf_trace_kernel<false, true><<<tgrid, WF_THREADS, 0, stream>>>(sv, b, list, nullptr);
+        else wf_trace_kernel<false, false><<<tgrid, WF_THREADS, 0, stream>>>(sv, b, list, nullptr);
         nl += 2;
         if ((step & 3ull) == 3ull || step + 1 == max_steps) {
             e = cudaMemcpyAsync(pinned, b.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);

@@ -10,7 +10,8 @@ namespace rptb {
                                        int features, cudaStream_t stream, uint32_t* launches);                     \
     cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,   \
                                             double* out_t, int32_t* out_obj, double* out_n,                        \
-                                            DeviceCounters* counters, bool stats, cudaStream_t stream);            \
+                                            DeviceCounters* counters, bool stats, int features,                    \
+                                            cudaStream_t stream);                                                  \
     cudaError_t launch_bsdf_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, double* out,         \
                                      cudaStream_t stream);                                                         \
     cudaError_t launch_sample_f_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, uint64_t seed,   \
@@ -31,7 +32,7 @@ size_t wavefront_struct_size();
 // run Renderer::sample with the wavefront schedule; blocks until the image is in args.out
 // (the step loop is driven from the host).  `pinned` = 4 bytes of page-locked host memory.
 cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float>& args, const WfBuffers* bufs,
-                              bool stats, cudaStream_t stream, uint32_t* pinned, uint32_t* launches);
+                              bool stats, bool use_bvh, cudaStream_t stream, uint32_t* pinned, uint32_t* launches);
 
 // max_bounces the render kernels are instantiated for
 constexpr uint32_t MAX_BOUNCES_SUPPORTED = 64;

@@ -27,6 +27,8 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             if (stats) render_kernel<R, 16, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
             else if (ext) render_kernel<R, 16, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
             else if constexpr (M<R>::literal) render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);  // the f64 gate is not specialised
+            else if ((features & F_BVH) && base == F_TREE) render_kernel<R, 16, false, F_TREE | F_BVH><<<grid, block, 0, stream>>>(sv, args);
+            else if (features & F_BVH) render_kernel<R, 16, false, F_ALL | F_BVH><<<grid, block, 0, stream>>>(sv, args);
             else if (base == 0 && small) render_kernel<R, 16, false, F_SMALL><<<grid, block, 0, stream>>>(sv, args);
             else if (base == 0) render_kernel<R, 16, false, 0><<<grid, block, 0, stream>>>(sv, args);
             else if (base == F_TREE) render_kernel<R, 16, false, F_TREE><<<grid, block, 0, stream>>>(sv, args);
@@ -49,12 +51,14 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
 
 template <class R>
 cudaError_t launch_closest_hit_impl(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin, double* out_t,
-                                    int32_t* out_obj, double* out_n, DeviceCounters* counters, bool stats,
+                                    int32_t* out_obj, double* out_n, DeviceCounters* counters, bool stats, int features,
                                     cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    if (stats) closest_hit_kernel<R, true><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
-    else closest_hit_kernel<R, false><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    // with counters: always the reference-shaped kd-tree (its node visits / triangle tests are the algorithmic work)
+    if (stats) closest_hit_kernel<R, true, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    else if (!M<R>::literal && (features & F_BVH)) closest_hit_kernel<R, false, F_EVERY | F_BVH><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    else closest_hit_kernel<R, false, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
     return cudaGetLastError();
 }
 
@@ -80,8 +84,10 @@ cudaError_t launch_sample_f_impl(const MaterialRec<R>& m, const double* dirs, ui
     }                                                                                                               \
     cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,    \
                                             double* out_t, int32_t* out_obj, double* out_n,                         \
-                                            DeviceCounters* counters, bool stats, cudaStream_t stream) {            \
-        return launch_closest_hit_impl<R>(sv, rays, n, tmin, out_t, out_obj, out_n, counters, stats, stream);       \
+                                            DeviceCounters* counters, bool stats, int features,                     \
+                                            cudaStream_t stream) {                                                  \
+        return launch_closest_hit_impl<R>(sv, rays, n, tmin, out_t, out_obj, out_n, counters, stats, features,      \
+                                          stream);                                                                  \
     }                                                                                                               \
     cudaError_t launch_bsdf_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, double* out,          \
                                      cudaStream_t stream) {                                                         \

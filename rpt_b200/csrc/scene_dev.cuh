@@ -37,7 +37,8 @@ enum : int {
     F_TREE = 1 /* kd-trees beyond one leaf */, F_TRANSP = 2 /* transparent materials */, F_HDRI = 4, F_ALL = 7,
     F_SMALL = 8 /* the scene tables fit SmallTables: read them from kernel-parameter (constant) space */,
     F_GROUP = 16 /* kd-trees over whole shapes (KdTree<Box<dyn Bounded>>) */, F_MONO = 32 /* MonomialSurface */,
-    F_EXT = F_GROUP | F_MONO, F_EVERY = F_ALL | F_EXT /* the one instantiation that knows every shape */
+    F_EXT = F_GROUP | F_MONO, F_EVERY = F_ALL | F_EXT /* the one instantiation that knows every shape */,
+    F_BVH = 64 /* f32 only: meshes are traversed through their BVH (MeshRec::bvh_*) instead of the reference-shaped kd-tree */
 };
 
 constexpr int KD_STACK = 64;          // max kd-tree depth the traversal stack holds
@@ -64,12 +65,29 @@ struct NodeOf<float> { typedef KdNodeDev type; };
 template <>
 struct NodeOf<double> { typedef KdNodeDev64 type; };
 
+// A node of the f32 path's own acceleration structure: a binary BVH built with the surface-area
+// heuristic (bvhbuild.cpp).  The node carries the boxes of BOTH children, so one 64-byte fetch decides
+// which of them the ray enters.  child >= 0: index of an inner node; child < 0: a leaf,
+// ~child = (first << 3) | (count - 1), naming triangles [first, first + count) in BVH order.
+struct BvhNodeDev {
+    float4 c0xy;  // child 0: lo.x, hi.x, lo.y, hi.y
+    float4 c1xy;  // child 1
+    float4 cz;    // lo0.z, hi0.z, lo1.z, hi1.z
+    int32_t child0, child1;
+    uint32_t _pad[2];
+};
+constexpr int BVH_STACK = 96;      // traversal stack entries; the builder keeps the depth below it (bvhbuild.cpp)
+constexpr int BVH_LEAF_MAX = 4;    // triangles per leaf (3 bits in the leaf code would allow 8)
+
 template <class R>
 struct MeshRec {
     const typename NodeOf<R>::type* nodes;
     const uint32_t* refs;
     const float4* tri48;  // f32 only (null for double)
     const float4* leaf_planes;  // f32, kd-tree meshes only: tri48[3*refs[k]] for every leaf ref k (planes in leaf order)
+    const BvhNodeDev* bvh_nodes;  // f32, when the scene was created with the BVH (F_BVH): node 0 is the root
+    const float4* bvh_tri48;      // tri48 permuted into BVH leaf order (a leaf's triangles are contiguous)
+    const uint32_t* bvh_ids;      // original triangle index of each BVH-order triangle (normals, Hit::aux)
     const R* verts;       // 9 per triangle
     const R* norms;       // 9 per triangle
     R bmin[3], bmax[3];   // KdTree::bounds

@@ -443,7 +443,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade_kernel(const SceneView<fl
 // shapes and single-leaf meshes are intersected on the spot, a kd-tree mesh switches the
 // lane into the TRAVERSE state, where each loop iteration descends to one leaf, tests its
 // triangles and pops.
-template <bool STATS>
+// BVH = true: a mesh with a real tree is traversed through its BVH (scene_dev.cuh, F_BVH) instead --
+// same state machine, each loop iteration descends to one BVH leaf, tests its <= 4 triangles and pops.
+template <bool STATS, bool BVH>
 __global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kernel(const SceneView<float> sv, const WfBuffers b,
                                                               const uint32_t* __restrict__ list,
                                                               DeviceCounters* counters) {
@@ -468,8 +470,11 @@ __global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kern
     R lo = 0.f, hi = 0.f;
     int sp = 0;
     bool mesh_hit = false;
-    uint32_t st_node[KD_STACK];
-    R st_lo[KD_STACK], st_hi[KD_STACK];
+    uint32_t st_node[BVH ? 1 : KD_STACK];
+    R st_lo[BVH ? 1 : KD_STACK], st_hi[BVH ? 1 : KD_STACK];
+    int32_t bstack[BVH ? BVH_STACK : 1];  // BVH mode: pending far children
+    int32_t cur = 0;
+    Vec3<R> oinv = wd_;                   // BVH mode: o / d per axis
 
     while (true) {
         // ---- fetch -----------------------------------------------------------------------
@@ -527,6 +532,10 @@ __global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kern
                     lo_o = o; lo_d = d; inv = iv;
                     mesh = &mm;
                     node = 0; lo = l0; hi = h0; sp = 0;
+                    if (BVH) {
+                        cur = 0;
+                        oinv = {o.x * iv.x, o.y * iv.y, o.z * iv.z};
+                    }
                     mesh_hit = false;
                     trav = true;
                     break;
@@ -549,7 +558,76 @@ __global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kern
         // ("while-while".  A finer-grained "if-if" schedule -- a few node steps, then one 4-triangle
         // batch per loop iteration -- was measured on the dragon proxy and lost: 101 vs 143 Msamples/s,
         // +35 % instructions for +1.5 active lanes.)
-        if (have && trav) {
+        if (BVH && have && trav) {
+            // ---- one round of the BVH traversal (geometry.cuh, bvh_intersect) -----------------
+            bool mesh_done = false;
+            while (cur >= 0) {
+                if (STATS) ts.node_visits++;
+                const BvhNodeDev n = load_bvh_node(mesh->bvh_nodes + cur);
+                const float ax0 = fmaf(n.c0xy.x, inv.x, -oinv.x), ax1 = fmaf(n.c0xy.y, inv.x, -oinv.x);
+                const float ay0 = fmaf(n.c0xy.z, inv.y, -oinv.y), ay1 = fmaf(n.c0xy.w, inv.y, -oinv.y);
+                const float az0 = fmaf(n.cz.x, inv.z, -oinv.z), az1 = fmaf(n.cz.y, inv.z, -oinv.z);
+                const float bx0 = fmaf(n.c1xy.x, inv.x, -oinv.x), bx1 = fmaf(n.c1xy.y, inv.x, -oinv.x);
+                const float by0 = fmaf(n.c1xy.z, inv.y, -oinv.y), by1 = fmaf(n.c1xy.w, inv.y, -oinv.y);
+                const float bz0 = fmaf(n.cz.z, inv.z, -oinv.z), bz1 = fmaf(n.cz.w, inv.z, -oinv.z);
+                const float an = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
+                const float af = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), h.t));
+                const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
+                const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), h.t));
+                const bool ha = an <= af, hb = bn <= bf;
+                if (ha && hb) {
+                    const bool a_first = an <= bn;
+                    bstack[sp++] = a_first ? n.child1 : n.child0;
+                    cur = a_first ? n.child0 : n.child1;
+                } else if (ha) {
+                    cur = n.child0;
+                } else if (hb) {
+                    cur = n.child1;
+                } else {
+                    if (sp == 0) { mesh_done = true; break; }
+                    cur = bstack[--sp];
+                }
+            }
+            if (!mesh_done) {  // cur is a leaf
+                const uint32_t code = (uint32_t)~cur;
+                const uint32_t first = code >> 3, cnt = (code & 7u) + 1u;
+                const float4* T = mesh->bvh_tri48 + 3 * (size_t)first;
+                float4 q0[BVH_LEAF_MAX];
+#pragma unroll
+                for (uint32_t j = 0; j < (uint32_t)BVH_LEAF_MAX; j++) q0[j] = __ldg(T + 3 * min(j, cnt - 1u));
+#pragma unroll
+                for (uint32_t j = 0; j < (uint32_t)BVH_LEAF_MAX; j++) {
+                    if (j >= cnt) break;
+                    if (STATS) ts.tri_tests++;
+                    const float cosine = q0[j].x * lo_d.x + q0[j].y * lo_d.y + q0[j].z * lo_d.z;
+                    if (fabsf(cosine) < 1e-8f) continue;
+                    const float time = __fdividef(q0[j].w - (q0[j].x * lo_o.x + q0[j].y * lo_o.y + q0[j].z * lo_o.z), cosine);
+                    if (time < tmin || time >= h.t) continue;
+                    const float4 q1 = __ldg(T + 3 * j + 1);
+                    const float4 q2 = __ldg(T + 3 * j + 2);
+                    const float px = fmaf(time, lo_d.x, lo_o.x), py = fmaf(time, lo_d.y, lo_o.y), pz = fmaf(time, lo_d.z, lo_o.z);
+                    const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
+                    const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
+                    const float u = 1.0f - v - w;
+                    if (u >= 0.0f && v >= 0.0f && w >= 0.0f) {
+                        h.t = time;
+                        h.bv = v;
+                        h.bw = w;
+                        h.aux = __ldg(mesh->bvh_ids + first + j);
+                        mesh_hit = true;
+                    }
+                }
+                if ((any && mesh_hit) || sp == 0) mesh_done = true;
+                else cur = bstack[--sp];
+            }
+            if (mesh_done) {  // back to the object walk (next object, or the end of the ray)
+                if (mesh_hit) h.obj = (int)oi;
+                trav = false;
+                if (any && mesh_hit) oi = sv.nobjects;
+                else oi++;
+            }
+        }
+        if (!BVH && have && trav) {
             auto nd = load_node(mesh->nodes + node);
             while ((nd.word & 3u) != 3u) {
                 if (STATS) ts.node_visits++;

@@ -27,6 +27,7 @@ def lib():
         L.hostemu_scene_features.argtypes = [C.c_void_p]
         L.hostemu_closest_hit.argtypes = [C.c_void_p, dp, C.c_uint64, C.c_double, C.c_uint32, dp, capi.c_i32_p, dp,
                                           C.POINTER(capi.Stats)]
+        L.hostemu_bvh_check.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.hostemu_illuminate.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_uint64, C.c_uint32, dp, dp, dp]
         _lib = L
     return _lib
@@ -54,6 +55,13 @@ class EmuScene:
     @property
     def features(self) -> int:
         return int(lib().hostemu_scene_features(self.handle))
+
+    def bvh_check(self, mesh: int = 0):
+        """{nodes, leaves, max_leaf, depth, distinct, violations} of the BVH of mesh `mesh`, or None if it has none."""
+        out = (C.c_uint64 * 6)()
+        if lib().hostemu_bvh_check(self.handle, mesh, out) != 0:
+            return None
+        return dict(zip(("nodes", "leaves", "max_leaf", "depth", "distinct", "violations"), [int(v) for v in out]))
 
     def closest_hit(self, rays, t_min=1e-12, precision=capi.PRECISION_F64):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)

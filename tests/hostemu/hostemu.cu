@@ -36,7 +36,7 @@ struct InPlace {
     uint64_t bytes() const { return total; }
 };
 
-template <class R>
+template <class R, int FEAT>
 void closest_hits(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin, double* out_t, int32_t* out_obj,
                   double* out_n, rptb_stats* stats) {
     unsigned long long nv = 0, tt = 0, ot = 0;
@@ -48,12 +48,12 @@ void closest_hits(const SceneView<R>& sv, const double* rays, uint64_t n, double
         TravStats ts = {0, 0, 0};
         Hit<R> h;
         h.t = M<R>::inf();
-        closest_hit<R, true, F_EVERY>(sv, o, d, (R)tmin, false, h, ts);
+        closest_hit<R, true, FEAT>(sv, o, d, (R)tmin, false, h, ts);
         out_obj[i] = h.obj;
         out_t[i] = h.obj >= 0 ? (double)h.t : (double)INFINITY;
         if (out_n) {
             Vec3<R> nn = {(R)0, (R)0, (R)0};
-            if (h.obj >= 0) nn = finalize_hit<R, F_EVERY>(sv, sv.objects[h.obj], o, d, h).n;
+            if (h.obj >= 0) nn = finalize_hit<R, FEAT>(sv, sv.objects[h.obj], o, d, h).n;
             out_n[3 * i] = (double)nn.x;
             out_n[3 * i + 1] = (double)nn.y;
             out_n[3 * i + 2] = (double)nn.z;
@@ -98,13 +98,14 @@ struct hostemu_scene {
 };
 
 // Returns NULL and writes the flattener's message to `err` on a bad description.
+// The BVH of the f32 path is built iff desc->accel == RPTB_ACCEL_BVH (no environment, no default here).
 hostemu_scene* hostemu_scene_create(const rptb_scene_desc* desc, char* err, size_t errlen) {
     hostemu_scene* s = new (std::nothrow) hostemu_scene();
     if (!s) return nullptr;
     std::memset(&s->v32, 0, sizeof(s->v32));
     std::memset(&s->v64, 0, sizeof(s->v64));
     std::string msg;
-    if (flatten_scene(desc, s->hs, msg) != RPTB_OK) {
+    if (flatten_scene(desc, s->hs, msg, desc->accel == RPTB_ACCEL_BVH) != RPTB_OK) {
         if (err && errlen) {
             std::strncpy(err, msg.c_str(), errlen - 1);
             err[errlen - 1] = 0;
@@ -126,8 +127,76 @@ int hostemu_scene_features(const hostemu_scene* s) { return s->features; }
 // precision: 0 = Real float, 1 = Real double (rptb_precision)
 int hostemu_closest_hit(const hostemu_scene* s, const double* rays, uint64_t n, double t_min, uint32_t precision,
                         double* out_t, int32_t* out_object, double* out_normal, rptb_stats* stats) {
-    if (precision == RPTB_PRECISION_F64) closest_hits<double>(s->v64, rays, n, t_min, out_t, out_object, out_normal, stats);
-    else closest_hits<float>(s->v32, rays, n, t_min, out_t, out_object, out_normal, stats);
+    // like launch_closest_hit_impl: f32 goes through the BVH when the scene has one
+    if (precision == RPTB_PRECISION_F64) closest_hits<double, F_EVERY>(s->v64, rays, n, t_min, out_t, out_object, out_normal, stats);
+    else if (s->features & F_BVH) closest_hits<float, F_EVERY | F_BVH>(s->v32, rays, n, t_min, out_t, out_object, out_normal, stats);
+    else closest_hits<float, F_EVERY>(s->v32, rays, n, t_min, out_t, out_object, out_normal, stats);
+    return 0;
+}
+
+// Structural check of the BVH of mesh `mesh`: out = {nodes, leaves, largest leaf, depth, distinct triangles
+// referenced, violations}.  A violation is a triangle vertex (as the kernels see it: float) outside the box
+// its parent stores for its leaf, a child box that sticks out of its parent's, or a malformed leaf code.
+int hostemu_bvh_check(const hostemu_scene* s, uint32_t mesh, uint64_t* out) {
+    const HostMesh& hm = s->hs.meshes[mesh];
+    for (int i = 0; i < 6; i++) out[i] = 0;
+    if (hm.bvh_nodes.empty()) return -1;
+    std::vector<uint8_t> seen(hm.ntris, 0);
+    uint64_t leaves = 0, max_leaf = 0, depth = 0, violations = 0;
+    struct Item { int32_t code; float lo[3], hi[3]; uint32_t depth; };
+    std::vector<Item> stack;
+    Item root;
+    root.code = 0;
+    root.depth = 0;
+    for (int a = 0; a < 3; a++) root.lo[a] = -INFINITY, root.hi[a] = INFINITY;
+    stack.push_back(root);
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        depth = std::max<uint64_t>(depth, it.depth);
+        if (it.code >= 0) {
+            if ((size_t)it.code >= hm.bvh_nodes.size()) { violations++; continue; }
+            const BvhNodeDev& n = hm.bvh_nodes[it.code];
+            Item c[2];
+            c[0].code = n.child0; c[1].code = n.child1;
+            c[0].lo[0] = n.c0xy.x; c[0].hi[0] = n.c0xy.y; c[0].lo[1] = n.c0xy.z; c[0].hi[1] = n.c0xy.w; c[0].lo[2] = n.cz.x; c[0].hi[2] = n.cz.y;
+            c[1].lo[0] = n.c1xy.x; c[1].hi[0] = n.c1xy.y; c[1].lo[1] = n.c1xy.z; c[1].hi[1] = n.c1xy.w; c[1].lo[2] = n.cz.z; c[1].hi[2] = n.cz.w;
+            for (int k = 0; k < 2; k++) {
+                c[k].depth = it.depth + 1;
+                // child boxes are padded independently of the parent's: allow the pad (relative 1e-5)
+                for (int a = 0; a < 3; a++) {
+                    const float tol = 1e-5f * std::fmax(1e-3f, std::fmax(std::fabs(c[k].lo[a]), std::fabs(c[k].hi[a])));
+                    if (c[k].lo[a] < it.lo[a] - tol || c[k].hi[a] > it.hi[a] + tol) violations++;
+                }
+                stack.push_back(c[k]);
+            }
+        } else {
+            const uint32_t code = (uint32_t)~it.code;
+            const uint32_t first = code >> 3, count = (code & 7u) + 1u;
+            leaves++;
+            max_leaf = std::max<uint64_t>(max_leaf, count);
+            if (count > (uint32_t)BVH_LEAF_MAX || (uint64_t)first + count > hm.ntris) { violations++; continue; }
+            for (uint32_t k = first; k < first + count; k++) {
+                const uint32_t id = hm.bvh_ids[k];
+                if (id >= hm.ntris) { violations++; continue; }
+                seen[id]++;
+                for (int v = 0; v < 3; v++)
+                    for (int a = 0; a < 3; a++) {
+                        const float x = hm.verts32[9 * (size_t)id + 3 * v + a];
+                        if (x < it.lo[a] || x > it.hi[a]) violations++;
+                    }
+                // the permuted triangle data is the original's
+                for (int j = 0; j < 3; j++)
+                    if (std::memcmp(&hm.bvh_tri48[3 * (size_t)k + j], &hm.tri48[3 * (size_t)id + j], sizeof(float4)) != 0) violations++;
+            }
+        }
+    }
+    uint64_t distinct = 0;
+    for (uint8_t c : seen) {
+        distinct += c != 0;
+        if (c > 1) violations++;  // every triangle in exactly one leaf
+    }
+    out[0] = hm.bvh_nodes.size(); out[1] = leaves; out[2] = max_leaf; out[3] = depth; out[4] = distinct; out[5] = violations;
     return 0;
 }
 

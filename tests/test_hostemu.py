@@ -123,3 +123,96 @@ def test_flattener_rejects_what_the_device_cannot_hold():
     h = C.c_void_p()
     rc = capi.lib().rptb_scene_create(C.byref(flat.desc), 0, C.byref(h))
     assert rc == -1 and b"group 3 out of range" in capi.lib().rptb_last_error() and not h
+
+
+# ---------------------------------------------------------------- the f32 path's own BVH ----------------
+def _bvh_pair(scene):
+    return (emu.EmuScene(api.FlatScene(scene, accel=capi.ACCEL_BVH)), emu.EmuScene(api.FlatScene(scene, accel=capi.ACCEL_KDTREE)))
+
+
+@pytest.mark.parametrize("name", ["teapot", "dragon_small"])
+def test_bvh_finds_the_hits_of_the_reference_tree(orc, name):
+    """rptb_accel BVH (bvhbuild.cpp + bvh_intersect): a different structure over the same triangles and the same
+    triangle test -> the f32 hits are those of the kd-tree traversal, to the bit (ties on shared edges aside),
+    for a fraction of the node visits and triangle tests."""
+    cfg = scenes.teapot_scene() if name == "teapot" else scenes.dragon_scene(330, 82)
+    eb, ek = _bvh_pair(cfg.scene)
+    assert (eb.features & 64) and not (ek.features & 64)
+    chk = eb.bvh_check(0)
+    ntris = len(cfg.scene.objects[0].shape.shape.triangles)
+    assert chk["violations"] == 0 and chk["distinct"] == ntris and chk["max_leaf"] <= 4 and chk["depth"] < 94
+    assert ek.bvh_check(0) is None
+    rng = np.random.default_rng(5)
+    rays = np.concatenate([util.camera_rays(cfg.camera, 30000, rng, spread=0.4), util.interior_rays([-2, -0.99, -2], [2, 1.5, 2], 15000, rng)])
+    tb, ob, nb, sb = eb.closest_hit(rays, precision=capi.PRECISION_F32)
+    tk, ok, nk, sk = ek.closest_hit(rays, precision=capi.PRECISION_F32)
+    same = (tb == tk) & (ob == ok)
+    assert same.mean() >= 0.9999
+    assert np.abs(nb[same] - nk[same]).max() <= 1e-6
+    assert sb["node_visits"] < 0.5 * sk["node_visits"] and sb["tri_tests"] < 0.1 * sk["tri_tests"]
+    # and against the oracle, the usual f32 tolerances
+    t0, o0, n0, _ = orc.OracleScene(api.FlatScene(cfg.scene)).closest_hit(rays)
+    agree = ob == o0
+    assert agree.mean() > 0.9999
+    hit = agree & (o0 >= 0)
+    rel = np.abs(tb[hit] - t0[hit]) / np.abs(t0[hit])
+    assert np.median(rel) <= 2e-7 and np.quantile(rel, 0.99) <= 1e-5 and np.quantile(rel, 0.999) <= 1e-4
+    # f64 never uses it
+    tb64, ob64, _, s64 = eb.closest_hit(rays, precision=capi.PRECISION_F64)
+    np.testing.assert_array_equal(tb64, t0)
+    assert s64["tri_tests"] == sk["tri_tests"] or s64["tri_tests"] > sb["tri_tests"]
+
+
+def test_bvh_builder_on_awkward_meshes():
+    rng = np.random.default_rng(8)
+
+    def mesh_scene(tris):
+        scene = api.Scene()
+        scene.add(api.Object(api.Mesh(np.asarray(tris))))
+        return scene
+
+    def check(tris, nrays=4000):
+        scene = mesh_scene(tris)
+        eb, ek = _bvh_pair(scene)
+        if not (ek.features & 1):          # the reference tree is one leaf: no BVH is built, the leaf is scanned
+            assert eb.bvh_check(0) is None and not (eb.features & 64)
+            return None
+        chk = eb.bvh_check(0)
+        assert chk["violations"] == 0 and chk["distinct"] == len(tris) and chk["max_leaf"] <= 4 and chk["depth"] < 94
+        lo, hi = np.asarray(tris)[:, :9].reshape(-1, 3).min(0), np.asarray(tris)[:, :9].reshape(-1, 3).max(0)
+        c, r = (lo + hi) / 2, np.linalg.norm(hi - lo) + 1e-3
+        o = c + util.random_unit(rng, nrays) * r
+        tgt = lo + rng.uniform(0, 1, (nrays, 3)) * (hi - lo)
+        rays = np.concatenate([o, util.normalize(tgt - o)], axis=1)
+        tb, ob, _, _ = eb.closest_hit(rays, precision=capi.PRECISION_F32)
+        tk, ok, _, _ = ek.closest_hit(rays, precision=capi.PRECISION_F32)
+        assert ((tb == tk) & (ob == ok)).mean() >= 0.999
+        return chk
+
+    # 64 copies of one triangle: the kd builder gives up (one leaf) -> no BVH
+    assert check(np.tile(api.Triangle.from_vertices([0, 0, 0], [1, 0, 0], [0, 1, 0]), (64, 1))) is None
+    # a 40 x 40 grid of quads (3 200 triangles, many coplanar, zero-thickness boxes)
+    g = []
+    for i in range(40):
+        for j in range(40):
+            a, b, c_, d = [i, 0, j], [i + 1, 0, j], [i + 1, 0, j + 1], [i, 0, j + 1]
+            g += [api.Triangle.from_vertices(a, b, c_), api.Triangle.from_vertices(a, c_, d)]
+    assert check(np.stack(g))["nodes"] > 500
+    # sizes spanning six decades along one axis (SAH peels them off one by one -> a deep, thin tree)
+    s = []
+    for k in range(60):
+        x = 1.5 ** k * 1e-3
+        s.append(api.Triangle.from_vertices([x, 0, 0], [x * 1.4, 0, 0], [x, x * 0.4, x * 0.1]))
+    chk = check(np.stack(s))
+    assert chk is None or chk["depth"] <= 60
+    # random soup
+    c = rng.uniform(-1, 1, (5000, 1, 3))
+    v = c + rng.normal(0, 0.03, (5000, 3, 3))
+    assert check(np.stack([api.Triangle.from_vertices(*t) for t in v]))["nodes"] > 1000
+
+
+def test_accel_field_is_validated():
+    flat = api.FlatScene(scenes.teapot_scene().scene)
+    flat.desc.accel = 7
+    with pytest.raises(ValueError, match="bad accel"):
+        emu.EmuScene(flat)
