@@ -165,6 +165,8 @@ def ncu_traffic(workload_name: str, spp: int, engine: int):
         if not isinstance(rec, dict):
             return None
         b = float(rec["dram_bytes_per_launch"])
+        if (workload_name == "dragon-proxy") != (engine == 2):
+            return None  # the dragon record is a wavefront trace launch; no capture of the megakernel on that workload yet
         return b if engine == 2 else b * spp / float(rec["capture_spp"])
     except Exception:
         return None

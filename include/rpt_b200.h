@@ -165,7 +165,7 @@ typedef struct rptb_env {
  *   KDTREE  the reference-shaped KdTree<Triangle> (src/kdtree.rs:99-223), node for node -- what the f64
  *           parity gate, rptb_closest_hit with stats, and the traversal counters of rptb_stats always use
  *   BVH     a binary SAH BVH built by the library over the same triangles, each in exactly one leaf
- * AUTO = the library's default (environment variable RPTB_ACCEL=kdtree|bvh overrides it).              */
+ * AUTO = the library's default, BVH (environment variable RPTB_ACCEL=kdtree|bvh overrides it).         */
 typedef enum rptb_accel { RPTB_ACCEL_AUTO = 0, RPTB_ACCEL_KDTREE = 1, RPTB_ACCEL_BVH = 2 } rptb_accel;
 
 /* ---- Scene: src/scene.rs:7-18 ---------------------------------------------- */
@@ -210,8 +210,9 @@ typedef enum rptb_precision {
  *               (analytic shapes, tiny meshes: sphere, cornell, glass)
  *   WAVEFRONT   path state in HBM, a shade kernel and a persistent trace kernel per path
  *               vertex -- best when kd-tree traversal dominates (teapot, dragon)
- * AUTO picks WAVEFRONT iff some mesh's kd-tree has more than one node (f32 only; the f64
- * parity gate always runs the megakernel).                                             */
+ * AUTO picks WAVEFRONT iff the scene was created with RPTB_ACCEL_KDTREE and its kd-trees hold >= 50 000
+ * nodes (with the BVH the megakernel wins on every scene measured); f32 only -- the f64 parity gate always
+ * runs the megakernel.                                                                  */
 typedef enum rptb_engine { RPTB_ENGINE_AUTO = 0, RPTB_ENGINE_MEGAKERNEL = 1, RPTB_ENGINE_WAVEFRONT = 2 } rptb_engine;
 
 typedef struct rptb_render_params {

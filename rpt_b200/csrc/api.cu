@@ -42,9 +42,10 @@ int parse_stl_bytes(const void* data, size_t len, std::vector<double>& tris, std
 
 using namespace rptb;
 
-// What RPTB_ACCEL_AUTO means when the environment does not say.
+// What RPTB_ACCEL_AUTO means when the environment does not say.  Measured on one B200 (tools/gpu_accel.py,
+// profiles/raw/accel_table.json): teapot 5.8 -> 16.5 Gsamples/s, dragon proxy 0.145 -> 0.89 Gsamples/s, same images.
 #ifndef RPTB_ACCEL_DEFAULT
-#define RPTB_ACCEL_DEFAULT RPTB_ACCEL_KDTREE
+#define RPTB_ACCEL_DEFAULT RPTB_ACCEL_BVH
 #endif
 
 namespace {
@@ -273,8 +274,11 @@ bool use_wavefront(const rptb_scene* s, const rptb_render_params* p) {
     if (s->features & F_EXT) return false;  // kd-trees over shapes / MonomialSurface: megakernel only
     if (p->engine == RPTB_ENGINE_WAVEFRONT) return true;
     if (p->engine == RPTB_ENGINE_MEGAKERNEL) return false;
-    // measured on one B200: the megakernel wins while traversal is cheap (teapot: 2 487 nodes,
-    // 5.2 vs 2.1 Gsamples/s), the wavefront wins once it dominates (dragon proxy: 823 k nodes)
+    // measured on one B200 with the reference-shaped kd-trees: the megakernel wins while traversal is cheap
+    // (teapot: 2 487 nodes, 5.8 vs 2.3 Gsamples/s), the wavefront wins once it dominates (dragon proxy: 823 k
+    // nodes, 45 vs 145 Msamples/s).  Through the BVH a ray costs ~25 node visits and ~3 triangle tests on
+    // either mesh and the megakernel wins on both (dragon proxy 892 vs 670 Msamples/s, teapot 16.5 vs 3.2 G).
+    if (s->features & F_BVH) return false;
     return s->has_tree && s->tree_nodes >= 50000 && s->sampled_lights <= 8;
 }
 
