@@ -216,3 +216,21 @@ def test_accel_field_is_validated():
     flat.desc.accel = 7
     with pytest.raises(ValueError, match="bad accel"):
         emu.EmuScene(flat)
+
+
+def test_bvh_under_a_kd_tree_of_shapes(orc):
+    """rptb_closest_hit without counters on a scene that has both a kd-tree of shapes and BVH meshes runs
+    closest_hit<F_EVERY | F_BVH>: the instances of examples/fractal_teapots are entered through the group's
+    kd-tree and then traversed through the shared teapot's BVH.  Same hits as through its kd-tree."""
+    cfg = scenes.fractal_teapots_scene(3)
+    eb, ek = _bvh_pair(cfg.scene)
+    assert (eb.features & (16 | 64)) == (16 | 64) and eb.bvh_check(0)["violations"] == 0
+    rng = np.random.default_rng(12)
+    rays = np.concatenate([util.camera_rays(cfg.camera, 30000, rng, spread=0.35), util.interior_rays([-2.5] * 3, [2.5] * 3, 15000, rng)])
+    tb, ob, nb, sb = eb.closest_hit(rays, precision=capi.PRECISION_F32)
+    tk, ok, nk, sk = ek.closest_hit(rays, precision=capi.PRECISION_F32)
+    same = (tb == tk) & (ob == ok)
+    assert same.mean() >= 0.9999 and np.abs(nb[same] - nk[same]).max() <= 1e-6
+    assert sb["tri_tests"] < 0.2 * sk["tri_tests"]
+    t0, o0, _, _ = orc.OracleScene(api.FlatScene(cfg.scene)).closest_hit(rays)
+    assert (ob == o0).mean() > 0.9995
