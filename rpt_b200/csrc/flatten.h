@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -696,5 +697,50 @@ bool bind_scene(HostScene& hs, Put& put, bool release, SceneView<float>& v32, Sc
     }
     return true;
 }
+
+// rptb_camera + rptb_render_params -> the kernel arguments (everything but the output / partial pointers).
+template <class R>
+void fill_args(const rptb_camera* cam, const rptb_render_params* p, RenderArgs<R>& a) {
+    std::memset(&a, 0, sizeof(a));
+    // Camera::cast_ray invariants (src/camera.rs:66-67)
+    const double d = 1.0 / std::tan(cam->fov / 2.0);
+    const double* di = cam->direction;
+    const double* up = cam->up;
+    double right[3] = {di[1] * up[2] - di[2] * up[1], di[2] * up[0] - di[0] * up[2], di[0] * up[1] - di[1] * up[0]};
+    const double len = std::sqrt(right[0] * right[0] + right[1] * right[1] + right[2] * right[2]);
+    for (int k = 0; k < 3; k++) {
+        a.cam.eye[k] = (R)cam->eye[k];
+        a.cam.direction[k] = (R)di[k];
+        a.cam.up[k] = (R)up[k];
+        a.cam.right[k] = (R)(right[k] / len);
+    }
+    a.cam.d = (R)d;
+    a.cam.aperture = (R)cam->aperture;
+    a.cam.focal_distance = (R)cam->focal_distance;
+    a.width = p->width;
+    a.height = p->height;
+    a.iterations = p->iterations;
+    a.max_bounces = p->max_bounces;
+    a.exposure_scale = (R)std::pow(2.0, p->exposure_value);
+    a.seed = p->seed;
+    a.first_sample = p->first_sample;
+    a.shard_count = p->shard_count ? p->shard_count : 1;
+    a.shard_index = p->shard_index;
+    a.tiles_x = (p->width + 15) / 16;
+    a.tiles_y = (p->height + 7) / 8;
+    const uint32_t ntiles = a.tiles_x * a.tiles_y;
+    a.ntiles_mine = ntiles > a.shard_index ? (ntiles - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
+    sample_chunks(p->iterations, a.nchunks, a.chunk);
+    sample_groups(a.ntiles_mine, a.nchunks, a.ngroups, a.chunks_per_group);
+    if (const char* g = getenv("RPTB_GROUPS")) {  // tuning aid: force the number of sample groups
+        uint32_t want = (uint32_t)atoi(g);
+        if (want < 1) want = 1;
+        if (want > a.nchunks) want = a.nchunks;
+        a.chunks_per_group = (a.nchunks + want - 1) / want;
+        a.ngroups = (a.nchunks + a.chunks_per_group - 1) / a.chunks_per_group;
+    }
+    a.partial = nullptr;
+}
+
 
 }  // namespace rptb

@@ -102,18 +102,34 @@ enum : int {
 // at the single get_closest_hit site; a lane with nothing to do in a slot (light sample
 // with provably zero contribution, path just ended) sits that trace out.  Per lane the
 // order of operations -- and of random draws -- is exactly trace_ray's.
-template <class R, int MAXD, bool STATS, int FEAT = F_ALL>
-__global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) render_kernel(const __grid_constant__ SceneView<R> sv, const __grid_constant__ RenderArgs<R> a) {
-    const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
+//
+// The body is `render_thread`: one thread's whole life, written against a warp policy W.  On the device W is
+// DeviceWarp (the real votes and reductions) and render_kernel is a one-line wrapper, so the generated code is
+// what it was when the body lived in the kernel.  tests/hostemu instantiates the same body with a
+// single-lane policy to run the integrator on the host against the oracle (test infrastructure).
+#ifdef __CUDACC__
+struct DeviceWarp {
+    static __device__ __forceinline__ unsigned activemask() { return __activemask(); }
+    static __device__ __forceinline__ bool all(unsigned m, bool p) { return __all_sync(m, p); }
+    static __device__ __forceinline__ uint32_t reduce_add(unsigned m, uint32_t v) { return __reduce_add_sync(m, v); }
+    static __device__ __forceinline__ bool is_leader(unsigned m, uint32_t lane) { return (int)lane == __ffs(m) - 1; }
+    static __device__ __forceinline__ void add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+};
+#endif
+
+template <class R, int MAXD, bool STATS, int FEAT, class W>
+RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const uint32_t block_x, const uint32_t block_y,
+                          const uint32_t thread_x) {
+    const uint32_t tile = a.shard_index + block_x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = thread_x >> 5, lane = thread_x & 31u;
     const uint32_t x = tx * TILE_W + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t y = ty * TILE_H + (warp >> 1) * 4u + (lane >> 3);
     if (x >= a.width || y >= a.height) return;
     const uint32_t pix = y * a.width + x;
     // The lanes of this warp that own a pixel.  They stay together until all of them have
     // finished their samples (independent thread scheduling gives no such guarantee).
-    const unsigned wmask = __activemask();
+    const unsigned wmask = W::activemask();
 
     const R tmin = (R)1e-12;  // EPSILON, renderer.rs:14
     const R dim = (R)max(a.width, a.height);
@@ -141,10 +157,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
     uint32_t mat_id = 0, li = 0;
     bool dead = false;
     // this thread's run of samples: [s, s_end) of [0, iterations) = chunks_per_group whole chunks
-    uint32_t s = blockIdx.y * a.chunks_per_group * a.chunk;
+    uint32_t s = block_y * a.chunks_per_group * a.chunk;
     const uint32_t s_end = min(s + a.chunks_per_group * a.chunk, a.iterations);
-    uint32_t chunk_id = blockIdx.y * a.chunks_per_group, chunk_left = a.chunk;
-    const size_t pslot = (size_t)blockIdx.x * RENDER_THREADS + threadIdx.x;
+    uint32_t chunk_id = block_y * a.chunks_per_group, chunk_left = a.chunk;
+    const size_t pslot = (size_t)block_x * RENDER_THREADS + thread_x;
     const size_t pstride = (size_t)a.ntiles_mine * RENDER_THREADS;
     int depth = 0;
     int status = ST_FRESH;
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
         }
 
         // ================= the single get_closest_hit site ==============================
-        if (__all_sync(wmask, status == ST_IDLE)) break;  // also re-converges the warp
+        if (W::all(wmask, status == ST_IDLE)) break;  // also re-converges the warp
         Hit<R> h;
         h.t = tmax;
         h.obj = -1;
@@ -358,38 +374,44 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
     }
 
     if (a.counters) {
-        const unsigned m = __activemask();
-        const int leader = __ffs(m) - 1;
-        const uint32_t v0 = __reduce_add_sync(m, pc.segments), v1 = __reduce_add_sync(m, pc.rays);
-        const uint32_t v2 = __reduce_add_sync(m, pc.mesh_hits), v3 = __reduce_add_sync(m, pc.env_lookups);
+        const unsigned m = W::activemask();
+        const uint32_t v0 = W::reduce_add(m, pc.segments), v1 = W::reduce_add(m, pc.rays);
+        const uint32_t v2 = W::reduce_add(m, pc.mesh_hits), v3 = W::reduce_add(m, pc.env_lookups);
         // node/tri counters can exceed 2^32 per warp on long renders: reduce in two halves
-        const uint32_t n_lo = __reduce_add_sync(m, pc.ts.node_visits & 0xFFFFu), n_hi = __reduce_add_sync(m, pc.ts.node_visits >> 16);
-        const uint32_t t_lo = __reduce_add_sync(m, pc.ts.tri_tests & 0xFFFFu), t_hi = __reduce_add_sync(m, pc.ts.tri_tests >> 16);
-        const uint32_t o_lo = __reduce_add_sync(m, pc.ts.object_tests & 0xFFFFu), o_hi = __reduce_add_sync(m, pc.ts.object_tests >> 16);
-        if ((int)lane == leader) {
-            atomicAdd(&a.counters->segments, (unsigned long long)v0);
-            atomicAdd(&a.counters->rays, (unsigned long long)v1);
-            atomicAdd(&a.counters->mesh_hits, (unsigned long long)v2);
-            atomicAdd(&a.counters->env_lookups, (unsigned long long)v3);
+        const uint32_t n_lo = W::reduce_add(m, pc.ts.node_visits & 0xFFFFu), n_hi = W::reduce_add(m, pc.ts.node_visits >> 16);
+        const uint32_t t_lo = W::reduce_add(m, pc.ts.tri_tests & 0xFFFFu), t_hi = W::reduce_add(m, pc.ts.tri_tests >> 16);
+        const uint32_t o_lo = W::reduce_add(m, pc.ts.object_tests & 0xFFFFu), o_hi = W::reduce_add(m, pc.ts.object_tests >> 16);
+        if (W::is_leader(m, lane)) {
+            W::add(&a.counters->segments, (unsigned long long)v0);
+            W::add(&a.counters->rays, (unsigned long long)v1);
+            W::add(&a.counters->mesh_hits, (unsigned long long)v2);
+            W::add(&a.counters->env_lookups, (unsigned long long)v3);
             if (STATS) {
-                atomicAdd(&a.counters->node_visits, (unsigned long long)n_lo + ((unsigned long long)n_hi << 16));
-                atomicAdd(&a.counters->tri_tests, (unsigned long long)t_lo + ((unsigned long long)t_hi << 16));
-                atomicAdd(&a.counters->object_tests, (unsigned long long)o_lo + ((unsigned long long)o_hi << 16));
+                W::add(&a.counters->node_visits, (unsigned long long)n_lo + ((unsigned long long)n_hi << 16));
+                W::add(&a.counters->tri_tests, (unsigned long long)t_lo + ((unsigned long long)t_hi << 16));
+                W::add(&a.counters->object_tests, (unsigned long long)o_lo + ((unsigned long long)o_hi << 16));
             }
         }
     }
 }
 
+#ifdef __CUDACC__
+template <class R, int MAXD, bool STATS, int FEAT = F_ALL>
+__global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) render_kernel(const __grid_constant__ SceneView<R> sv, const __grid_constant__ RenderArgs<R> a) {
+    render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x);
+}
+#endif
+
 // Add the chunk sums of every pixel in chunk order and apply 1/iterations * 2^EV (renderer.rs:141).
 template <class R>
-__global__ void resolve_chunks_kernel(const RenderArgs<R> a) {
-    const uint32_t tile = a.shard_index + blockIdx.x * a.shard_count;
+RPTB_D void resolve_chunks_thread(const RenderArgs<R>& a, const uint32_t block_x, const uint32_t thread_x) {
+    const uint32_t tile = a.shard_index + block_x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = thread_x >> 5, lane = thread_x & 31u;
     const uint32_t x = tx * TILE_W + (warp & 1u) * 8u + (lane & 7u);
     const uint32_t y = ty * TILE_H + (warp >> 1) * 4u + (lane >> 3);
     if (x >= a.width || y >= a.height) return;
-    const size_t slot = (size_t)blockIdx.x * RENDER_THREADS + threadIdx.x;
+    const size_t slot = (size_t)block_x * RENDER_THREADS + thread_x;
     const size_t stride = (size_t)a.ntiles_mine * RENDER_THREADS;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (uint32_t c = 0; c < a.nchunks; c++) {
@@ -402,6 +424,12 @@ __global__ void resolve_chunks_kernel(const RenderArgs<R> a) {
     out[1] = (R)(s1 / it * (double)a.exposure_scale);
     out[2] = (R)(s2 / it * (double)a.exposure_scale);
 }
+#ifdef __CUDACC__
+template <class R>
+__global__ void resolve_chunks_kernel(const RenderArgs<R> a) {
+    resolve_chunks_thread<R>(a, blockIdx.x, threadIdx.x);
+}
+#endif
 
 // Zero the pixels of tiles that belong to other shards (so an all-reduce(sum) of the
 // shard buffers is the full image, bit-identical for any shard count).

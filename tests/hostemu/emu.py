@@ -27,6 +27,7 @@ def lib():
         L.hostemu_scene_features.argtypes = [C.c_void_p]
         L.hostemu_closest_hit.argtypes = [C.c_void_p, dp, C.c_uint64, C.c_double, C.c_uint32, dp, capi.c_i32_p, dp,
                                           C.POINTER(capi.Stats)]
+        L.hostemu_render.argtypes = [C.c_void_p, C.POINTER(capi.Camera), C.POINTER(capi.RenderParams), dp, C.POINTER(capi.Stats)]
         L.hostemu_bvh_check.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.hostemu_illuminate.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_uint64, C.c_uint32, dp, dp, dp]
         _lib = L
@@ -55,6 +56,16 @@ class EmuScene:
     @property
     def features(self) -> int:
         return int(lib().hostemu_scene_features(self.handle))
+
+    def render(self, camera, params):
+        """Renderer::sample through the emulated megakernel -> ((w*h, 3) float64, stats dict, FEAT bits of the variant)."""
+        out = np.empty((params.width * params.height, 3))
+        st = capi.Stats()
+        cam = camera.to_c() if hasattr(camera, "to_c") else camera
+        feat = lib().hostemu_render(self.handle, C.byref(cam), C.byref(params), out.ctypes.data_as(dp), C.byref(st))
+        if feat < -0:
+            raise ValueError("bad render parameters")
+        return out, st.as_dict(), int(feat)
 
     def bvh_check(self, mesh: int = 0):
         """{nodes, leaves, max_leaf, depth, distinct, violations} of the BVH of mesh `mesh`, or None if it has none."""

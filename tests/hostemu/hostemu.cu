@@ -1,8 +1,9 @@
 // hostemu.cu -- TEST INFRASTRUCTURE, NOT PRODUCT.  Never linked into librpt_b200.so, never loaded by
 // rpt_b200/*: only tests/test_hostemu.py builds and loads it.
 //
-// The geometry / light-sampling device functions of rpt_b200/csrc (geometry.cuh, shading.cuh: the code
-// the CUDA kernels inline) compiled for the HOST with RPTB_HOST_EMU, over the very arrays
+// The device functions of rpt_b200/csrc (geometry.cuh, shading.cuh: the code the CUDA kernels inline; and
+// render_thread of integrator.cuh: the whole body of the path-tracing megakernel, run one lane at a time
+// with a single-lane warp policy) compiled for the HOST with RPTB_HOST_EMU, over the very arrays
 // rptb_scene_create would upload (flatten.h), so that their control flow -- kd traversal, the kd-tree of
 // shapes, MonomialSurface, Transformed, finalize_hit, shape_sample -- can be checked against the oracle
 // in the build container, which has no GPU.  It proves nothing about the kernels' scheduling, fast-math
@@ -18,7 +19,8 @@
 #include <string>
 
 #include "../../rpt_b200/csrc/flatten.h"
-#include "../../rpt_b200/csrc/shading.cuh"
+#include "../../rpt_b200/csrc/integrator.cuh"
+#include "../../rpt_b200/csrc/launch.h"
 
 using namespace rptb;
 
@@ -86,6 +88,95 @@ void illuminations(const SceneView<R>& sv, uint32_t light, const double* pos, ui
     }
 }
 
+// The megakernel's warp policy for one lane run on its own: a vote over the warp is the lane's own
+// predicate, a reduction its own value.  (The kernel's warp-level structure -- slot schedule, reconvergence,
+// the shared Philox refill -- only changes WHEN lanes do things, never what a lane computes.)
+struct HostLane {
+    static __host__ __device__ unsigned activemask() { return 1u; }
+    static __host__ __device__ bool all(unsigned, bool p) { return p; }
+    static __host__ __device__ uint32_t reduce_add(unsigned, uint32_t v) { return v; }
+    static __host__ __device__ bool is_leader(unsigned, uint32_t) { return true; }
+    static __host__ __device__ void add(unsigned long long* p, unsigned long long v) {
+#ifndef __CUDA_ARCH__
+#pragma omp atomic
+        *p += v;
+#else
+        (void)p, (void)v;
+#endif
+    }
+};
+
+template <class R, int MAXD, bool STATS, int FEAT>
+void run_grid(const SceneView<R>& sv, const RenderArgs<R>& a) {
+    const int64_t nblocks = (int64_t)a.ntiles_mine * a.ngroups;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < nblocks; b++) {
+        const uint32_t bx = (uint32_t)(b % a.ntiles_mine), by = (uint32_t)(b / a.ntiles_mine);
+        for (uint32_t t = 0; t < (uint32_t)RENDER_THREADS; t++) render_thread<R, MAXD, STATS, FEAT, HostLane>(sv, a, bx, by, t);
+    }
+    if (a.nchunks > 1) {
+#pragma omp parallel for schedule(static)
+        for (int64_t bx = 0; bx < (int64_t)a.ntiles_mine; bx++)
+            for (uint32_t t = 0; t < (uint32_t)RENDER_THREADS; t++) resolve_chunks_thread<R>(a, (uint32_t)bx, t);
+    }
+}
+
+// The instantiation launch_render_impl (launch_impl.cuh) would launch for these features -- keep in step with it.
+// Returns the FEAT it ran.
+template <class R>
+int run_render(const SceneView<R>& sv, const RenderArgs<R>& a, bool stats, int features) {
+    const int base = features & F_ALL;
+    const bool small = (features & F_SMALL) != 0, ext = (features & F_EXT) != 0;
+    if (a.max_bounces > 16) {
+        if (stats) run_grid<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY>(sv, a);
+        else run_grid<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY>(sv, a);
+        return F_EVERY;
+    }
+    if (stats) { run_grid<R, 16, true, F_EVERY>(sv, a); return F_EVERY; }
+    if (ext) { run_grid<R, 16, false, F_EVERY>(sv, a); return F_EVERY; }
+    if constexpr (M<R>::literal) {
+        run_grid<R, 16, false, F_ALL>(sv, a);
+        return F_ALL;
+    } else {
+        if ((features & F_BVH) && base == F_TREE) { run_grid<R, 16, false, F_TREE | F_BVH>(sv, a); return F_TREE | F_BVH; }
+        if (features & F_BVH) { run_grid<R, 16, false, F_ALL | F_BVH>(sv, a); return F_ALL | F_BVH; }
+        if (base == 0 && small) { run_grid<R, 16, false, F_SMALL>(sv, a); return F_SMALL; }
+        if (base == 0) { run_grid<R, 16, false, 0>(sv, a); return 0; }
+        if (base == F_TREE) { run_grid<R, 16, false, F_TREE>(sv, a); return F_TREE; }
+        if (base == (F_TRANSP | F_HDRI) && small) { run_grid<R, 16, false, F_TRANSP | F_HDRI | F_SMALL>(sv, a); return F_TRANSP | F_HDRI | F_SMALL; }
+        if (base == (F_TRANSP | F_HDRI)) { run_grid<R, 16, false, F_TRANSP | F_HDRI>(sv, a); return F_TRANSP | F_HDRI; }
+        run_grid<R, 16, false, F_ALL>(sv, a);
+        return F_ALL;
+    }
+}
+
+template <class R>
+int render_impl(const SceneView<R>& sv, const rptb_camera* cam, const rptb_render_params* p, int features, double* out_rgb,
+                rptb_stats* stats) {
+    RenderArgs<R> a;
+    fill_args(cam, p, a);
+    const size_t nvals = (size_t)p->width * p->height * 3;
+    std::vector<R> out(nvals, (R)0);  // pixels of other shards stay zero (clear_kernel)
+    std::vector<double> partial;
+    if (a.nchunks > 1) partial.assign((size_t)a.nchunks * a.ntiles_mine * RENDER_THREADS * 3, 0.0);
+    DeviceCounters counters;
+    std::memset(&counters, 0, sizeof(counters));
+    a.out = out.data();
+    a.partial = partial.empty() ? nullptr : partial.data();
+    a.counters = &counters;
+    int feat = -1;
+    if (a.ntiles_mine > 0) feat = run_render<R>(sv, a, p->collect_stats != 0, features);
+    for (size_t i = 0; i < nvals; i++) out_rgb[i] = (double)out[i];
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->segments = counters.segments; stats->rays = counters.rays; stats->node_visits = counters.node_visits;
+        stats->tri_tests = counters.tri_tests; stats->mesh_hits = counters.mesh_hits; stats->env_lookups = counters.env_lookups;
+        stats->object_tests = counters.object_tests;
+        stats->engine = RPTB_ENGINE_MEGAKERNEL;
+    }
+    return feat;
+}
+
 }  // namespace
 
 extern "C" {
@@ -137,6 +228,16 @@ int hostemu_closest_hit(const hostemu_scene* s, const double* rays, uint64_t n, 
 // Structural check of the BVH of mesh `mesh`: out = {nodes, leaves, largest leaf, depth, distinct triangles
 // referenced, violations}.  A violation is a triangle vertex (as the kernels see it: float) outside the box
 // its parent stores for its leaf, a child box that sticks out of its parent's, or a malformed leaf code.
+// Renderer::sample through the megakernel's thread body (every lane run on its own; see HostLane).  Same contract
+// as rptb_render_samples; returns the FEAT bits of the kernel instantiation that was emulated, or -1 on bad params.
+int hostemu_render(const hostemu_scene* s, const rptb_camera* cam, const rptb_render_params* p, double* out_rgb, rptb_stats* stats) {
+    if (!s || !cam || !p || !out_rgb || p->width == 0 || p->height == 0 || p->iterations == 0 ||
+        p->max_bounces > MAX_BOUNCES_SUPPORTED)
+        return -1;
+    if (p->precision == RPTB_PRECISION_F64) return render_impl<double>(s->v64, cam, p, F_ALL | (s->features & F_EXT), out_rgb, stats);
+    return render_impl<float>(s->v32, cam, p, s->features, out_rgb, stats);
+}
+
 int hostemu_bvh_check(const hostemu_scene* s, uint32_t mesh, uint64_t* out) {
     const HostMesh& hm = s->hs.meshes[mesh];
     for (int i = 0; i < 6; i++) out[i] = 0;

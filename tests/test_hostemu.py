@@ -1,7 +1,8 @@
-"""The device geometry code checked against the oracle WITHOUT a GPU.
+"""The device code checked against the oracle WITHOUT a GPU.
 
-tests/hostemu compiles the functions the CUDA kernels inline (closest_hit, kd_intersect, group_intersect,
-monomial_intersect, finalize_hit, shape_sample, illuminate -- rpt_b200/csrc/geometry.cuh, shading.cuh) for the
+tests/hostemu compiles the functions the CUDA kernels inline (closest_hit, kd_intersect, bvh_intersect,
+group_intersect, monomial_intersect, finalize_hit, shape_sample, illuminate -- rpt_b200/csrc/geometry.cuh,
+shading.cuh) and render_thread, the whole body of the path-tracing megakernel (integrator.cuh), for the
 host and runs them over the arrays rptb_scene_create would upload.  With Real = double every operation is
 the oracle's, so hits, normals and traversal counters must agree exactly; with Real = float within the
 f32 tolerances the GPU parity tests use.  This is test infrastructure (it cannot say anything about the
@@ -234,3 +235,88 @@ def test_bvh_under_a_kd_tree_of_shapes(orc):
     assert sb["tri_tests"] < 0.2 * sk["tri_tests"]
     t0, o0, _, _ = orc.OracleScene(api.FlatScene(cfg.scene)).closest_hit(rays)
     assert (ob == o0).mean() > 0.9995
+
+
+# ---------------------------------------------------------------- the megakernel, lane by lane ----------
+# render_thread (integrator.cuh) is the whole body of the path-tracing megakernel; hostemu runs it for every
+# thread of the grid with a single-lane warp policy.  The flattened recursion (slot schedule, per-level clamp
+# stack, forward accumulation, path regeneration, sample chunks) must then BE the reference's trace_ray:
+# with Real = double, on the same libm as the oracle, every pixel and every counter comes out equal.
+RENDERS = {  # name: (config factory, w, h, spp, max_bounces, accel, FEAT of the f32 variant)
+    "cornell": (scenes.cornell_scene, 32, 32, 8, 6, capi.ACCEL_AUTO, 0),
+    "sphere": (scenes.sphere_scene, 48, 27, 8, 2, capi.ACCEL_AUTO, F_SMALL),
+    "teapot_kd": (scenes.teapot_scene, 48, 27, 4, 2, capi.ACCEL_KDTREE, F_TREE),
+    "teapot_bvh": (scenes.teapot_scene, 48, 27, 4, 2, capi.ACCEL_BVH, F_TREE | 64),
+    "glass": (lambda: scenes.glass_scene(64, 32), 48, 27, 8, 12, capi.ACCEL_AUTO, F_TRANSP | F_HDRI | F_SMALL),
+    "fractal_teapots": (lambda: scenes.fractal_teapots_scene(3), 48, 36, 4, 1, capi.ACCEL_AUTO, 7 | F_GROUP | F_MONO),
+    "monomial_glass": (lambda: scenes.monomial_glass_scene(64, 32), 48, 36, 8, 1, capi.ACCEL_AUTO, 7 | F_GROUP | F_MONO),
+}
+
+
+def _params(cfg, w, h, spp, mb, seed=1, precision=capi.PRECISION_F32, **kw):
+    return api.Renderer(cfg.scene, cfg.camera).width(w).height(h).max_bounces(mb).seed(seed).precision(precision).params(spp, **kw)
+
+
+@pytest.mark.parametrize("name", sorted(RENDERS))
+def test_megakernel_body_is_trace_ray(orc, name):
+    mk, w, h, spp, mb, accel, want_feat = RENDERS[name]
+    cfg = mk()
+    flat = api.FlatScene(cfg.scene, accel=accel)
+    e, o = emu.EmuScene(flat), orc.OracleScene(flat)
+    ref, st0 = o.render(cfg.camera, _params(cfg, w, h, spp, mb))
+    g64, s64, f64 = e.render(cfg.camera, _params(cfg, w, h, spp, mb, precision=capi.PRECISION_F64))
+    np.testing.assert_allclose(g64, ref, rtol=1e-12, atol=0)          # (equal to the bit in practice)
+    assert (s64["segments"], s64["rays"]) == (st0["segments"], st0["rays"])
+    assert s64["env_lookups"] == st0["env_lookups"] and s64["mesh_hits"] == st0["mesh_hits"]
+    # the f32 product variant the library would launch for this scene, same random streams
+    ref2, _ = o.render(cfg.camera, _params(cfg, w, h, spp, mb, seed=2))
+    cl = lambda a: np.clip(a, 0.0, 1.0)
+    noise = util.rmse(cl(ref), cl(ref2))
+    g32, s32, f32 = e.render(cfg.camera, _params(cfg, w, h, spp, mb))
+    assert f32 == want_feat
+    assert np.isfinite(g32).all()
+    assert util.rmse(cl(g32), cl(ref)) <= 0.25 * noise
+    assert abs(cl(g32).mean() - cl(ref).mean()) <= 5e-3 * cl(ref).mean()
+    assert 0.85 * st0["segments"] <= s32["segments"] <= st0["segments"]   # zero-weight subtrees are not traced in f32
+
+
+def test_megakernel_counting_variant_and_counters(orc):
+    cfg = scenes.teapot_scene()
+    flat = api.FlatScene(cfg.scene, accel=capi.ACCEL_BVH)
+    e, o = emu.EmuScene(flat), orc.OracleScene(flat)
+    ref, st0 = o.render(cfg.camera, _params(cfg, 48, 27, 4, 2))
+    a, sa, fa = e.render(cfg.camera, _params(cfg, 48, 27, 4, 2, precision=capi.PRECISION_F64, collect_stats=1))
+    np.testing.assert_allclose(a, ref, rtol=1e-12, atol=0)
+    assert fa == 7 | F_GROUP | F_MONO                                    # counting passes run F_EVERY on the kd-trees
+    assert sa["node_visits"] > 0 and sa["tri_tests"] > 0
+    # shadow rays are any-hit queries on the device: never more traversal work than the reference's closest-hit
+    assert sa["node_visits"] <= st0["node_visits"] and sa["tri_tests"] <= st0["tri_tests"]
+    assert sa["object_tests"] == st0["object_tests"] or sa["object_tests"] <= st0["object_tests"]
+    b, sb, fb = e.render(cfg.camera, _params(cfg, 48, 27, 4, 2, collect_stats=1))   # f32 counting pass vs f32 BVH pass
+    c, sc, fc = e.render(cfg.camera, _params(cfg, 48, 27, 4, 2))
+    assert fb == 7 | F_GROUP | F_MONO and fc == F_TREE | 64
+    assert sb["segments"] == sc["segments"] and np.abs(b - c).max() <= 1e-5 * max(1.0, np.abs(b).max())
+
+
+def test_megakernel_chunks_shards_and_sample_ranges(orc):
+    """Sample chunks (iterations > 64: partial sums + resolve), pixel-tile shards and first_sample ranges are
+    bookkeeping around the same per-pixel streams: sums of shards are the image, bit for bit, and the f64 image
+    still equals the oracle's."""
+    cfg = scenes.cornell_scene()
+    flat = api.FlatScene(cfg.scene)
+    e, o = emu.EmuScene(flat), orc.OracleScene(flat)
+    w, h, spp, mb = 20, 12, 150, 3                                           # 3 chunks of 64, ragged tiles
+    ref, _ = o.render(cfg.camera, _params(cfg, w, h, spp, mb))
+    g64, _, _ = e.render(cfg.camera, _params(cfg, w, h, spp, mb, precision=capi.PRECISION_F64))
+    np.testing.assert_allclose(g64, ref, rtol=1e-12, atol=0)
+    full, _, _ = e.render(cfg.camera, _params(cfg, w, h, spp, mb))
+    parts = [e.render(cfg.camera, _params(cfg, w, h, spp, mb, shard_index=i, shard_count=3))[0] for i in range(3)]
+    np.testing.assert_array_equal(parts[0] + parts[1] + parts[2], full)
+    for i in range(3):                                                       # a shard only writes its own tiles
+        own = (np.arange(w * h) % w // 16 + (np.arange(w * h) // w // 8) * ((w + 15) // 16)) % 3 == i
+        assert (parts[i][~own] == 0).all()
+    a, _, _ = e.render(cfg.camera, _params(cfg, w, h, 40, mb, first_sample=0))
+    b, _, _ = e.render(cfg.camera, _params(cfg, w, h, 40, mb, first_sample=40))
+    ab, _, _ = e.render(cfg.camera, _params(cfg, w, h, 80, mb, first_sample=0))
+    assert not np.array_equal(a, b)                                          # disjoint streams ...
+    np.testing.assert_allclose((a + b) / 2, ab, rtol=2e-5, atol=1e-7)        # ... of the same per-sample values
