@@ -306,7 +306,11 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         } else {
             const int rc = ensure_partial(s, a);
             if (rc != RPTB_OK) return rc;
-            CU(launch_render_f32(s->view32, a, p->collect_stats != 0, s->features, stream, launches));
+            // Scenes with kd-trees of shapes: their mesh children go through the BVH only on request
+            // (RPTB_EXT_BVH=1) -- that instantiation is checked in host emulation but has not run on a GPU yet.
+            int feats = s->features;
+            if ((feats & F_EXT) && getenv("RPTB_EXT_BVH") == nullptr) feats &= ~F_BVH;
+            CU(launch_render_f32(s->view32, a, p->collect_stats != 0, feats, stream, launches));
         }
     } else {
         RenderArgs<double> a;

@@ -265,6 +265,12 @@ RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, 
 // in [tmin, h.t), or any hit for a shadow ray -- and the same triangle test (tri48); only the set of
 // triangles a ray has to look at shrinks (dragon proxy: 419 -> ~10 per ray).  Exact ties in t between two
 // triangles (shared edges) may resolve to the other triangle than in the reference's leaf order.
+// 1/x for slab tests written as b * (1/d) - o * (1/d): an exactly zero direction component would make both
+// products infinite and their difference NaN, and fminf/fmaxf over ONE NaN plane silently shrink the interval
+// (a box the ray is inside of gets culled).  A component of magnitude < 1e-30 is treated as +-1e-30: every
+// product stays finite, and the error this makes in t is far below the padding of the boxes.
+RPTB_D float slab_rcp(float x) { return M<float>::rcp(fabsf(x) < 1e-30f ? copysignf(1e-30f, x) : x); }
+
 RPTB_D BvhNodeDev load_bvh_node(const BvhNodeDev* p) {
     BvhNodeDev n;
     const float4* q = reinterpret_cast<const float4*>(p);
@@ -280,7 +286,7 @@ RPTB_D BvhNodeDev load_bvh_node(const BvhNodeDev* p) {
 template <bool STATS>
 RPTB_D bool bvh_intersect(const MeshRec<float>& m, Vec3<float> o, Vec3<float> d, float tmin, bool any, Hit<float>& h,
                           TravStats& ts) {
-    const Vec3<float> inv = {M<float>::rcp(d.x), M<float>::rcp(d.y), M<float>::rcp(d.z)};
+    const Vec3<float> inv = {slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z)};
     // o * inv per axis, so that a slab is one FMA: (b - o) * inv = b * inv - o * inv
     const Vec3<float> oi = {o.x * inv.x, o.y * inv.y, o.z * inv.z};
     int32_t stack[BVH_STACK];
@@ -540,7 +546,7 @@ RPTB_D bool group_intersect(const SceneView<R>& sv, const GroupRec<R>& g, Vec3<R
     constexpr int CHILD = FEAT & ~F_GROUP;  // children are never groups
     R lo, hi;
     Vec3<R> inv = {(R)0, (R)0, (R)0};
-    if (!M<R>::literal) inv = {M<R>::rcp(d.x), M<R>::rcp(d.y), M<R>::rcp(d.z)};
+    if constexpr (!M<R>::literal) inv = {slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z)};  // for the child-box cull below
     {  // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
         const R x1 = (g.bmin[0] - o.x) / d.x, x2 = (g.bmax[0] - o.x) / d.x;
         const R y1 = (g.bmin[1] - o.y) / d.y, y2 = (g.bmax[1] - o.y) / d.y;

@@ -25,6 +25,7 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             // the variants tuned for the BASELINE scenes carry none of that code
             const bool ext = (features & F_EXT) != 0;
             if (stats) render_kernel<R, 16, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            else if (!M<R>::literal && ext && (features & F_BVH)) render_kernel<R, 16, false, F_EVERY | F_BVH><<<grid, block, 0, stream>>>(sv, args);
             else if (ext) render_kernel<R, 16, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
             else if constexpr (M<R>::literal) render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);  // the f64 gate is not specialised
             else if ((features & F_BVH) && base == F_TREE) render_kernel<R, 16, false, F_TREE | F_BVH><<<grid, block, 0, stream>>>(sv, args);

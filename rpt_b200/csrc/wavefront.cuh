@@ -534,7 +534,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kern
                     node = 0; lo = l0; hi = h0; sp = 0;
                     if (BVH) {
                         cur = 0;
-                        oinv = {o.x * iv.x, o.y * iv.y, o.z * iv.z};
+                        inv = {slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z)};  // finite even for a zero component (geometry.cuh)
+                        oinv = {o.x * inv.x, o.y * inv.y, o.z * inv.z};
                     }
                     mesh_hit = false;
                     trav = true;

@@ -27,7 +27,8 @@ def lib():
         L.hostemu_scene_features.argtypes = [C.c_void_p]
         L.hostemu_closest_hit.argtypes = [C.c_void_p, dp, C.c_uint64, C.c_double, C.c_uint32, dp, capi.c_i32_p, dp,
                                           C.POINTER(capi.Stats)]
-        L.hostemu_render.argtypes = [C.c_void_p, C.POINTER(capi.Camera), C.POINTER(capi.RenderParams), dp, C.POINTER(capi.Stats)]
+        L.hostemu_render.argtypes = [C.c_void_p, C.POINTER(capi.Camera), C.POINTER(capi.RenderParams), C.c_int, dp, C.POINTER(capi.Stats)]
+        L.hostemu_occluded.argtypes = [C.c_void_p, dp, dp, C.c_uint64, C.c_double, C.c_uint32, C.c_int, capi.c_i32_p]
         L.hostemu_bvh_check.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.hostemu_illuminate.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_uint64, C.c_uint32, dp, dp, dp]
         _lib = L
@@ -57,15 +58,24 @@ class EmuScene:
     def features(self) -> int:
         return int(lib().hostemu_scene_features(self.handle))
 
-    def render(self, camera, params):
+    def render(self, camera, params, ext_bvh: bool = False):
         """Renderer::sample through the emulated megakernel -> ((w*h, 3) float64, stats dict, FEAT bits of the variant)."""
         out = np.empty((params.width * params.height, 3))
         st = capi.Stats()
         cam = camera.to_c() if hasattr(camera, "to_c") else camera
-        feat = lib().hostemu_render(self.handle, C.byref(cam), C.byref(params), out.ctypes.data_as(dp), C.byref(st))
+        feat = lib().hostemu_render(self.handle, C.byref(cam), C.byref(params), 1 if ext_bvh else 0, out.ctypes.data_as(dp), C.byref(st))
         if feat < -0:
             raise ValueError("bad render parameters")
         return out, st.as_dict(), int(feat)
+
+    def occluded(self, rays, tmax, t_min=1e-12, precision=capi.PRECISION_F32, use_bvh=True):
+        """Any-hit shadow queries: 1 where something lies in [t_min, tmax) on the ray."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        tmax = np.ascontiguousarray(np.broadcast_to(np.asarray(tmax, dtype=np.float64), (rays.shape[0],)))
+        out = np.empty(rays.shape[0], np.int32)
+        lib().hostemu_occluded(self.handle, rays.ctypes.data_as(dp), tmax.ctypes.data_as(dp), rays.shape[0], t_min, precision,
+                               1 if use_bvh else 0, out.ctypes.data_as(capi.c_i32_p))
+        return out
 
     def bvh_check(self, mesh: int = 0):
         """{nodes, leaves, max_leaf, depth, distinct, violations} of the BVH of mesh `mesh`, or None if it has none."""

@@ -38,6 +38,21 @@ struct InPlace {
     uint64_t bytes() const { return total; }
 };
 
+// Shadow queries as sample_lights issues them (renderer.rs:190-197 through the megakernel's any-hit path):
+// out[i] = 1 if something lies on ray i at t in [tmin, tmax[i]), found with `any` = true.
+template <class R, int FEAT>
+void occluded(const SceneView<R>& sv, const double* rays, const double* tmax, uint64_t n, double tmin, int32_t* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const double* r = rays + 6 * i;
+        TravStats ts = {0, 0, 0};
+        Hit<R> h;
+        h.t = (R)tmax[i];
+        closest_hit<R, false, FEAT>(sv, mk((R)r[0], (R)r[1], (R)r[2]), mk((R)r[3], (R)r[4], (R)r[5]), (R)tmin, true, h, ts);
+        out[i] = h.obj >= 0 ? 1 : 0;
+    }
+}
+
 template <class R, int FEAT>
 void closest_hits(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin, double* out_t, int32_t* out_obj,
                   double* out_n, rptb_stats* stats) {
@@ -133,6 +148,8 @@ int run_render(const SceneView<R>& sv, const RenderArgs<R>& a, bool stats, int f
         return F_EVERY;
     }
     if (stats) { run_grid<R, 16, true, F_EVERY>(sv, a); return F_EVERY; }
+    if constexpr (!M<R>::literal)
+        if (ext && (features & F_BVH)) { run_grid<R, 16, false, F_EVERY | F_BVH>(sv, a); return F_EVERY | F_BVH; }
     if (ext) { run_grid<R, 16, false, F_EVERY>(sv, a); return F_EVERY; }
     if constexpr (M<R>::literal) {
         run_grid<R, 16, false, F_ALL>(sv, a);
@@ -230,12 +247,16 @@ int hostemu_closest_hit(const hostemu_scene* s, const double* rays, uint64_t n, 
 // its parent stores for its leaf, a child box that sticks out of its parent's, or a malformed leaf code.
 // Renderer::sample through the megakernel's thread body (every lane run on its own; see HostLane).  Same contract
 // as rptb_render_samples; returns the FEAT bits of the kernel instantiation that was emulated, or -1 on bad params.
-int hostemu_render(const hostemu_scene* s, const rptb_camera* cam, const rptb_render_params* p, double* out_rgb, rptb_stats* stats) {
+// ext_bvh: what RPTB_EXT_BVH=1 asks of the library (mesh children of kd-trees of shapes through their BVH).
+int hostemu_render(const hostemu_scene* s, const rptb_camera* cam, const rptb_render_params* p, int ext_bvh, double* out_rgb,
+                   rptb_stats* stats) {
     if (!s || !cam || !p || !out_rgb || p->width == 0 || p->height == 0 || p->iterations == 0 ||
         p->max_bounces > MAX_BOUNCES_SUPPORTED)
         return -1;
     if (p->precision == RPTB_PRECISION_F64) return render_impl<double>(s->v64, cam, p, F_ALL | (s->features & F_EXT), out_rgb, stats);
-    return render_impl<float>(s->v32, cam, p, s->features, out_rgb, stats);
+    int feats = s->features;
+    if ((feats & F_EXT) && !ext_bvh) feats &= ~F_BVH;
+    return render_impl<float>(s->v32, cam, p, feats, out_rgb, stats);
 }
 
 int hostemu_bvh_check(const hostemu_scene* s, uint32_t mesh, uint64_t* out) {
@@ -298,6 +319,15 @@ int hostemu_bvh_check(const hostemu_scene* s, uint32_t mesh, uint64_t* out) {
         if (c > 1) violations++;  // every triangle in exactly one leaf
     }
     out[0] = hm.bvh_nodes.size(); out[1] = leaves; out[2] = max_leaf; out[3] = depth; out[4] = distinct; out[5] = violations;
+    return 0;
+}
+
+// precision as above; use_bvh: take the BVH where the scene has one (f32 only)
+int hostemu_occluded(const hostemu_scene* s, const double* rays, const double* tmax, uint64_t n, double t_min, uint32_t precision,
+                     int use_bvh, int32_t* out) {
+    if (precision == RPTB_PRECISION_F64) occluded<double, F_EVERY>(s->v64, rays, tmax, n, t_min, out);
+    else if (use_bvh && (s->features & F_BVH)) occluded<float, F_EVERY | F_BVH>(s->v32, rays, tmax, n, t_min, out);
+    else occluded<float, F_EVERY>(s->v32, rays, tmax, n, t_min, out);
     return 0;
 }
 

@@ -126,3 +126,29 @@ def test_bvh_device_bytes_and_env_override(pairs, monkeypatch):
     monkeypatch.setenv("RPTB_ACCEL", "kdtree")
     with api.DeviceScene(api.FlatScene(cfg.scene)) as ds:
         assert ds.device_bytes() == kd.device_bytes()
+
+
+def test_bvh_axis_aligned_directional_light(gpu_ok):
+    """A Directional light along an axis gives every shadow ray an exactly zero direction component -- the case
+    slab_rcp (geometry.cuh) exists for: the BVH must cast the teapot's shadow exactly where the kd-tree does."""
+    cfg = scenes.teapot_scene()
+    scene = api.Scene()
+    for o in cfg.scene.objects:
+        scene.add(o)
+    scene.add(api.Light.Directional(api.vec3(0.9, 0.9, 0.9), api.vec3(0.0, -1.0, 0.0)))
+    scene.add(api.Light.Directional(api.vec3(0.2, 0.1, 0.1), api.vec3(1.0, 0.0, 0.0)))
+    camera = api.Camera.look_at(api.vec3(0.0, 6.0, 0.001), api.vec3(0.0, -1.0, 0.0), api.vec3(0.0, 0.0, -1.0), 0.8)
+    w, h, spp = 128, 96, 4
+    imgs = {}
+    for accel in (capi.ACCEL_KDTREE, capi.ACCEL_BVH):
+        with api.DeviceScene(api.FlatScene(scene, accel=accel)) as ds:
+            cfg2 = scenes.Config("teapot_dir", scene, camera, w, h, spp, 0)
+            imgs[accel], st = _render(cfg2, ds, w, h, spp, 0, 2, capi.ENGINE_MEGAKERNEL)
+            imgs[(accel, "wf")], _ = _render(cfg2, ds, w, h, spp, 0, 2, capi.ENGINE_WAVEFRONT)
+    a, b = imgs[capi.ACCEL_KDTREE], imgs[capi.ACCEL_BVH]
+    rel = np.abs(a - b).max(axis=1) / np.maximum(np.abs(a).max(axis=1), 1e-6)
+    assert (rel <= 1e-5).mean() >= 0.999, (rel <= 1e-5).mean()
+    lum = a.sum(axis=1)
+    assert (lum < 0.25 * np.median(lum)).mean() > 0.02          # there is a shadow to get wrong
+    rel = np.abs(imgs[(capi.ACCEL_KDTREE, "wf")] - imgs[(capi.ACCEL_BVH, "wf")]).max(axis=1) / np.maximum(np.abs(a).max(axis=1), 1e-6)
+    assert (rel <= 1e-5).mean() >= 0.999

@@ -7,6 +7,8 @@ host and runs them over the arrays rptb_scene_create would upload.  With Real = 
 the oracle's, so hits, normals and traversal counters must agree exactly; with Real = float within the
 f32 tolerances the GPU parity tests use.  This is test infrastructure (it cannot say anything about the
 kernels' scheduling or fast-math); the `-m gpu` tests through the C ABI remain the gate."""
+import math
+
 import numpy as np
 import pytest
 
@@ -320,3 +322,89 @@ def test_megakernel_chunks_shards_and_sample_ranges(orc):
     ab, _, _ = e.render(cfg.camera, _params(cfg, w, h, 80, mb, first_sample=0))
     assert not np.array_equal(a, b)                                          # disjoint streams ...
     np.testing.assert_allclose((a + b) / 2, ab, rtol=2e-5, atol=1e-7)        # ... of the same per-sample values
+
+
+def test_megakernel_corner_cases_equal_the_oracle(orc):
+    """Corners of Renderer::sample the BASELINE scenes do not touch, each through the emulated megakernel in f64
+    (exactly the oracle) and f32 (finite, within noise): thin-lens camera (aperture > 0), exposure value,
+    a directional light, an emissive object seen directly, a scene with no lights, one with no objects, and
+    max_bounces > 16 (the MAXD = 64 instantiation)."""
+    def check(scene, camera, w, h, spp, mb, ev=0.0):
+        flat = api.FlatScene(scene)
+        e, o = emu.EmuScene(flat), orc.OracleScene(flat)
+        r = api.Renderer(scene, camera).width(w).height(h).max_bounces(mb).seed(4).exposure_value(ev)
+        ref, st0 = o.render(camera, r.params(spp))
+        g64, s64, _ = e.render(camera, r.precision(capi.PRECISION_F64).params(spp))
+        np.testing.assert_allclose(g64, ref, rtol=1e-12, atol=0)
+        assert (s64["segments"], s64["rays"]) == (st0["segments"], st0["rays"])
+        g32, s32, _ = e.render(camera, r.precision(capi.PRECISION_F32).params(spp))
+        assert np.isfinite(g32).all()
+        scale = max(1e-3, float(np.abs(ref).mean()))
+        assert abs(g32.mean() - ref.mean()) <= 0.02 * scale + 1e-6
+        return ref
+
+    base = scenes.sphere_scene()
+    cam = api.Camera.look_at(api.vec3(-2.5, 4.0, 6.5), api.vec3(0.0, -0.25, 0.0), api.vec3(0.0, 1.0, 0.0), math.pi / 4)
+    a = check(base.scene, cam.focus(api.vec3(0.0, 0.0, 0.0), 0.15), 32, 18, 8, 2)           # depth of field
+    b = check(base.scene, api.Camera.look_at(api.vec3(-2.5, 4.0, 6.5), api.vec3(0.0, -0.25, 0.0), api.vec3(0.0, 1.0, 0.0), math.pi / 4),
+              32, 18, 8, 2, ev=1.5)                                                       # 2^1.5 brighter
+    assert b.mean() > 2.0 * a.mean() * 0.8
+    scene = api.Scene()                                                                     # directional + ambient, emissive sphere in view
+    scene.add(api.Object(api.sphere()).material(api.Material.light(api.hex_color(0xFFAA33), 3.0)))
+    scene.add(api.Object(api.plane(api.vec3(0.0, 1.0, 0.0), -1.0)).material(api.Material.diffuse(api.hex_color(0x8888FF))))
+    scene.add(api.Light.Directional(api.vec3(0.8, 0.8, 0.8), api.vec3(0.3, -1.0, -0.2)))
+    scene.add(api.Light.Ambient(api.vec3(0.05, 0.05, 0.05)))
+    check(scene, cam, 32, 18, 8, 3)
+    nolight = api.Scene()                                                                   # no lights: environment only
+    nolight.environment = api.Environment.Color(api.vec3(0.2, 0.4, 0.8))
+    nolight.add(api.Object(api.sphere()).material(api.Material.metallic_(api.hex_color(0xFFFFFF), 0.2)))
+    check(nolight, api.Camera.default(), 24, 16, 8, 4)
+    empty = api.Scene()                                                                     # nothing at all: every path escapes
+    empty.environment = api.Environment.Color(api.vec3(0.1, 0.2, 0.3))
+    img = check(empty, api.Camera.default(), 16, 8, 2, 2)
+    np.testing.assert_allclose(img, np.tile([0.1, 0.2, 0.3], (16 * 8, 1)), rtol=1e-15)
+    glass = scenes.glass_scene(32, 16)                                                      # 40 bounces: MAXD = 64 kernels
+    check(glass.scene, glass.camera, 24, 14, 4, 40)
+
+
+def test_megakernel_kd_tree_of_shapes_over_bvh_meshes(orc):
+    """RPTB_EXT_BVH=1 (opt-in until it has run on a GPU): render_kernel<F_EVERY | F_BVH>, the instances of
+    examples/fractal_teapots entered through the group's kd-tree and traversed through the shared teapot's BVH.
+    Emulated: same image as through the kd-tree."""
+    cfg = scenes.fractal_teapots_scene(3)
+    e = emu.EmuScene(api.FlatScene(cfg.scene, accel=capi.ACCEL_BVH))
+    p = _params(cfg, 48, 36, 4, 1)
+    a, sa, fa = e.render(cfg.camera, p)
+    b, sb, fb = e.render(cfg.camera, p, ext_bvh=True)
+    assert fa == 7 | F_GROUP | F_MONO and fb == 7 | F_GROUP | F_MONO | 64
+    assert (sa["segments"], sa["rays"]) == (sb["segments"], sb["rays"])
+    assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(a).max())
+
+
+@pytest.mark.parametrize("name", ["teapot", "fractal_teapots"])
+def test_bvh_with_exactly_zero_direction_components(orc, name):
+    """Axis-aligned rays (a Directional light along an axis, an orthogonal view): 1/d is infinite for the zero
+    components.  A slab test written as b/d - o/d then produces NaN for ONE plane of a box the ray is inside of,
+    and min/max over a single NaN shrink the interval -- the BVH lost about half of the occluders of
+    examples/fractal_teapots' directional light (0, -0.65, -1) before slab_rcp.  Any-hit and closest-hit queries
+    through the BVH must equal those through the kd-tree, and the f64 gate."""
+    cfg = scenes.teapot_scene() if name == "teapot" else scenes.fractal_teapots_scene(3)
+    flat = api.FlatScene(cfg.scene, accel=capi.ACCEL_BVH)
+    e, o = emu.EmuScene(flat), orc.OracleScene(flat)
+    rng = np.random.default_rng(6)
+    n = 20000
+    for axis_dir in ([0.0, 0.65, 1.0], [0.0, 0.0, 1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [-1.0, 0.0, 0.0], [0.3, 0.0, -1.0]):
+        d = np.asarray(axis_dir) / np.linalg.norm(axis_dir)
+        # origins on a plane behind the scene, perpendicular-ish to d
+        u = rng.uniform(-2.5, 2.5, (n, 3))
+        org = u - (u @ d)[:, None] * d - 6.0 * d
+        rays = np.concatenate([org, np.tile(d, (n, 1))], axis=1)
+        kd = e.occluded(rays, np.inf, use_bvh=False)
+        bvh = e.occluded(rays, np.inf, use_bvh=True)
+        gate = e.occluded(rays, np.inf, precision=capi.PRECISION_F64)
+        assert (kd != bvh).mean() <= 2e-4 and (bvh != gate).mean() <= 5e-4, axis_dir   # silhouette-grazing rays only
+        assert bvh.mean() > 0.01
+        tb, ob, _, _ = e.closest_hit(rays, precision=capi.PRECISION_F32)
+        t0, o0, _, _ = o.closest_hit(rays)
+        assert (ob == o0).mean() >= 0.9995
+        assert ((ob >= 0) == (bvh == 1)).mean() >= 0.9995                             # any-hit agrees with closest-hit
