@@ -234,8 +234,8 @@ typedef struct rptb_render_params {
 typedef struct rptb_stats {
     uint64_t segments;    /* trace_ray invocations (src/renderer.rs:145)       */
     uint64_t rays;        /* get_closest_hit calls incl. shadow rays (:211)    */
-    uint64_t node_visits; /* kd nodes visited (src/kdtree.rs:151), if collected */
-    uint64_t tri_tests;   /* Triangle::intersect calls (mesh.rs:49), if collected */
+    uint64_t node_visits; /* kd nodes visited (src/kdtree.rs:151), if collected: counted on the reference-shaped */
+    uint64_t tri_tests;   /* trees (a counting pass never takes the BVH); Triangle::intersect calls (mesh.rs:49) */
     uint64_t mesh_hits;   /* closest hits that landed on a mesh                */
     uint64_t env_lookups; /* escaped paths that sampled an HDRI                */
     uint64_t object_tests;/* Shape::intersect dispatches (objects tested per ray, summed) */
