@@ -44,6 +44,7 @@ def parse_args():
                              "fractal_spheres", "fractal_teapots", "monomial_glass"],  # the last three: exploration only
                     help="default = the BASELINE configs[1] workload; anything else is for exploration / profiling")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (exploration only)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "megakernel", "wavefront"], help="rptb_engine (exploration only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -280,7 +281,7 @@ def run_native(args):
     cfg = workload(args.workload, args.spp)
     spp_total = cfg.spp * world
     r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces) \
-        .seed(1).device(local)
+        .seed(1).device(local).engine({"auto": capi.ENGINE_AUTO, "megakernel": capi.ENGINE_MEGAKERNEL, "wavefront": capi.ENGINE_WAVEFRONT}[args.engine])
     flat = api.FlatScene(cfg.scene)
     npix = cfg.width * cfg.height
     stream = torch.cuda.Stream(dev)

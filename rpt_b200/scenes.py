@@ -5,7 +5,8 @@ BASELINE.json; where it is silent, from the example file.
     sphere   examples/sphere.rs:4-34
     cornell  examples/cornell.rs:14-88
     teapot   examples/teapot.rs:10-34
-    dragon   examples/dragon.rs:32-75   (mesh: procedural stand-in, see dragon_proxy)
+    dragon   examples/dragon.rs:32-75   (mesh: examples/pegasus.zip subdivided to 801 104 triangles, see
+                                         pegasus_proxy; `dragon-knot` keeps round 1's procedural tube as a second case)
     glass    examples/glass.rs:27-49    (HDRI: synthetic stand-in, see synthetic_hdri)
 
 and, for the two-level kd-trees and the MonomialSurface, not BASELINE configs:
@@ -103,12 +104,83 @@ def teapot_scene() -> Config:
                   "examples/teapot.rs; teapot.obj has 2256 triangles; max_bounces 0 is the example's default")
 
 
-def dragon_proxy(n_u: int = 1320, n_v: int = 330, seed: int = 7) -> np.ndarray:
-    """A closed, bumpy (2,3) torus-knot tube with n_u*n_v*2 triangles (871 200 by default,
-    the Stanford dragon has 871 414), smooth vertex normals, scaled into the dragon's
-    bounding box so that `scale 3.4` rests it on the plane y = -1 like examples/dragon.rs.
-    The real dragon.obj is an HTTP download in the reference (examples/dragon.rs:11-14)
-    and is not available offline; every table labels this mesh "dragon-proxy"."""
+def pegasus_indexed():
+    """examples/pegasus.zip as parsed by load_obj (tools/make_assets.py): vertices, vertex normals, faces."""
+    z = np.load(os.path.join(_ASSETS, "pegasus_indexed.npz"))
+    return z["verts"], z["norms"], z["faces"]
+
+
+def _unit(n: np.ndarray) -> np.ndarray:
+    """normalize rows; a zero row (pegasus.obj has a few zero vertex normals) stays zero"""
+    l = np.linalg.norm(n, axis=1, keepdims=True)
+    return np.divide(n, l, out=np.zeros_like(n), where=l > 0)
+
+
+def subdivide4(v: np.ndarray, n: np.ndarray, f: np.ndarray, alpha: float = 0.75):
+    """1 -> 4: a vertex on every edge (shared by the two faces of the edge, so the mesh stays closed), moved off
+    the flat midpoint by Phong tessellation -- the mean of its projections onto the tangent planes of the edge's
+    two ends, blended in by `alpha` -- so the finer mesh is a smoother surface, not four coplanar pieces."""
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    key = np.sort(e, axis=1).astype(np.int64)
+    uniq, inv = np.unique(key[:, 0] * len(v) + key[:, 1], return_inverse=True)
+    a, b = (uniq // len(v)).astype(np.int64), (uniq % len(v)).astype(np.int64)
+    m = 0.5 * (v[a] + v[b])
+    na, nb = _unit(n[a]), _unit(n[b])
+    pa = m - np.sum((m - v[a]) * na, axis=1, keepdims=True) * na
+    pb = m - np.sum((m - v[b]) * nb, axis=1, keepdims=True) * nb
+    mid = (1.0 - alpha) * m + alpha * 0.5 * (pa + pb)
+    v2 = np.concatenate([v, mid])
+    n2 = np.concatenate([n, _unit(na + nb)])
+    nf = len(f)
+    m01, m12, m20 = (len(v) + inv[0:nf]), (len(v) + inv[nf:2 * nf]), (len(v) + inv[2 * nf:3 * nf])
+    i0, i1, i2 = f[:, 0].astype(np.int64), f[:, 1].astype(np.int64), f[:, 2].astype(np.int64)
+    f2 = np.stack([np.stack([i0, m01, m20], 1), np.stack([m01, i1, m12], 1), np.stack([m20, m12, i2], 1),
+                   np.stack([m01, m12, m20], 1)], axis=1).reshape(-1, 3)
+    return v2, n2, f2
+
+
+def subdivide2(v: np.ndarray, n: np.ndarray, f: np.ndarray) -> np.ndarray:
+    """1 -> 2: every triangle is cut from the (linear) midpoint of its longest edge to the opposite corner.
+    Returns (2 * len(f), 18) rows v1 v2 v3 n1 n2 n3, the input of Mesh::new."""
+    p = v[f]  # (F, 3, 3)
+    q = n[f]
+    l = np.stack([np.sum((p[:, 1] - p[:, 0]) ** 2, 1), np.sum((p[:, 2] - p[:, 1]) ** 2, 1), np.sum((p[:, 0] - p[:, 2]) ** 2, 1)], 1)
+    k = np.argmax(l, axis=1)  # edge k joins corner k and k + 1
+    r = np.arange(len(f))
+    ia, ib, ic = k, (k + 1) % 3, (k + 2) % 3
+    A, B, Cc = p[r, ia], p[r, ib], p[r, ic]
+    nA, nB, nC = q[r, ia], q[r, ib], q[r, ic]
+    Mid = 0.5 * (A + B)
+    nM = _unit(_unit(nA) + _unit(nB))
+    t1 = np.concatenate([A, Mid, Cc, nA, nM, nC], axis=1)  # (a, m, c) and (m, b, c): the winding of (a, b, c)
+    t2 = np.concatenate([Mid, B, Cc, nM, nB, nC], axis=1)
+    return np.ascontiguousarray(np.stack([t1, t2], axis=1).reshape(-1, 18))
+
+
+def pegasus_proxy(level: int = 2) -> np.ndarray:
+    """The offline stand-in SURVEY 8(d) fixes for the Stanford dragon (an HTTP download in the reference,
+    examples/dragon.rs:11-14; 871 414 triangles): the scanned statue of examples/pegasus.zip (100 138 triangles,
+    edge lengths 4e-4 .. 6e-2: thin legs and wings, concavities) subdivided 1 -> 4 then 1 -> 2 = 801 104
+    triangles, and put where the G3D dragon.obj sits -- longest dimension 0.7, centred in x and z, resting on
+    y = -1/3.4 so that examples/dragon.rs's `scale 3.4` stands it on the plane y = -1.  Every table labels
+    it "dragon-proxy".  level 0 = the 100 138 original triangles, 1 = 400 552, 2 = 801 104."""
+    v, n, f = pegasus_indexed()
+    lo, hi = v.min(0), v.max(0)
+    s = 0.7 / float((hi - lo).max())
+    c = 0.5 * (lo + hi)
+    v = (v - np.array([c[0], lo[1], c[2]])) * s
+    v[:, 1] += -1.0 / 3.4
+    if level >= 1:
+        v, n, f = subdivide4(v, n, f)
+    if level >= 2:
+        return subdivide2(v, n, f)
+    return np.ascontiguousarray(np.concatenate([v[f].reshape(-1, 9), n[f].reshape(-1, 9)], axis=1))
+
+
+def knot_proxy(n_u: int = 1320, n_v: int = 330, seed: int = 7) -> np.ndarray:
+    """Round 1's stand-in, kept as a second case: a closed, bumpy (2,3) torus-knot tube with n_u*n_v*2
+    triangles (871 200 by default), smooth vertex normals, scaled into the dragon's bounding box.  Uniform
+    triangle size, no thin features: the easiest input a mesh of that size can be for a kd-tree or a BVH."""
     rng = np.random.default_rng(seed)
     u = np.linspace(0.0, 2.0 * np.pi, n_u, endpoint=False)
     v = np.linspace(0.0, 2.0 * np.pi, n_v, endpoint=False)
@@ -161,21 +233,22 @@ def dragon_proxy(n_u: int = 1320, n_v: int = 330, seed: int = 7) -> np.ndarray:
 _DRAGON_CACHE = {}
 
 
-def dragon_mesh(n_u: int = 1320, n_v: int = 330) -> Mesh:
-    key = (n_u, n_v)
+def dragon_mesh(level: int = 2, knot=None) -> Mesh:
+    """knot = (n_u, n_v) selects round 1's procedural tube instead of the pegasus-derived mesh"""
+    key = ("knot",) + tuple(knot) if knot else ("pegasus", level)
     if key not in _DRAGON_CACHE:
         path = os.environ.get("RPT_DRAGON_OBJ")
-        if path and os.path.exists(path):
+        if path and os.path.exists(path) and not knot:
             from .api import load_obj
             _DRAGON_CACHE[key] = load_obj(path)
         else:
-            _DRAGON_CACHE[key] = Mesh(dragon_proxy(n_u, n_v))
+            _DRAGON_CACHE[key] = Mesh(knot_proxy(*knot) if knot else pegasus_proxy(level))
     return _DRAGON_CACHE[key]
 
 
-def dragon_scene(n_u: int = 1320, n_v: int = 330) -> Config:
+def dragon_scene(level: int = 2, knot=None) -> Config:
     scene = Scene()
-    dragon = dragon_mesh(n_u, n_v)
+    dragon = dragon_mesh(level, knot)
     scene.add(Object(dragon.scale(vec3(3.4, 3.4, 3.4)).rotate_y(math.pi / 2))
               .material(Material.specular(hex_color(0xB7CA79), 0.1)))
     scene.add(Object(plane(vec3(0.0, 1.0, 0.0), -1.0)).material(Material.diffuse(hex_color(0xAAAAAA))))
@@ -185,9 +258,14 @@ def dragon_scene(n_u: int = 1320, n_v: int = 330) -> Config:
     scene.add(Light.Object(Object(sphere().scale(vec3(0.05, 0.05, 0.05)).translate(vec3(-1.0, 0.71, 0.0)))
                            .material(Material.light(hex_color(0xFFAAAA), 400.0))))
     camera = Camera.look_at(vec3(-2.5, 4.0, 6.5), vec3(0.0, 0.0, 0.0), vec3(0.0, 1.0, 0.0), math.pi / 6)
-    real = bool(os.environ.get("RPT_DRAGON_OBJ"))
-    return Config("dragon" if real else "dragon-proxy", scene, camera, 1920, 1080, 1024, 2,
-                  "examples/dragon.rs layout; mesh = %s (%d triangles)" % ("dragon.obj" if real else "procedural proxy", len(dragon)))
+    real = bool(os.environ.get("RPT_DRAGON_OBJ")) and not knot
+    name = "dragon" if real else "dragon-knot" if knot else "dragon-proxy"
+    mesh = "dragon.obj" if real else "procedural torus-knot tube" if knot else "examples/pegasus.zip subdivided (level %d)" % level
+    return Config(name, scene, camera, 1920, 1080, 1024, 2, "examples/dragon.rs layout; mesh = %s (%d triangles)" % (mesh, len(dragon)))
+
+
+def dragon_knot_scene(n_u: int = 1320, n_v: int = 330) -> Config:
+    return dragon_scene(knot=(n_u, n_v))
 
 
 def synthetic_hdri(width: int = 2048, height: int = 1024, seed: int = 11) -> Hdri:
@@ -298,6 +376,7 @@ EXTRA_CONFIGS = {
     "fractal_spheres": fractal_spheres_scene,
     "fractal_teapots": fractal_teapots_scene,
     "monomial_glass": monomial_glass_scene,
+    "dragon_knot": dragon_knot_scene,
 }
 
 CONFIGS = {

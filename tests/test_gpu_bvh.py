@@ -23,7 +23,7 @@ def pairs(gpu_ok):
 
     def get(name):
         if name not in cache:
-            cfg = scenes.teapot_scene() if name == "teapot" else scenes.dragon_scene(660, 165)
+            cfg = scenes.teapot_scene() if name == "teapot" else scenes.dragon_scene(level=0)
             kd = api.DeviceScene(api.FlatScene(cfg.scene, accel=capi.ACCEL_KDTREE))
             bvh = api.DeviceScene(api.FlatScene(cfg.scene, accel=capi.ACCEL_BVH))
             cache[name] = (cfg, kd, bvh)

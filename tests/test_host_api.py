@@ -129,8 +129,35 @@ def test_tile_owner_partition():
     assert np.abs(frac - 1 / 8).max() < 0.01  # interleaving balances the shards
 
 
-def test_dragon_proxy_is_closed_and_outward():
-    tris = scenes.dragon_proxy(120, 30)
+def test_pegasus_proxy_is_the_reference_mesh_subdivided():
+    """the dragon stand-in is examples/pegasus.zip (100 138 triangles) subdivided 1 -> 4 -> 2."""
+    v, n, f = scenes.pegasus_indexed()
+    assert v.shape == (50059, 3) and n.shape == (50059, 3) and f.shape == (100138, 3)
+    t0 = scenes.pegasus_proxy(0)
+    assert t0.shape == (100138, 18)
+    assert abs(t0[:, [1, 4, 7]].min() * 3.4 + 1.0) < 1e-9  # rests on the plane y = -1 after scale 3.4
+    ext = t0[:, 0:9].reshape(-1, 3).max(0) - t0[:, 0:9].reshape(-1, 3).min(0)
+    assert abs(ext.max() - 0.7) < 1e-12  # the G3D dragon.obj's longest dimension
+    t1v, t1n, t1f = scenes.subdivide4(*[a.copy() for a in (v, n, f)])
+    assert t1f.shape == (4 * 100138, 3) and len(t1v) == 50059 + 150203  # one new vertex per edge: still an indexed, closed mesh
+    ed = np.sort(np.concatenate([t1f[:, [0, 1]], t1f[:, [1, 2]], t1f[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(ed[:, 0] * len(t1v) + ed[:, 1], return_counts=True)
+    assert (cnt == 2).mean() > 0.9999  # pegasus.obj itself has 4 non-manifold edges
+    # orientation and area survive: face normals of the children agree with the parent's
+    p = v[f]
+    pn = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    c = t1v[t1f].reshape(-1, 4, 3, 3)
+    cn = np.cross(c[:, :, 1] - c[:, :, 0], c[:, :, 2] - c[:, :, 0])
+    assert ((cn * pn[:, None, :]).sum(2) > 0).mean() > 0.995
+    t2 = scenes.subdivide2(t1v, t1n, t1f)
+    assert t2.shape == (801104, 18) and np.isfinite(t2).all()
+    a2 = 0.5 * np.linalg.norm(np.cross(t2[:, 3:6] - t2[:, 0:3], t2[:, 6:9] - t2[:, 0:3]), axis=1)
+    a1 = 0.5 * np.linalg.norm(np.cross(c[:, :, 1] - c[:, :, 0], c[:, :, 2] - c[:, :, 0]), axis=2).reshape(-1)
+    assert np.allclose(a2.reshape(-1, 2).sum(1), a1, rtol=1e-9, atol=1e-18)  # 1 -> 2 cuts, it does not move anything
+
+
+def test_dragon_knot_is_closed_and_outward():
+    tris = scenes.knot_proxy(120, 30)
     assert tris.shape == (120 * 30 * 2, 18)
     v1, v2, v3 = tris[:, 0:3], tris[:, 3:6], tris[:, 6:9]
     fn = np.cross(v2 - v1, v3 - v1)

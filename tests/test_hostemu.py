@@ -133,12 +133,12 @@ def _bvh_pair(scene):
     return (emu.EmuScene(api.FlatScene(scene, accel=capi.ACCEL_BVH)), emu.EmuScene(api.FlatScene(scene, accel=capi.ACCEL_KDTREE)))
 
 
-@pytest.mark.parametrize("name", ["teapot", "dragon_small"])
+@pytest.mark.parametrize("name", ["teapot", "dragon_small", "pegasus"])
 def test_bvh_finds_the_hits_of_the_reference_tree(orc, name):
     """rptb_accel BVH (bvhbuild.cpp + bvh_intersect): a different structure over the same triangles and the same
     triangle test -> the f32 hits are those of the kd-tree traversal, to the bit (ties on shared edges aside),
     for a fraction of the node visits and triangle tests."""
-    cfg = scenes.teapot_scene() if name == "teapot" else scenes.dragon_scene(330, 82)
+    cfg = scenes.teapot_scene() if name == "teapot" else scenes.dragon_knot_scene(330, 82) if name == "dragon_small" else scenes.dragon_scene(level=0)
     eb, ek = _bvh_pair(cfg.scene)
     assert (eb.features & 64) and not (ek.features & 64)
     chk = eb.bvh_check(0)
