@@ -143,6 +143,7 @@ def algorithmic_bytes(stats: dict, pixels: int) -> float:
     material per segment (<= one fetch), 64 B (4 texels x 16 B) per HDRI lookup, 12 B per
     pixel written."""
     return (64.0 * stats["object_tests"] + 8.0 * stats["node_visits"] + 52.0 * stats["tri_tests"]
+            + 64.0 * stats.get("bvh_node_visits", 0) + 52.0 * stats.get("bvh_tri_tests", 0)
             + 36.0 * stats["mesh_hits"] + 32.0 * stats["segments"] + 64.0 * stats["env_lookups"] + 12.0 * pixels)
 
 
@@ -307,7 +308,8 @@ def run_native(args):
         st = capi.Stats()
         render_shard_device(r, spp_total, out, rank, world, 0, raw, stats=st, collect_stats=1)
         mine = st.as_dict()
-        keys = ["segments", "rays", "node_visits", "tri_tests", "mesh_hits", "env_lookups", "object_tests"]
+        keys = ["segments", "rays", "node_visits", "tri_tests", "mesh_hits", "env_lookups", "object_tests",
+                "bvh_node_visits", "bvh_tri_tests"]
         tot = torch.tensor([mine[k] for k in keys], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
@@ -418,7 +420,7 @@ def run_native(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(cfg.name, spp_total, engine), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_all / world,
-                "bytes_model": "64*object_tests + 8*node_visits + 52*tri_tests + 36*mesh_hits + 32*segments + 64*env_lookups + 12*pixels",
+                "bytes_model": "64*object_tests + 8*node_visits + 52*tri_tests + 64*bvh_node_visits + 52*bvh_tri_tests + 36*mesh_hits + 32*segments + 64*env_lookups + 12*pixels (counters of the structure that rendered the step)",
                 "counters_per_step": total,
                 "secondary": issue,
             },

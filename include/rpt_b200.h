@@ -226,7 +226,10 @@ typedef struct rptb_render_params {
     uint32_t shard_index; /* this process renders pixel tiles t with      */
     uint32_t shard_count; /* t % shard_count == shard_index; others stay 0 */
     uint32_t precision;   /* rptb_precision */
-    uint32_t collect_stats; /* 0 = segments only; 1 = + node visits / tri tests */
+    uint32_t collect_stats; /* 0 = segments / rays only; 1 = + traversal counters of the structure that rendered the image
+                               (the f32 path's BVH -> bvh_node_visits / bvh_tri_tests; a kd-tree scene or the f64 gate ->
+                               node_visits / tri_tests); 2 = a counting pass over the reference-shaped kd-trees whatever
+                               the scene was created with (SURVEY 8d's algorithmic work) */
     uint32_t engine;      /* rptb_engine: 0 = pick by scene                   */
     uint32_t _pad;
 } rptb_render_params;
@@ -234,14 +237,16 @@ typedef struct rptb_render_params {
 typedef struct rptb_stats {
     uint64_t segments;    /* trace_ray invocations (src/renderer.rs:145)       */
     uint64_t rays;        /* get_closest_hit calls incl. shadow rays (:211)    */
-    uint64_t node_visits; /* kd nodes visited (src/kdtree.rs:151), if collected: counted on the reference-shaped */
-    uint64_t tri_tests;   /* trees (a counting pass never takes the BVH); Triangle::intersect calls (mesh.rs:49) */
+    uint64_t node_visits; /* kd nodes visited (src/kdtree.rs:151) and Triangle::intersect calls (mesh.rs:49) on the      */
+    uint64_t tri_tests;   /* reference-shaped trees, when those were walked (collect_stats above)                         */
     uint64_t mesh_hits;   /* closest hits that landed on a mesh                */
     uint64_t env_lookups; /* escaped paths that sampled an HDRI                */
     uint64_t object_tests;/* Shape::intersect dispatches (objects tested per ray, summed) */
     double gpu_ms;        /* device time of the render launch(es)              */
     uint32_t launches;    /* kernels launched by the call                      */
     uint32_t engine;      /* rptb_engine that rendered the call (1 or 2)       */
+    uint64_t bvh_node_visits; /* 64-byte two-box nodes of the f32 path's BVH fetched, and triangles (48 B + 4 B id) tested  */
+    uint64_t bvh_tri_tests;   /* in its leaves -- what the product path actually read when the scene has a BVH              */
 } rptb_stats;
 
 typedef struct rptb_scene rptb_scene; /* opaque */
@@ -255,6 +260,14 @@ int rptb_device_count(void);
 /* Replaces: construction of the borrowed `&Scene` the renderer walks
  * (src/renderer.rs:20, src/scene.rs:7-18).  Copies everything to `device`. */
 int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out);
+/* The same scene replicated on `ndevices` GPUs (devices[i], or 0..ndevices-1 when `devices` is NULL): flattened
+ * once, uploaded once per device.  Replaces: the fan-out inside Renderer::sample (src/renderer.rs:117-129, rayon
+ * over rows) -- rptb_render_samples on such a handle runs one host thread per GPU, GPU i renders the 16x8-pixel
+ * tiles t with t % ndevices == i and copies exactly its own pixels into the caller's image, so there is nothing to
+ * reduce and the image is bit-identical for any ndevices.  rptb_render_samples_device, rptb_closest_hit and
+ * rptb_illuminate on it address replica 0 (the first is RPTB_ERR_UNSUPPORTED when ndevices > 1).          */
+int rptb_scene_create_multi(const rptb_scene_desc* desc, const int* devices, int ndevices, rptb_scene** out);
+int rptb_scene_device_count(const rptb_scene* scene);
 void rptb_scene_destroy(rptb_scene* scene);
 /* Bytes of flattened scene resident on the device (f32 layout). */
 uint64_t rptb_scene_device_bytes(const rptb_scene* scene);
@@ -292,6 +305,13 @@ int rptb_bsdf_eval(const rptb_material* material, const double* dirs, uint64_t n
  * pdf = -1 encodes `None`.                                                    */
 int rptb_sample_f(const rptb_material* material, const double* dirs, uint64_t n, uint64_t seed,
                   uint32_t precision, int device, double* out_wi, double* out_pdf);
+
+/* Point-wise Light::illuminate (src/light.rs:23-47) of scene.lights[light] at n world positions (n x 3
+ * doubles), Shape::sample of an Object light included (src/shape/sphere.rs:52-64, src/shape.rs:139-150,
+ * src/kdtree.rs:138-143, src/shape/mesh.rs:84-98, src/shape/cube.rs:74-87); draw i uses Philox key (seed, i).
+ * out_intensity n x 3, out_wi n x 3 (direction to the light), out_dist n.                                   */
+int rptb_illuminate(rptb_scene* scene, uint32_t light, const double* pos, uint64_t n, uint64_t seed,
+                    uint32_t precision, double* out_intensity, double* out_wi, double* out_dist);
 
 /* Replaces: KdTree::new -> construct (src/kdtree.rs:108-119,235-355).  Host
  * side; produces the reference-shaped tree for hosts that cannot hand theirs

@@ -166,6 +166,8 @@ class Stats(C.Structure):
         ("gpu_ms", C.c_double),
         ("launches", C.c_uint32),
         ("engine", C.c_uint32),
+        ("bvh_node_visits", C.c_uint64),
+        ("bvh_tri_tests", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -201,6 +203,8 @@ SYMBOLS = [
     ("rptb_last_error", C.c_char_p, []),
     ("rptb_device_count", C.c_int, []),
     ("rptb_scene_create", C.c_int, [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    ("rptb_scene_create_multi", C.c_int, [C.POINTER(SceneDesc), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    ("rptb_scene_device_count", C.c_int, [C.c_void_p]),
     ("rptb_scene_destroy", None, [C.c_void_p]),
     ("rptb_scene_device_bytes", C.c_uint64, [C.c_void_p]),
     ("rptb_render_samples", C.c_int,
@@ -213,6 +217,8 @@ SYMBOLS = [
     ("rptb_bsdf_eval", C.c_int, [C.POINTER(Material), c_double_p, C.c_uint64, C.c_uint32, C.c_int, c_double_p]),
     ("rptb_sample_f", C.c_int,
      [C.POINTER(Material), c_double_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, c_double_p, c_double_p]),
+    ("rptb_illuminate", C.c_int,
+     [C.c_void_p, C.c_uint32, c_double_p, C.c_uint64, C.c_uint64, C.c_uint32, c_double_p, c_double_p, c_double_p]),
     ("rptb_build_kdtree", C.c_int, [c_double_p, C.c_uint64, C.POINTER(KdTreeOut)]),
     ("rptb_build_kdtree_boxes", C.c_int, [c_double_p, C.c_uint64, C.POINTER(KdTreeOut)]),
     ("rptb_free_kdtree", None, [C.POINTER(KdTreeOut)]),

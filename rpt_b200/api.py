@@ -746,12 +746,40 @@ class FlatScene:
 class DeviceScene:
     """RAII wrapper of the opaque rptb_scene handle."""
 
-    def __init__(self, scene_or_flat, device: int = 0, accel: int = capi.ACCEL_AUTO):
+    def __init__(self, scene_or_flat, device=0, accel: int = capi.ACCEL_AUTO):
+        """`device`: one CUDA device index, or a sequence of them -> rptb_scene_create_multi (the scene replicated
+        on every listed GPU; Renderer::sample then fans out over them inside rptb_render_samples)."""
         self.flat = scene_or_flat if isinstance(scene_or_flat, FlatScene) else FlatScene(scene_or_flat, accel)
         self.handle = C.c_void_p()
-        self.device = device
-        capi.check(capi.lib().rptb_scene_create(C.byref(self.flat.desc), device, C.byref(self.handle)),
-                   "rptb_scene_create")
+        if isinstance(device, (list, tuple)):
+            self.devices = [int(d) for d in device]
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            self.device = self.devices[0]
+            capi.check(capi.lib().rptb_scene_create_multi(C.byref(self.flat.desc), arr, len(self.devices), C.byref(self.handle)),
+                       "rptb_scene_create_multi")
+        else:
+            self.device = int(device)
+            self.devices = [self.device]
+            capi.check(capi.lib().rptb_scene_create(C.byref(self.flat.desc), self.device, C.byref(self.handle)),
+                       "rptb_scene_create")
+
+    def device_count(self) -> int:
+        return int(capi.lib().rptb_scene_device_count(self.handle))
+
+    # Light::illuminate of scene.lights[light] at a batch of positions (src/light.rs:23-47)
+    def illuminate(self, light: int, pos: np.ndarray, seed: int = 0, precision: int = capi.PRECISION_F32):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        n = pos.shape[0]
+        inten = np.empty((n, 3), np.float64)
+        wi = np.empty((n, 3), np.float64)
+        dist = np.empty(n, np.float64)
+        capi.check(
+            capi.lib().rptb_illuminate(self.handle, light, pos.ctypes.data_as(capi.c_double_p), n, seed, precision,
+                                       inten.ctypes.data_as(capi.c_double_p), wi.ctypes.data_as(capi.c_double_p),
+                                       dist.ctypes.data_as(capi.c_double_p)),
+            "rptb_illuminate",
+        )
+        return inten, wi, dist
 
     def close(self) -> None:
         if self.handle:
@@ -894,8 +922,10 @@ class Renderer:
         self._seed = int(seed)
         return self
 
-    def device(self, device: int) -> "Renderer":
-        self._device = int(device)
+    def device(self, device) -> "Renderer":
+        """One CUDA device index, or a list of them: Renderer::sample then fans out over those GPUs behind the
+        same rptb_render_samples call (rptb_scene_create_multi)."""
+        self._device = [int(d) for d in device] if isinstance(device, (list, tuple)) else int(device)
         return self
 
     def precision(self, precision: int) -> "Renderer":
@@ -925,6 +955,9 @@ class Renderer:
         p.engine = self._engine
         return p
 
+    def _first_device(self) -> int:
+        return self._device[0] if isinstance(self._device, list) else self._device
+
     def device_scene(self) -> DeviceScene:
         if self._dev_scene is None:
             self._dev_scene = DeviceScene(self.scene, self._device, self._accel)
@@ -952,12 +985,12 @@ class Renderer:
         buffer.add_samples(colors)
 
     def render(self) -> np.ndarray:  # :96-100
-        buffer = Buffer(self._width, self._height, self._filter, self._device)
+        buffer = Buffer(self._width, self._height, self._filter, self._first_device())
         self.sample(self._num_samples, buffer)
         return buffer.image()
 
     def iterative_render(self, callback_interval: int, callback: Callable[[int, Buffer], None]) -> None:  # :103-115
-        buffer = Buffer(self._width, self._height, self._filter, self._device)
+        buffer = Buffer(self._width, self._height, self._filter, self._first_device())
         iteration = 0
         while iteration < self._num_samples:
             steps = min(self._num_samples - iteration, callback_interval)

@@ -19,6 +19,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rpt_b200.h"
@@ -82,26 +83,53 @@ struct DeviceGuard {
     }
 };
 
-// Stream-ordered allocations from the device's default memory pool, which is told to keep what
-// is freed: creating and destroying a scene per call (what the reference's `Renderer::render` on a
-// host `Scene` amounts to) then costs microseconds instead of the 1-400 ms cudaMalloc/cudaFree took.
+// Stream-ordered allocations from a memory pool of the library's OWN (one per device, created on first use):
+// creating and destroying a scene per call (what the reference's `Renderer::render` on a host `Scene`
+// amounts to) costs microseconds instead of the 1-400 ms cudaMalloc/cudaFree took, because the pool keeps
+// what is freed while scenes are alive.  The device's default pool -- which torch, NCCL and the host
+// application share -- is left alone; when the last scene on a device is destroyed the pool is trimmed to
+// nothing, so the memory goes back to the driver.
+struct DevicePool {
+    cudaMemPool_t pool = nullptr;
+    int scenes = 0;
+};
+std::mutex g_pool_mutex;
+DevicePool g_pools[64];
+
 cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t stream) {
-    static std::mutex m;
-    static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64) {
-        std::lock_guard<std::mutex> lk(m);
-        if (!configured[dev]) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                uint64_t keep = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            configured[dev] = true;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(p, bytes, stream);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        DevicePool& dp = g_pools[dev];
+        if (!dp.pool) {
+            cudaMemPoolProps props;
+            std::memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            const cudaError_t e = cudaMemPoolCreate(&dp.pool, &props);
+            if (e != cudaSuccess) return e;
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(dp.pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
+        pool = dp.pool;
     }
-    return cudaMallocAsync(p, bytes, stream);
+    return cudaMallocFromPoolAsync(p, bytes, pool, stream);
+}
+void pool_scene_born(int dev) {
+    if (dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    g_pools[dev].scenes++;
+}
+void pool_scene_gone(int dev) {  // call after the scene's frees have completed
+    if (dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    DevicePool& dp = g_pools[dev];
+    if (dp.scenes > 0 && --dp.scenes == 0 && dp.pool) cudaMemPoolTrimTo(dp.pool, 0);
 }
 
 // All device allocations of a scene, freed together.
@@ -156,6 +184,16 @@ struct rptb_scene {
     double* partial = nullptr;      // per-chunk pixel sums of the megakernel (nchunks > 1)
     size_t partial_bytes = 0;
     uint32_t* wf_pinned = nullptr;  // page-locked word for the step loop's termination check
+    // A render enqueued on a caller's stream returns before it has run, while it still uses the scratch above
+    // (partial, counters, out64, wf_mem).  `busy` is recorded behind it; the next call on ANY stream -- and every
+    // stream-ordered free or reallocation of scratch on `stream` -- first waits for it.
+    cudaEvent_t busy = nullptr;
+    bool busy_pending = false;
+    // page-locked staging for the device -> host copy of rptb_render_samples
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    // rptb_scene_create_multi: the replicas on the other devices (this handle is replica 0)
+    std::vector<rptb_scene*> peers;
 };
 
 namespace {
@@ -182,16 +220,14 @@ struct ArenaPut {
     uint64_t bytes() const { return arena.bytes; }
 };
 
-int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
-    HostScene hs;
-    std::string err;
-    int rc = flatten_scene(d, hs, err, resolve_accel(d->accel) == RPTB_ACCEL_BVH);
-    if (rc != RPTB_OK) return fail(rc, "%s", err.c_str());
-    if (getenv("RPTB_NO_SMALL") != nullptr) hs.small_ok = false;
+// Uploads the flattened scene to s->device (the current device).  `release` = drop the host copies of the big
+// arrays as they are handed over (the last -- or only -- replica).
+int scene_bind_device(HostScene& hs, rptb_scene* s, bool release) {
+    pool_scene_born(s->device);
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->arena.stream = s->stream;
     ArenaPut put{s->arena};
-    if (!bind_scene(hs, put, true, s->view32, s->view64, s->f32_bytes)) CU(put.error);
+    if (!bind_scene(hs, put, release, s->view32, s->view64, s->f32_bytes)) CU(put.error);
     s->features = hs.features;
     s->has_tree = hs.has_tree;
     s->tree_nodes = hs.tree_nodes;
@@ -204,7 +240,25 @@ int scene_create_impl(const rptb_scene_desc* d, rptb_scene* s) {
     CU(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), s->stream));
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
+    CU(cudaEventCreateWithFlags(&s->busy, cudaEventDisableTiming));
     CU(cudaStreamSynchronize(s->stream));  // the scene is resident when create returns
+    return RPTB_OK;
+}
+
+int flatten_desc(const rptb_scene_desc* d, HostScene& hs) {
+    std::string err;
+    const int rc = flatten_scene(d, hs, err, resolve_accel(d->accel) == RPTB_ACCEL_BVH);
+    if (rc != RPTB_OK) return fail(rc, "%s", err.c_str());
+    if (getenv("RPTB_NO_SMALL") != nullptr) hs.small_ok = false;
+    return RPTB_OK;
+}
+
+// Orders `target` (and the library's own stream, on which scratch is freed and reallocated) behind a render
+// that an earlier call left running on a caller's stream.
+int wait_busy(rptb_scene* s, cudaStream_t target) {
+    if (!s->busy_pending) return RPTB_OK;
+    CU(cudaStreamWaitEvent(s->stream, s->busy, 0));
+    if (target != s->stream) CU(cudaStreamWaitEvent(target, s->busy, 0));
     return RPTB_OK;
 }
 
@@ -218,6 +272,7 @@ int check_params(const rptb_scene* s, const rptb_camera* cam, const rptb_render_
     if (p->shard_index >= sc) return fail(RPTB_ERR_BAD_ARG, "shard_index %u >= shard_count %u", p->shard_index, sc);
     if (p->precision > RPTB_PRECISION_F64) return fail(RPTB_ERR_BAD_ARG, "bad precision %u", p->precision);
     if (p->engine > RPTB_ENGINE_WAVEFRONT) return fail(RPTB_ERR_BAD_ARG, "bad engine %u", p->engine);
+    if (p->collect_stats > 2) return fail(RPTB_ERR_BAD_ARG, "bad collect_stats %u", p->collect_stats);
     if (p->engine == RPTB_ENGINE_WAVEFRONT && p->precision != RPTB_PRECISION_F32)
         return fail(RPTB_ERR_UNSUPPORTED, "the wavefront engine is f32 only (the f64 parity gate is the megakernel)");
     if (p->engine == RPTB_ENGINE_WAVEFRONT && s->sampled_lights > 8)
@@ -247,6 +302,8 @@ void read_stats(const DeviceCounters& c, rptb_stats* st) {
     st->mesh_hits = c.mesh_hits;
     st->env_lookups = c.env_lookups;
     st->object_tests = c.object_tests;
+    st->bvh_node_visits = c.bvh_node_visits;
+    st->bvh_tri_tests = c.bvh_tri_tests;
 }
 
 // Chunk-sum scratch of the megakernel: nchunks * ntiles_mine * 128 * 3 doubles.
@@ -266,14 +323,15 @@ int ensure_partial(rptb_scene* s, RenderArgs<R>& a) {
     return RPTB_OK;
 }
 
-// Launch the render on `stream` into a device buffer of the precision's type.
+// Launch the render on `stream` into a device buffer of the precision's type.  `compact`: see RenderArgs::compact.
 int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p, float* out32, double* out64,
-                  cudaStream_t stream, bool want_counters, uint32_t* launches) {
+                  cudaStream_t stream, bool want_counters, bool compact, uint32_t* launches) {
     if (want_counters) CU(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), stream));
     if (p->precision == RPTB_PRECISION_F32) {
         RenderArgs<float> a;
         fill_args(cam, p, a);
         a.out = out32;
+        a.compact = compact ? 1u : 0u;
         a.counters = want_counters ? s->counters : nullptr;
         if (use_wavefront(s, p)) {
             const uint32_t npix = a.ntiles_mine * 128u;
@@ -306,20 +364,17 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         } else {
             const int rc = ensure_partial(s, a);
             if (rc != RPTB_OK) return rc;
-            // Scenes with kd-trees of shapes: their mesh children go through the BVH only on request
-            // (RPTB_EXT_BVH=1) -- that instantiation is checked in host emulation but has not run on a GPU yet.
-            int feats = s->features;
-            if ((feats & F_EXT) && getenv("RPTB_EXT_BVH") == nullptr) feats &= ~F_BVH;
-            CU(launch_render_f32(s->view32, a, p->collect_stats != 0, feats, stream, launches));
+            CU(launch_render_f32(s->view32, a, (int)p->collect_stats, s->features, stream, launches));
         }
     } else {
         RenderArgs<double> a;
         fill_args(cam, p, a);
         a.out = out64;
+        a.compact = compact ? 1u : 0u;
         a.counters = want_counters ? s->counters : nullptr;
         const int rc = ensure_partial(s, a);
         if (rc != RPTB_OK) return rc;
-        CU(launch_render_f64(s->view64, a, p->collect_stats != 0, F_ALL | (s->features & F_EXT), stream, launches));
+        CU(launch_render_f64(s->view64, a, (int)p->collect_stats, F_ALL | (s->features & F_EXT), stream, launches));
     }
     return RPTB_OK;
 }
@@ -338,6 +393,99 @@ int ensure_out(rptb_scene* s, size_t nvals) {
     return RPTB_OK;
 }
 
+int ensure_stage(rptb_scene* s, size_t bytes) {
+    if (s->stage_bytes >= bytes) return RPTB_OK;
+    if (s->stage) cudaFreeHost(s->stage);
+    s->stage = nullptr;
+    s->stage_bytes = 0;
+    CU(cudaHostAlloc(&s->stage, bytes, cudaHostAllocDefault));
+    s->stage_bytes = bytes;
+    return RPTB_OK;
+}
+
+// One replica's share of Renderer::sample, straight into the caller's host image: render the pixel tiles t with
+// t % shard_count == shard_index into a compact tile-major device buffer, copy exactly those pixels back
+// through page-locked staging and scatter them into out_rgb (row-major doubles).  Pixels of other shards are not
+// touched.  Runs on the library's own stream and returns when out_rgb holds this shard.
+int render_shard_to_host(rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p, double* out_rgb, rptb_stats* stats) {
+    std::lock_guard<std::mutex> lk(s->lock);
+    DeviceGuard g(s->device);
+    if (!g.ok) return fail(RPTB_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    int rc = wait_busy(s, s->stream);
+    if (rc != RPTB_OK) return rc;
+    const uint32_t sc = p->shard_count ? p->shard_count : 1u;
+    const uint32_t tiles_x = (p->width + 15u) / 16u, tiles_y = (p->height + 7u) / 8u, ntiles = tiles_x * tiles_y;
+    const uint32_t mine = ntiles > p->shard_index ? (ntiles - p->shard_index + sc - 1u) / sc : 0u;
+    const size_t nvals = (size_t)mine * 128u * 3u;
+    const bool f32 = p->precision == RPTB_PRECISION_F32;
+    rc = ensure_out(s, nvals ? nvals : 1);
+    if (rc != RPTB_OK) return rc;
+    rc = ensure_stage(s, (nvals ? nvals : 1) * sizeof(double));
+    if (rc != RPTB_OK) return rc;
+    uint32_t launches = 0;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    rc = render_launch(s, cam, p, s->out32, s->out64, s->stream, true, true, &launches);
+    if (rc != RPTB_OK) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    DeviceCounters c;
+    CU(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    if (nvals) {
+        if (f32) CU(cudaMemcpyAsync(s->stage, s->out32, nvals * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        else CU(cudaMemcpyAsync(s->stage, s->out64, nvals * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    s->busy_pending = false;
+    const float* h32 = (const float*)s->stage;
+    const double* h64 = (const double*)s->stage;
+    const uint32_t W = p->width, H = p->height;
+#pragma omp parallel for schedule(static) if (mine > 64)
+    for (int64_t k = 0; k < (int64_t)mine; k++) {
+        const uint32_t tile = p->shard_index + (uint32_t)k * sc;
+        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+        for (uint32_t j = 0; j < 128u; j++) {  // thread j of the CTA: warp (j >> 5) covers an 8 x 4 block of the 16 x 8 tile
+            const uint32_t warp = j >> 5, lane = j & 31u;
+            const uint32_t x = tx * 16u + (warp & 1u) * 8u + (lane & 7u), y = ty * 8u + (warp >> 1) * 4u + (lane >> 3);
+            if (x >= W || y >= H) continue;
+            const size_t src = ((size_t)k * 128u + j) * 3u;
+            double* dst = out_rgb + 3 * ((size_t)y * W + x);
+            if (f32) { dst[0] = (double)h32[src]; dst[1] = (double)h32[src + 1]; dst[2] = (double)h32[src + 2]; }
+            else { dst[0] = h64[src]; dst[1] = h64[src + 1]; dst[2] = h64[src + 2]; }
+        }
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        read_stats(c, stats);
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->gpu_ms = ms;
+        stats->launches = launches;
+        stats->engine = use_wavefront(s, p) ? RPTB_ENGINE_WAVEFRONT : RPTB_ENGINE_MEGAKERNEL;
+    }
+    return RPTB_OK;
+}
+
+void destroy_replica(rptb_scene* s) {
+    DeviceGuard g(s->device);
+    cudaDeviceSynchronize();  // renders may have been enqueued on a caller's stream
+    s->arena.release();
+    if (s->counters) cudaFreeAsync(s->counters, s->stream);
+    if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
+    if (s->partial) cudaFreeAsync(s->partial, s->stream);
+    if (s->wf_pinned) cudaFreeHost(s->wf_pinned);
+    if (s->stage) cudaFreeHost(s->stage);
+    if (s->out32) cudaFreeAsync(s->out32, s->stream);
+    if (s->out64) cudaFreeAsync(s->out64, s->stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->busy) cudaEventDestroy(s->busy);
+    if (s->stream) {
+        cudaStreamDestroy(s->stream);
+        pool_scene_gone(s->device);  // counted by scene_bind_device right before the stream was made
+    }
+    delete s;
+}
+
 }  // namespace
 
 // ================================================================== C ABI ======
@@ -352,7 +500,7 @@ int rptb_device_count(void) {
     return n;
 }
 
-int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out) {
+int rptb_scene_create_multi(const rptb_scene_desc* desc, const int* devices, int ndevices, rptb_scene** out) {
     if (!desc || !out) return fail(RPTB_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     if ((desc->nmaterials && !desc->materials) || (desc->nobjects && !desc->objects) || (desc->nlights && !desc->lights) ||
@@ -369,68 +517,95 @@ int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out)
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RPTB_ERR_NO_DEVICE, "no CUDA device");
-    if (device < 0 || device >= ndev) return fail(RPTB_ERR_BAD_ARG, "device %d of %d", device, ndev);
-    DeviceGuard g(device);
-    if (!g.ok) return fail(RPTB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    rptb_scene* s = new (std::nothrow) rptb_scene();
-    if (!s) return fail(RPTB_ERR_OOM, "host allocation failed");
-    s->device = device;
-    std::memset(&s->view32, 0, sizeof(s->view32));
-    std::memset(&s->view64, 0, sizeof(s->view64));
-    int rc;
+    if (ndevices <= 0 || ndevices > 64) return fail(RPTB_ERR_BAD_ARG, "ndevices %d", ndevices);
+    std::vector<int> devs(ndevices);
+    for (int i = 0; i < ndevices; i++) {
+        devs[i] = devices ? devices[i] : i;
+        if (devs[i] < 0 || devs[i] >= ndev) return fail(RPTB_ERR_BAD_ARG, "device %d of %d", devs[i], ndev);
+        for (int j = 0; j < i; j++)
+            if (devs[j] == devs[i]) return fail(RPTB_ERR_BAD_ARG, "device %d listed twice", devs[i]);
+    }
+    std::vector<rptb_scene*> reps;
+    int rc = RPTB_OK;
     try {
-        rc = scene_create_impl(desc, s);
+        HostScene hs;  // flattened once (kd-tree folding, BVH build), uploaded once per device
+        rc = flatten_desc(desc, hs);
+        for (int i = 0; rc == RPTB_OK && i < ndevices; i++) {
+            DeviceGuard g(devs[i]);
+            if (!g.ok) {
+                rc = fail(RPTB_ERR_CUDA, "cudaSetDevice(%d) failed", devs[i]);
+                break;
+            }
+            rptb_scene* s = new (std::nothrow) rptb_scene();
+            if (!s) {
+                rc = fail(RPTB_ERR_OOM, "host allocation failed");
+                break;
+            }
+            s->device = devs[i];
+            std::memset(&s->view32, 0, sizeof(s->view32));
+            std::memset(&s->view64, 0, sizeof(s->view64));
+            reps.push_back(s);
+            rc = scene_bind_device(hs, s, i + 1 == ndevices);
+            s->features = hs.features;
+            s->has_tree = hs.has_tree;
+            s->tree_nodes = hs.tree_nodes;
+            s->sampled_lights = hs.sampled_lights;
+            for (int k = 0; k < 3; k++) {
+                s->wlo[k] = hs.wlo[k];
+                s->whi[k] = hs.whi[k];
+            }
+        }
     } catch (const std::bad_alloc&) {
         rc = fail(RPTB_ERR_OOM, "host allocation failed while flattening the scene");
     }
     if (rc != RPTB_OK) {
         const std::string keep = g_error;
-        rptb_scene_destroy(s);
+        for (rptb_scene* r : reps) destroy_replica(r);
         g_error = keep;
         return rc;
     }
-    *out = s;
+    reps[0]->peers.assign(reps.begin() + 1, reps.end());
+    *out = reps[0];
     return RPTB_OK;
+}
+
+int rptb_scene_create(const rptb_scene_desc* desc, int device, rptb_scene** out) {
+    return rptb_scene_create_multi(desc, &device, 1, out);
 }
 
 void rptb_scene_destroy(rptb_scene* s) {
     if (!s) return;
-    DeviceGuard g(s->device);
-    cudaDeviceSynchronize();  // renders may have been enqueued on a caller's stream
-    s->arena.release();
-    if (s->counters) cudaFreeAsync(s->counters, s->stream);
-    if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
-    if (s->partial) cudaFreeAsync(s->partial, s->stream);
-    if (s->wf_pinned) cudaFreeHost(s->wf_pinned);
-    if (s->out32) cudaFreeAsync(s->out32, s->stream);
-    if (s->out64) cudaFreeAsync(s->out64, s->stream);
-    if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
-    if (s->stream) cudaStreamDestroy(s->stream);
-    delete s;
+    for (rptb_scene* r : s->peers) destroy_replica(r);
+    destroy_replica(s);
 }
 
 uint64_t rptb_scene_device_bytes(const rptb_scene* s) { return s ? s->f32_bytes : 0; }
+
+int rptb_scene_device_count(const rptb_scene* s) { return s ? 1 + (int)s->peers.size() : 0; }
 
 int rptb_render_samples_device(rptb_scene* s, const rptb_camera* cam, const rptb_render_params* p, float* out_dev,
                                void* stream_v, rptb_stats* stats) {
     int rc = check_params(s, cam, p);
     if (rc != RPTB_OK) return rc;
     if (!out_dev) return fail(RPTB_ERR_BAD_ARG, "null output");
+    if (!s->peers.empty())
+        return fail(RPTB_ERR_UNSUPPORTED, "a multi-device handle renders into host memory (rptb_render_samples); device-resident "
+                                          "output is per device: create one handle per GPU and shard with shard_index / shard_count");
     std::lock_guard<std::mutex> lk(s->lock);
     DeviceGuard g(s->device);
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : s->stream;
+    rc = wait_busy(s, stream);
+    if (rc != RPTB_OK) return rc;
     const size_t nvals = (size_t)p->width * p->height * 3;
     uint32_t launches = 0;
     if (stats) CU(cudaEventRecord(s->ev0, stream));
     if (p->precision == RPTB_PRECISION_F32) {
-        rc = render_launch(s, cam, p, out_dev, nullptr, stream, stats != nullptr, &launches);
+        rc = render_launch(s, cam, p, out_dev, nullptr, stream, stats != nullptr, false, &launches);
         if (rc != RPTB_OK) return rc;
     } else {
         rc = ensure_out(s, nvals);
         if (rc != RPTB_OK) return rc;
-        rc = render_launch(s, cam, p, nullptr, s->out64, stream, stats != nullptr, &launches);
+        rc = render_launch(s, cam, p, nullptr, s->out64, stream, stats != nullptr, false, &launches);
         if (rc != RPTB_OK) return rc;
         CU(launch_convert_f64_to_f32(s->out64, out_dev, nvals, stream));
         launches++;
@@ -440,6 +615,7 @@ int rptb_render_samples_device(rptb_scene* s, const rptb_camera* cam, const rptb
         DeviceCounters c;
         CU(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
+        s->busy_pending = false;
         std::memset(stats, 0, sizeof(*stats));
         read_stats(c, stats);
         float ms = 0;
@@ -449,6 +625,11 @@ int rptb_render_samples_device(rptb_scene* s, const rptb_camera* cam, const rptb
         stats->engine = use_wavefront(s, p) ? RPTB_ENGINE_WAVEFRONT : RPTB_ENGINE_MEGAKERNEL;
     } else if (!stream_v) {
         CU(cudaStreamSynchronize(stream));
+        s->busy_pending = false;
+    } else {
+        // still running on the caller's stream when we return: later calls order themselves behind this point
+        CU(cudaEventRecord(s->busy, stream));
+        s->busy_pending = true;
     }
     return RPTB_OK;
 }
@@ -458,35 +639,45 @@ int rptb_render_samples(rptb_scene* s, const rptb_camera* cam, const rptb_render
     int rc = check_params(s, cam, p);
     if (rc != RPTB_OK) return rc;
     if (!out_rgb) return fail(RPTB_ERR_BAD_ARG, "null output");
-    std::lock_guard<std::mutex> lk(s->lock);
-    DeviceGuard g(s->device);
+    const uint32_t outer = p->shard_count ? p->shard_count : 1u;
+    const uint32_t nrep = 1u + (uint32_t)s->peers.size();
     const size_t nvals = (size_t)p->width * p->height * 3;
-    rc = ensure_out(s, nvals);
-    if (rc != RPTB_OK) return rc;
-    uint32_t launches = 0;
-    CU(cudaEventRecord(s->ev0, s->stream));
-    rc = render_launch(s, cam, p, s->out32, s->out64, s->stream, true, &launches);
-    if (rc != RPTB_OK) return rc;
-    CU(cudaEventRecord(s->ev1, s->stream));
-    DeviceCounters c;
-    CU(cudaMemcpyAsync(&c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
-    if (p->precision == RPTB_PRECISION_F32) {
-        std::vector<float> tmp(nvals);
-        CU(cudaMemcpyAsync(tmp.data(), s->out32, nvals * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        for (size_t i = 0; i < nvals; i++) out_rgb[i] = (double)tmp[i];
-    } else {
-        CU(cudaMemcpyAsync(out_rgb, s->out64, nvals * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+    // pixels of the caller's OTHER shards read as zero (as rptb_render_samples_device leaves them)
+    if (outer > 1) std::memset(out_rgb, 0, nvals * sizeof(double));
+    if (nrep == 1) return render_shard_to_host(s, cam, p, out_rgb, stats);
+    // Renderer::sample's fan-out (src/renderer.rs:117-129: rayon over rows) across the replicas: one host thread
+    // per GPU, replica i renders the pixel tiles t with t % (outer * nrep) == shard_index * nrep + i and copies
+    // exactly those pixels into out_rgb.  Every pixel has one owner and the RNG is keyed by pixel, so the image
+    // is bit-identical for any number of devices; there is nothing to reduce, hence no collective.
+    std::vector<int> rcs(nrep, RPTB_OK);
+    std::vector<std::string> errs(nrep);
+    std::vector<rptb_stats> sts(nrep);
+    std::vector<std::thread> workers;
+    for (uint32_t i = 0; i < nrep; i++) {
+        workers.emplace_back([&, i]() {
+            rptb_render_params q = *p;
+            q.shard_count = outer * nrep;
+            q.shard_index = p->shard_index * nrep + i;
+            rptb_scene* rep = i == 0 ? s : s->peers[i - 1];
+            rcs[i] = render_shard_to_host(rep, cam, &q, out_rgb, &sts[i]);
+            if (rcs[i] != RPTB_OK) errs[i] = g_error;  // g_error is thread-local
+        });
     }
+    for (std::thread& t : workers) t.join();
+    for (uint32_t i = 0; i < nrep; i++)
+        if (rcs[i] != RPTB_OK) return fail(rcs[i], "device %d: %s", i == 0 ? s->device : s->peers[i - 1]->device, errs[i].c_str());
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
-        read_stats(c, stats);
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-        stats->gpu_ms = ms;
-        stats->launches = launches;
-        stats->engine = use_wavefront(s, p) ? RPTB_ENGINE_WAVEFRONT : RPTB_ENGINE_MEGAKERNEL;
+        for (uint32_t i = 0; i < nrep; i++) {
+            stats->segments += sts[i].segments; stats->rays += sts[i].rays;
+            stats->node_visits += sts[i].node_visits; stats->tri_tests += sts[i].tri_tests;
+            stats->mesh_hits += sts[i].mesh_hits; stats->env_lookups += sts[i].env_lookups;
+            stats->object_tests += sts[i].object_tests;
+            stats->bvh_node_visits += sts[i].bvh_node_visits; stats->bvh_tri_tests += sts[i].bvh_tri_tests;
+            stats->gpu_ms = std::max(stats->gpu_ms, sts[i].gpu_ms);  // the devices run concurrently
+            stats->launches += sts[i].launches;
+        }
+        stats->engine = sts[0].engine;
     }
     return RPTB_OK;
 }
@@ -523,9 +714,9 @@ int rptb_closest_hit(rptb_scene* s, const double* rays, uint64_t n, double t_min
     CUC(cudaMemsetAsync(s->counters, 0, sizeof(DeviceCounters), s->stream));
     CUC(cudaEventRecord(s->ev0, s->stream));
     if (precision == RPTB_PRECISION_F32)
-        CUC(launch_closest_hit_f32(s->view32, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->features, s->stream));
+        CUC(launch_closest_hit_f32(s->view32, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats ? 1 : 0, s->features, s->stream));
     else
-        CUC(launch_closest_hit_f64(s->view64, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats != nullptr, s->features, s->stream));
+        CUC(launch_closest_hit_f64(s->view64, d_rays, n, t_min, d_t, d_obj, d_n, stats ? s->counters : nullptr, stats ? 1 : 0, s->features, s->stream));
     CUC(cudaEventRecord(s->ev1, s->stream));
     CUC(cudaMemcpyAsync(out_t, d_t, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUC(cudaMemcpyAsync(out_object, d_obj, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
@@ -540,6 +731,36 @@ int rptb_closest_hit(rptb_scene* s, const double* rays, uint64_t n, double t_min
         stats->gpu_ms = ms;
         stats->launches = 1;
     }
+    cleanup();
+    return RPTB_OK;
+}
+
+int rptb_illuminate(rptb_scene* s, uint32_t light, const double* pos, uint64_t n, uint64_t seed, uint32_t precision,
+                    double* out_intensity, double* out_wi, double* out_dist) {
+    if (!s || (n && (!pos || !out_intensity || !out_wi || !out_dist))) return fail(RPTB_ERR_BAD_ARG, "null argument");
+    if (precision > RPTB_PRECISION_F64) return fail(RPTB_ERR_BAD_ARG, "bad precision %u", precision);
+    if (light >= s->view32.nlights) return fail(RPTB_ERR_BAD_ARG, "light %u of %u", light, s->view32.nlights);
+    if (n == 0) return RPTB_OK;
+    std::lock_guard<std::mutex> lk(s->lock);
+    DeviceGuard g(s->device);
+    double *d_pos = nullptr, *d_i = nullptr, *d_wi = nullptr, *d_dist = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_pos);
+        cudaFree(d_i);
+        cudaFree(d_wi);
+        cudaFree(d_dist);
+    };
+    CUC(cudaMalloc(&d_pos, n * 3 * sizeof(double)));
+    CUC(cudaMalloc(&d_i, n * 3 * sizeof(double)));
+    CUC(cudaMalloc(&d_wi, n * 3 * sizeof(double)));
+    CUC(cudaMalloc(&d_dist, n * sizeof(double)));
+    CUC(cudaMemcpyAsync(d_pos, pos, n * 3 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (precision == RPTB_PRECISION_F32) CUC(launch_illuminate_f32(s->view32, light, d_pos, n, seed, d_i, d_wi, d_dist, s->stream));
+    else CUC(launch_illuminate_f64(s->view64, light, d_pos, n, seed, d_i, d_wi, d_dist, s->stream));
+    CUC(cudaMemcpyAsync(out_intensity, d_i, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUC(cudaMemcpyAsync(out_wi, d_wi, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUC(cudaMemcpyAsync(out_dist, d_dist, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUC(cudaStreamSynchronize(s->stream));
     cleanup();
     return RPTB_OK;
 }

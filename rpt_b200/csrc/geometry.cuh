@@ -37,7 +37,8 @@ struct Hit {
 };
 
 struct TravStats {
-    uint32_t node_visits, tri_tests, object_tests;
+    uint32_t node_visits, tri_tests, object_tests;  // the reference-shaped kd-trees (kdtree.rs:151, mesh.rs:49) and Shape::intersect dispatches
+    uint32_t bvh_nodes, bvh_tris;                   // the f32 path's BVH: 64-byte nodes fetched, triangles tested
 };
 
 template <class R>
@@ -295,7 +296,7 @@ RPTB_D bool bvh_intersect(const MeshRec<float>& m, Vec3<float> o, Vec3<float> d,
     bool hit = false;
     while (true) {
         while (cur >= 0) {  // inner node: test both children
-            if (STATS) ts.node_visits++;
+            if (STATS) ts.bvh_nodes++;
             const BvhNodeDev n = load_bvh_node(m.bvh_nodes + cur);
             const float ax0 = fmaf(n.c0xy.x, inv.x, -oi.x), ax1 = fmaf(n.c0xy.y, inv.x, -oi.x);
             const float ay0 = fmaf(n.c0xy.z, inv.y, -oi.y), ay1 = fmaf(n.c0xy.w, inv.y, -oi.y);
@@ -326,7 +327,7 @@ RPTB_D bool bvh_intersect(const MeshRec<float>& m, Vec3<float> o, Vec3<float> d,
             const uint32_t code = (uint32_t)~cur;
             const uint32_t first = code >> 3, count = (code & 7u) + 1u;
             for (uint32_t k = first; k < first + count; k++) {
-                if (STATS) ts.tri_tests++;
+                if (STATS) ts.bvh_tris++;
                 const float4* q = m.bvh_tri48 + 3 * (size_t)k;
                 const float4 q0 = ldg(q);
                 const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;

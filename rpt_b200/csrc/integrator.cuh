@@ -139,7 +139,7 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
     uint32_t Ks = 0;  // lights that need a shadow ray (warp-uniform)
     for (uint32_t i = 0; i < sv.nlights; i++) Ks += scene_light<FEAT>(sv, i).kind != LIGHT_AMBIENT ? 1u : 0u;
 
-    PathCounters pc = {0, 0, 0, 0, {0, 0, 0}};
+    PathCounters pc = {0, 0, 0, 0, {0, 0, 0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     Level<R> stack[MAXD];
     Rng<R> rng;
@@ -367,7 +367,7 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
         // the chunk sums were published as they completed; resolve_chunks_kernel finishes the pixel
     } else {
         const double it = (double)a.iterations;
-        R* out = a.out + 3 * (size_t)pix;
+        R* out = a.out + 3 * (a.compact ? pslot : (size_t)pix);
         out[0] = (R)(acc0 / it * (double)a.exposure_scale);
         out[1] = (R)(acc1 / it * (double)a.exposure_scale);
         out[2] = (R)(acc2 / it * (double)a.exposure_scale);
@@ -381,6 +381,8 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
         const uint32_t n_lo = W::reduce_add(m, pc.ts.node_visits & 0xFFFFu), n_hi = W::reduce_add(m, pc.ts.node_visits >> 16);
         const uint32_t t_lo = W::reduce_add(m, pc.ts.tri_tests & 0xFFFFu), t_hi = W::reduce_add(m, pc.ts.tri_tests >> 16);
         const uint32_t o_lo = W::reduce_add(m, pc.ts.object_tests & 0xFFFFu), o_hi = W::reduce_add(m, pc.ts.object_tests >> 16);
+        const uint32_t bn_lo = W::reduce_add(m, pc.ts.bvh_nodes & 0xFFFFu), bn_hi = W::reduce_add(m, pc.ts.bvh_nodes >> 16);
+        const uint32_t bt_lo = W::reduce_add(m, pc.ts.bvh_tris & 0xFFFFu), bt_hi = W::reduce_add(m, pc.ts.bvh_tris >> 16);
         if (W::is_leader(m, lane)) {
             W::add(&a.counters->segments, (unsigned long long)v0);
             W::add(&a.counters->rays, (unsigned long long)v1);
@@ -390,6 +392,10 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
                 W::add(&a.counters->node_visits, (unsigned long long)n_lo + ((unsigned long long)n_hi << 16));
                 W::add(&a.counters->tri_tests, (unsigned long long)t_lo + ((unsigned long long)t_hi << 16));
                 W::add(&a.counters->object_tests, (unsigned long long)o_lo + ((unsigned long long)o_hi << 16));
+                if ((FEAT & F_BVH) != 0) {
+                    W::add(&a.counters->bvh_node_visits, (unsigned long long)bn_lo + ((unsigned long long)bn_hi << 16));
+                    W::add(&a.counters->bvh_tri_tests, (unsigned long long)bt_lo + ((unsigned long long)bt_hi << 16));
+                }
             }
         }
     }
@@ -419,7 +425,7 @@ RPTB_D void resolve_chunks_thread(const RenderArgs<R>& a, const uint32_t block_x
         s0 += p[0]; s1 += p[1]; s2 += p[2];
     }
     const double it = (double)a.iterations;
-    R* out = a.out + 3 * ((size_t)y * a.width + x);
+    R* out = a.out + 3 * (a.compact ? slot : (size_t)y * a.width + x);
     out[0] = (R)(s0 / it * (double)a.exposure_scale);
     out[1] = (R)(s1 / it * (double)a.exposure_scale);
     out[2] = (R)(s2 / it * (double)a.exposure_scale);
@@ -445,7 +451,7 @@ __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restri
                                    double* __restrict__ out_t, int32_t* __restrict__ out_obj,
                                    double* __restrict__ out_n, DeviceCounters* counters) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    TravStats ts = {0, 0, 0};
+    TravStats ts = {0, 0, 0, 0, 0};
     if (i < n) {
         const double* r = rays + 6 * i;
         const Vec3<R> o = {(R)r[0], (R)r[1], (R)r[2]};
@@ -469,6 +475,10 @@ __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restri
             atomicAdd(&counters->node_visits, (unsigned long long)ts.node_visits);
             atomicAdd(&counters->tri_tests, (unsigned long long)ts.tri_tests);
             atomicAdd(&counters->object_tests, (unsigned long long)ts.object_tests);
+            if ((FEAT & F_BVH) != 0) {
+                atomicAdd(&counters->bvh_node_visits, (unsigned long long)ts.bvh_nodes);
+                atomicAdd(&counters->bvh_tri_tests, (unsigned long long)ts.bvh_tris);
+            }
         }
     }
 }
@@ -503,6 +513,26 @@ __global__ void sample_f_kernel(const MaterialRec<R> m, const double* __restrict
     out_wi[3 * i + 1] = (double)wi.y;
     out_wi[3 * i + 2] = (double)wi.z;
     out_pdf[i] = (double)pdf;
+}
+
+// ---- point-wise Light::illuminate (light.rs:23-47), Shape::sample of the light's object included ----------
+// Stream i = Philox(seed, i, sample 0), like sample_f_kernel.  Ambient returns (color, 0, 0) as the reference does.
+template <class R, int FEAT>
+__global__ void illuminate_kernel(const SceneView<R> sv, uint32_t light, const double* __restrict__ pos, uint64_t n, uint64_t seed,
+                                  double* __restrict__ out_i, double* __restrict__ out_wi, double* __restrict__ out_dist) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const LightRec<R>& l = sv.lights[light];
+    Vec3<R> I = mk(l.color[0], l.color[1], l.color[2]), wi = mk((R)0, (R)0, (R)0);
+    R dist = (R)0;
+    if (l.kind != LIGHT_AMBIENT) {
+        Rng<R> rng;
+        rng.init(seed, (uint32_t)i, 0);
+        illuminate<R, FEAT>(sv, l, mk((R)pos[3 * i], (R)pos[3 * i + 1], (R)pos[3 * i + 2]), rng, I, wi, dist);
+    }
+    out_i[3 * i] = (double)I.x; out_i[3 * i + 1] = (double)I.y; out_i[3 * i + 2] = (double)I.z;
+    out_wi[3 * i] = (double)wi.x; out_wi[3 * i + 1] = (double)wi.y; out_wi[3 * i + 2] = (double)wi.z;
+    out_dist[i] = (double)dist;
 }
 
 }  // namespace rptb

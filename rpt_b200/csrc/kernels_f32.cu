@@ -75,7 +75,7 @@ cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float
     uint32_t nl = 0;
     cudaError_t e;
     const size_t nvals = (size_t)args.width * args.height * 3;
-    if (args.shard_count > 1) {
+    if (args.shard_count > 1 && !args.compact) {
         clear_kernel<float><<<(unsigned)((nvals + 255) / 256), 256, 0, stream>>>(args.out, nvals);
         nl++;
     }

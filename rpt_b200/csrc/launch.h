@@ -6,16 +6,19 @@
 namespace rptb {
 
 #define RPTB_DECLARE_LAUNCHERS(SUFFIX, R)                                                                          \
-    cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats,              \
+    cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, int stats,               \
                                        int features, cudaStream_t stream, uint32_t* launches);                     \
     cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,   \
                                             double* out_t, int32_t* out_obj, double* out_n,                        \
-                                            DeviceCounters* counters, bool stats, int features,                    \
+                                            DeviceCounters* counters, int stats, int features,                     \
                                             cudaStream_t stream);                                                  \
     cudaError_t launch_bsdf_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, double* out,         \
                                      cudaStream_t stream);                                                         \
     cudaError_t launch_sample_f_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, uint64_t seed,   \
-                                         double* out_wi, double* out_pdf, cudaStream_t stream);
+                                         double* out_wi, double* out_pdf, cudaStream_t stream);                    \
+    cudaError_t launch_illuminate_##SUFFIX(const SceneView<R>& sv, uint32_t light, const double* pos, uint64_t n,  \
+                                           uint64_t seed, double* out_i, double* out_wi, double* out_dist,         \
+                                           cudaStream_t stream);
 
 RPTB_DECLARE_LAUNCHERS(f32, float)
 RPTB_DECLARE_LAUNCHERS(f64, double)

@@ -6,11 +6,11 @@
 namespace rptb {
 
 template <class R>
-cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats, int features,
+cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args, int stats, int features,
                                cudaStream_t stream, uint32_t* launches) {
     uint32_t nl = 0;
     const size_t nvals = (size_t)args.width * args.height * 3;
-    if (args.shard_count > 1) {  // other shards' pixels must read as zero
+    if (args.shard_count > 1 && !args.compact) {  // other shards' pixels must read as zero
         clear_kernel<R><<<(unsigned)((nvals + 255) / 256), 256, 0, stream>>>(args.out, nvals);
         nl++;
     }
@@ -24,7 +24,11 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             // kd-trees over whole shapes and MonomialSurface live in one extra instantiation (F_EVERY), so
             // the variants tuned for the BASELINE scenes carry none of that code
             const bool ext = (features & F_EXT) != 0;
-            if (stats) render_kernel<R, 16, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            // counting passes: stats == 1 counts what the product path traverses (the BVH when the scene has one),
+            // stats == 2 walks the reference-shaped kd-trees (the algorithmic work of SURVEY 8d)
+            const bool count_bvh = !M<R>::literal && stats == 1 && (features & F_BVH);
+            if (count_bvh) render_kernel<R, 16, true, F_EVERY | F_BVH><<<grid, block, 0, stream>>>(sv, args);
+            else if (stats) render_kernel<R, 16, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
             else if (!M<R>::literal && ext && (features & F_BVH)) render_kernel<R, 16, false, F_EVERY | F_BVH><<<grid, block, 0, stream>>>(sv, args);
             else if (ext) render_kernel<R, 16, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
             else if constexpr (M<R>::literal) render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);  // the f64 gate is not specialised
@@ -37,7 +41,11 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             else if (base == (F_TRANSP | F_HDRI)) render_kernel<R, 16, false, F_TRANSP | F_HDRI><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
         } else {
-            if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            // deep paths (max_bounces > 16): one general instantiation per structure
+            const bool bvh = !M<R>::literal && (features & F_BVH) && stats != 2;
+            if (stats && bvh) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY | F_BVH><<<grid, block, 0, stream>>>(sv, args);
+            else if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            else if (bvh) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY | F_BVH><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
         }
         nl++;
@@ -52,12 +60,13 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
 
 template <class R>
 cudaError_t launch_closest_hit_impl(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin, double* out_t,
-                                    int32_t* out_obj, double* out_n, DeviceCounters* counters, bool stats, int features,
+                                    int32_t* out_obj, double* out_n, DeviceCounters* counters, int stats, int features,
                                     cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    // with counters: always the reference-shaped kd-tree (its node visits / triangle tests are the algorithmic work)
-    if (stats) closest_hit_kernel<R, true, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    // stats == 1: counters of the structure the product path traverses; stats == 2: the reference-shaped kd-trees
+    if (!M<R>::literal && stats == 1 && (features & F_BVH)) closest_hit_kernel<R, true, F_EVERY | F_BVH><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    else if (stats) closest_hit_kernel<R, true, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
     else if (!M<R>::literal && (features & F_BVH)) closest_hit_kernel<R, false, F_EVERY | F_BVH><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
     else closest_hit_kernel<R, false, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
     return cudaGetLastError();
@@ -78,14 +87,22 @@ cudaError_t launch_sample_f_impl(const MaterialRec<R>& m, const double* dirs, ui
     return cudaGetLastError();
 }
 
+template <class R>
+cudaError_t launch_illuminate_impl(const SceneView<R>& sv, uint32_t light, const double* pos, uint64_t n, uint64_t seed,
+                                   double* out_i, double* out_wi, double* out_dist, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    illuminate_kernel<R, F_EVERY><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sv, light, pos, n, seed, out_i, out_wi, out_dist);
+    return cudaGetLastError();
+}
+
 #define RPTB_DEFINE_LAUNCHERS(SUFFIX, R)                                                                            \
-    cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, bool stats,               \
+    cudaError_t launch_render_##SUFFIX(const SceneView<R>& sv, const RenderArgs<R>& args, int stats,                \
                                        int features, cudaStream_t stream, uint32_t* launches) {                     \
         return launch_render_impl<R>(sv, args, stats, features, stream, launches);                                  \
     }                                                                                                               \
     cudaError_t launch_closest_hit_##SUFFIX(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin,    \
                                             double* out_t, int32_t* out_obj, double* out_n,                         \
-                                            DeviceCounters* counters, bool stats, int features,                     \
+                                            DeviceCounters* counters, int stats, int features,                      \
                                             cudaStream_t stream) {                                                  \
         return launch_closest_hit_impl<R>(sv, rays, n, tmin, out_t, out_obj, out_n, counters, stats, features,      \
                                           stream);                                                                  \
@@ -97,6 +114,11 @@ cudaError_t launch_sample_f_impl(const MaterialRec<R>& m, const double* dirs, ui
     cudaError_t launch_sample_f_##SUFFIX(const MaterialRec<R>& m, const double* dirs, uint64_t n, uint64_t seed,    \
                                          double* out_wi, double* out_pdf, cudaStream_t stream) {                    \
         return launch_sample_f_impl<R>(m, dirs, n, seed, out_wi, out_pdf, stream);                                  \
+    }                                                                                                               \
+    cudaError_t launch_illuminate_##SUFFIX(const SceneView<R>& sv, uint32_t light, const double* pos, uint64_t n,   \
+                                           uint64_t seed, double* out_i, double* out_wi, double* out_dist,          \
+                                           cudaStream_t stream) {                                                   \
+        return launch_illuminate_impl<R>(sv, light, pos, n, seed, out_i, out_wi, out_dist, stream);                 \
     }
 
 }  // namespace rptb

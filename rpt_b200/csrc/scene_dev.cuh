@@ -188,6 +188,7 @@ struct CameraRec {
 
 struct DeviceCounters {
     unsigned long long segments, rays, node_visits, tri_tests, mesh_hits, env_lookups, object_tests;
+    unsigned long long bvh_node_visits, bvh_tri_tests;  // the f32 path's own structure (F_BVH), counted when it is what was traversed
 };
 
 template <class R>
@@ -208,6 +209,10 @@ struct RenderArgs {
     // when the shard has many tiles (long runs, little tail), many when it has few.
     uint32_t nchunks, chunk, ngroups, chunks_per_group;
     double* partial;  // nchunks > 1 only
+    // compact = 1: `out` holds ntiles_mine * 128 * 3 values in tile-major order (owned tile k, thread j of the
+    // CTA -> out[(k * 128 + j) * 3]); nothing is written for other shards' pixels.  The multi-device handle
+    // copies exactly its own pixels back this way (api.cu); 0 = the full row-major width * height * 3 image.
+    uint32_t compact, _pad;
 };
 
 // chunk = max(64, ceil(iterations / 32)) samples, so at most 32 chunks

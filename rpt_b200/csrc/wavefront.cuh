@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_TRACE_MIN_BLOCKS) wf_trace_kern
     const R tmin = (R)1e-12;
     const uint32_t total = b.count[0];
     const uint32_t lane = threadIdx.x & 31u;
-    TravStats ts = {0, 0, 0};
+    TravStats ts = {0, 0, 0, 0, 0};
 
     bool have = false, exhausted = false;
     uint32_t slot = 0;
@@ -731,7 +731,7 @@ __global__ void wf_finish_kernel(const RenderArgs<float> a, const WfBuffers b) {
     if (x >= a.width || y >= a.height) return;
     const WfPath& st = b.paths[p];
     const double it = (double)a.iterations;
-    float* out = a.out + 3 * ((size_t)y * a.width + x);
+    float* out = a.out + 3 * (a.compact ? (size_t)p : (size_t)y * a.width + x);  // path p of a one-chunk render = pixel slot p
     out[0] = (float)(st.acc[0] / it * (double)a.exposure_scale);
     out[1] = (float)(st.acc[1] / it * (double)a.exposure_scale);
     out[2] = (float)(st.acc[2] / it * (double)a.exposure_scale);

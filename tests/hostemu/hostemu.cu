@@ -45,7 +45,7 @@ void occluded(const SceneView<R>& sv, const double* rays, const double* tmax, ui
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; i++) {
         const double* r = rays + 6 * i;
-        TravStats ts = {0, 0, 0};
+        TravStats ts = {0, 0, 0, 0, 0};
         Hit<R> h;
         h.t = (R)tmax[i];
         closest_hit<R, false, FEAT>(sv, mk((R)r[0], (R)r[1], (R)r[2]), mk((R)r[3], (R)r[4], (R)r[5]), (R)tmin, true, h, ts);
@@ -56,13 +56,13 @@ void occluded(const SceneView<R>& sv, const double* rays, const double* tmax, ui
 template <class R, int FEAT>
 void closest_hits(const SceneView<R>& sv, const double* rays, uint64_t n, double tmin, double* out_t, int32_t* out_obj,
                   double* out_n, rptb_stats* stats) {
-    unsigned long long nv = 0, tt = 0, ot = 0;
-#pragma omp parallel for schedule(static) reduction(+ : nv, tt, ot)
+    unsigned long long nv = 0, tt = 0, ot = 0, bn = 0, bt = 0;
+#pragma omp parallel for schedule(static) reduction(+ : nv, tt, ot, bn, bt)
     for (int64_t i = 0; i < (int64_t)n; i++) {  // body of closest_hit_kernel (integrator.cuh)
         const double* r = rays + 6 * i;
         const Vec3<R> o = {(R)r[0], (R)r[1], (R)r[2]};
         const Vec3<R> d = {(R)r[3], (R)r[4], (R)r[5]};
-        TravStats ts = {0, 0, 0};
+        TravStats ts = {0, 0, 0, 0, 0};
         Hit<R> h;
         h.t = M<R>::inf();
         closest_hit<R, true, FEAT>(sv, o, d, (R)tmin, false, h, ts);
@@ -78,6 +78,8 @@ void closest_hits(const SceneView<R>& sv, const double* rays, uint64_t n, double
         nv += ts.node_visits;
         tt += ts.tri_tests;
         ot += ts.object_tests;
+        bn += ts.bvh_nodes;
+        bt += ts.bvh_tris;
     }
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -85,6 +87,8 @@ void closest_hits(const SceneView<R>& sv, const double* rays, uint64_t n, double
         stats->node_visits = nv;
         stats->tri_tests = tt;
         stats->object_tests = ot;
+        stats->bvh_node_visits = bn;
+        stats->bvh_tri_tests = bt;
     }
 }
 
@@ -139,14 +143,22 @@ void run_grid(const SceneView<R>& sv, const RenderArgs<R>& a) {
 // The instantiation launch_render_impl (launch_impl.cuh) would launch for these features -- keep in step with it.
 // Returns the FEAT it ran.
 template <class R>
-int run_render(const SceneView<R>& sv, const RenderArgs<R>& a, bool stats, int features) {
+int run_render(const SceneView<R>& sv, const RenderArgs<R>& a, int stats, int features) {  // launch_render_impl's dispatch
     const int base = features & F_ALL;
     const bool small = (features & F_SMALL) != 0, ext = (features & F_EXT) != 0;
     if (a.max_bounces > 16) {
+        if constexpr (!M<R>::literal)
+            if ((features & F_BVH) && stats != 2) {
+                if (stats) run_grid<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY | F_BVH>(sv, a);
+                else run_grid<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY | F_BVH>(sv, a);
+                return F_EVERY | F_BVH;
+            }
         if (stats) run_grid<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY>(sv, a);
         else run_grid<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY>(sv, a);
         return F_EVERY;
     }
+    if constexpr (!M<R>::literal)
+        if (stats == 1 && (features & F_BVH)) { run_grid<R, 16, true, F_EVERY | F_BVH>(sv, a); return F_EVERY | F_BVH; }
     if (stats) { run_grid<R, 16, true, F_EVERY>(sv, a); return F_EVERY; }
     if constexpr (!M<R>::literal)
         if (ext && (features & F_BVH)) { run_grid<R, 16, false, F_EVERY | F_BVH>(sv, a); return F_EVERY | F_BVH; }
@@ -182,13 +194,14 @@ int render_impl(const SceneView<R>& sv, const rptb_camera* cam, const rptb_rende
     a.partial = partial.empty() ? nullptr : partial.data();
     a.counters = &counters;
     int feat = -1;
-    if (a.ntiles_mine > 0) feat = run_render<R>(sv, a, p->collect_stats != 0, features);
+    if (a.ntiles_mine > 0) feat = run_render<R>(sv, a, (int)p->collect_stats, features);
     for (size_t i = 0; i < nvals; i++) out_rgb[i] = (double)out[i];
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->segments = counters.segments; stats->rays = counters.rays; stats->node_visits = counters.node_visits;
         stats->tri_tests = counters.tri_tests; stats->mesh_hits = counters.mesh_hits; stats->env_lookups = counters.env_lookups;
         stats->object_tests = counters.object_tests;
+        stats->bvh_node_visits = counters.bvh_node_visits; stats->bvh_tri_tests = counters.bvh_tri_tests;
         stats->engine = RPTB_ENGINE_MEGAKERNEL;
     }
     return feat;

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header_sizes(tmp_path):
         assert int(got[n]) == C.sizeof(t), n
     # and the sizes the docs quote
     assert C.sizeof(capi.Material) == 64 and C.sizeof(capi.KdNode) == 32 and C.sizeof(capi.Camera) == 96
-    assert C.sizeof(capi.RenderParams) == 64 and C.sizeof(capi.Stats) == 72
+    assert C.sizeof(capi.RenderParams) == 64 and C.sizeof(capi.Stats) == 88
     assert C.sizeof(capi.Object) == 16 + 128 + 32 + 16
 
 

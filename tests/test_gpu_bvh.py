@@ -56,11 +56,14 @@ def test_bvh_closest_hits_are_the_kd_trees(orc, pairs, name):
     same = (tb == tk) & (ob == ok)
     assert same.mean() >= 0.9999, same.mean()
     assert np.abs(nb[same] - nk[same]).max() <= 1e-6
-    # with counters the query goes through the reference-shaped tree on both scenes: identical, counters too
+    # with counters each scene counts the structure it traverses: same answers as without, its own counters
     t1, o1, n1, s1 = kd.closest_hit(rays, precision=F32, want_stats=True)
     t2, o2, n2, s2 = bvh.closest_hit(rays, precision=F32, want_stats=True)
-    np.testing.assert_array_equal(t1, t2)
-    assert s1["node_visits"] == s2["node_visits"] and s1["tri_tests"] == s2["tri_tests"]
+    np.testing.assert_array_equal(t1, tk)
+    np.testing.assert_array_equal(t2, tb)
+    assert s1["node_visits"] > 0 and s1["tri_tests"] > 0 and s1["bvh_node_visits"] == 0 and s1["bvh_tri_tests"] == 0
+    assert s2["node_visits"] == 0 and s2["tri_tests"] == 0
+    assert 0 < s2["bvh_node_visits"] < 0.5 * s1["node_visits"] and 0 < s2["bvh_tri_tests"] < 0.1 * s1["tri_tests"]
     # the f64 gate ignores the BVH
     t3, o3, _ = bvh.closest_hit(rays[:20000], precision=F64)
     t0, o0, _, _ = orc.OracleScene(bvh.flat).closest_hit(rays[:20000])
@@ -111,10 +114,19 @@ def test_bvh_shards_and_stats_pass(pairs):
         np.testing.assert_array_equal(parts[0] + parts[1], full)
     # the counting pass walks the reference-shaped trees (its counters are SURVEY 8d's algorithmic work):
     # same counters as the kd scene, image equal to the kd scene's counting pass
-    a, sa = _render(cfg, kd, w, h, spp, mb, 5, capi.ENGINE_MEGAKERNEL, stats=1)
-    b, sb = _render(cfg, bvh, w, h, spp, mb, 5, capi.ENGINE_MEGAKERNEL, stats=1)
+    a, sa = _render(cfg, kd, w, h, spp, mb, 5, capi.ENGINE_MEGAKERNEL, stats=2)
+    b, sb = _render(cfg, bvh, w, h, spp, mb, 5, capi.ENGINE_MEGAKERNEL, stats=2)
     np.testing.assert_array_equal(a, b)
     assert sa["node_visits"] == sb["node_visits"] > 0 and sa["tri_tests"] == sb["tri_tests"] > 0
+    assert sb["bvh_node_visits"] == 0
+    # collect_stats = 1 counts what the product path traverses on THIS scene: the BVH (rptb_stats::bvh_*), and the
+    # image is the BVH image (another instantiation of the same code: equal up to FMA contraction)
+    c, sc = _render(cfg, bvh, w, h, spp, mb, 5, capi.ENGINE_MEGAKERNEL, stats=1)
+    plain, sp = _render(cfg, bvh, w, h, spp, mb, 5, capi.ENGINE_MEGAKERNEL)
+    assert sc["node_visits"] == 0 and sc["segments"] == sp["segments"] and sc["rays"] == sp["rays"]
+    assert 0 < sc["bvh_node_visits"] < 0.5 * sb["node_visits"] and 0 < sc["bvh_tri_tests"] < 0.1 * sb["tri_tests"]
+    rel = np.abs(c - plain) / np.maximum(np.abs(plain), 1e-4)
+    assert np.quantile(rel.max(axis=1), 0.99) < 1e-4
 
 
 def test_bvh_device_bytes_and_env_override(pairs, monkeypatch):

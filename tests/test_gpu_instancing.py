@@ -114,7 +114,12 @@ def test_stats_kernel_and_plain_kernel_agree(cfgs):
     a, _ = _gpu_render(cfg, ds, w, h, spp, mb, 3, F32, stats=0)
     b, st = _gpu_render(cfg, ds, w, h, spp, mb, 3, F32, stats=1)
     np.testing.assert_array_equal(a, b)
-    assert st["node_visits"] > 0 and st["tri_tests"] > 0 and st["object_tests"] > st["rays"]
+    # the group's kd-tree over the instances counts as kd nodes; the instances' triangles are reached through the BVH
+    assert st["node_visits"] > 0 and st["bvh_tri_tests"] > 0 and st["bvh_node_visits"] > 0 and st["object_tests"] > st["rays"]
+    c, st2 = _gpu_render(cfg, ds, w, h, spp, mb, 3, F32, stats=2)   # the reference-shaped trees all the way down
+    assert st2["tri_tests"] > st["bvh_tri_tests"] and st2["bvh_node_visits"] == 0
+    rel = np.abs(c - a) / np.maximum(np.abs(a), 1e-4)
+    assert np.quantile(rel.max(axis=1), 0.99) < 1e-4
 
 
 @pytest.mark.parametrize("precision", [F32, F64])

@@ -152,7 +152,8 @@ def test_bvh_finds_the_hits_of_the_reference_tree(orc, name):
     same = (tb == tk) & (ob == ok)
     assert same.mean() >= 0.9999
     assert np.abs(nb[same] - nk[same]).max() <= 1e-6
-    assert sb["node_visits"] < 0.5 * sk["node_visits"] and sb["tri_tests"] < 0.1 * sk["tri_tests"]
+    assert sb["node_visits"] == 0 and sb["tri_tests"] == 0 and sk["bvh_node_visits"] == 0   # each structure has its own counters
+    assert 0 < sb["bvh_node_visits"] < 0.5 * sk["node_visits"] and 0 < sb["bvh_tri_tests"] < 0.1 * sk["tri_tests"]
     # and against the oracle, the usual f32 tolerances
     t0, o0, n0, _ = orc.OracleScene(api.FlatScene(cfg.scene)).closest_hit(rays)
     agree = ob == o0
@@ -163,7 +164,7 @@ def test_bvh_finds_the_hits_of_the_reference_tree(orc, name):
     # f64 never uses it
     tb64, ob64, _, s64 = eb.closest_hit(rays, precision=capi.PRECISION_F64)
     np.testing.assert_array_equal(tb64, t0)
-    assert s64["tri_tests"] == sk["tri_tests"] or s64["tri_tests"] > sb["tri_tests"]
+    assert s64["tri_tests"] == sk["tri_tests"] or s64["tri_tests"] > sb["bvh_tri_tests"]
 
 
 def test_bvh_builder_on_awkward_meshes():
@@ -234,7 +235,7 @@ def test_bvh_under_a_kd_tree_of_shapes(orc):
     tk, ok, nk, sk = ek.closest_hit(rays, precision=capi.PRECISION_F32)
     same = (tb == tk) & (ob == ok)
     assert same.mean() >= 0.9999 and np.abs(nb[same] - nk[same]).max() <= 1e-6
-    assert sb["tri_tests"] < 0.2 * sk["tri_tests"]
+    assert 0 < sb["bvh_tri_tests"] < 0.2 * sk["tri_tests"]
     t0, o0, _, _ = orc.OracleScene(api.FlatScene(cfg.scene)).closest_hit(rays)
     assert (ob == o0).mean() > 0.9995
 
@@ -294,10 +295,16 @@ def test_megakernel_counting_variant_and_counters(orc):
     # shadow rays are any-hit queries on the device: never more traversal work than the reference's closest-hit
     assert sa["node_visits"] <= st0["node_visits"] and sa["tri_tests"] <= st0["tri_tests"]
     assert sa["object_tests"] == st0["object_tests"] or sa["object_tests"] <= st0["object_tests"]
-    b, sb, fb = e.render(cfg.camera, _params(cfg, 48, 27, 4, 2, collect_stats=1))   # f32 counting pass vs f32 BVH pass
+    b, sb, fb = e.render(cfg.camera, _params(cfg, 48, 27, 4, 2, collect_stats=2))   # f32 counting pass over the kd-trees vs f32 BVH pass
     c, sc, fc = e.render(cfg.camera, _params(cfg, 48, 27, 4, 2))
     assert fb == 7 | F_GROUP | F_MONO and fc == F_TREE | 64
     assert sb["segments"] == sc["segments"] and np.abs(b - c).max() <= 1e-5 * max(1.0, np.abs(b).max())
+    assert sb["node_visits"] > 0 and sb["bvh_node_visits"] == 0
+    # collect_stats = 1 counts the structure the product path traverses: the BVH, and the image is the BVH image bit for bit
+    d, sd, fd = e.render(cfg.camera, _params(cfg, 48, 27, 4, 2, collect_stats=1))
+    assert fd == 7 | F_GROUP | F_MONO | 64 and sd["node_visits"] == 0
+    assert 0 < sd["bvh_node_visits"] < sb["node_visits"] and 0 < sd["bvh_tri_tests"] < 0.2 * sb["tri_tests"]
+    np.testing.assert_array_equal(d, c)
 
 
 def test_megakernel_chunks_shards_and_sample_ranges(orc):

@@ -122,3 +122,51 @@ def golden_config(name):
     if name == "monomial_glass":
         return scenes.monomial_glass_scene(128, 64)
     return scenes.CONFIGS[name]()
+
+
+# ---- SURVEY 8(d) parity criterion at full size -----------------------------------------------------------------
+class Moments:
+    """Per-pixel, per-channel mean and variance-of-the-mean of a render delivered as equally weighted batches --
+    the reference's own mechanism: Renderer::iterative_render appends one entry per pixel per `sample()` call and
+    Buffer::variance reads the spread of those entries (src/renderer.rs:103-115, src/buffer.rs:59-73)."""
+
+    def __init__(self, npix):
+        self.n = 0
+        self.s1 = np.zeros((npix, 3))
+        self.s2 = np.zeros((npix, 3))
+
+    def add(self, batch):
+        self.n += 1
+        self.s1 += batch
+        self.s2 += batch * batch
+
+    @property
+    def mean(self):
+        return self.s1 / self.n
+
+    @property
+    def var_of_mean(self):
+        n = self.n
+        s2 = np.maximum(self.s2 - self.s1 * self.s1 / n, 0.0) / (n - 1)  # unbiased sample variance of the batches
+        return s2 / n
+
+
+def z_outlier_fraction(a: "Moments", b: "Moments", z_limit=4.0):
+    """Fraction of pixels where some channel has |mu_a - mu_b| / sqrt(var_a/N + var_b/N) beyond z_limit.  With few
+    batches the statistic is Student-t, not normal: it is mapped through Welch's degrees of freedom to the normal
+    quantile with the same tail probability, so `z_limit` keeps its meaning for any batch count.  A rounding floor
+    (1e-5 relative) keeps pixels that are constant on both sides (environment, 0 variance) from dividing by 0."""
+    from scipy import stats as sps
+
+    d = a.mean - b.mean
+    va, vb = a.var_of_mean, b.var_of_mean
+    floor = (1e-5 * np.maximum(np.maximum(np.abs(a.mean), np.abs(b.mean)), 1e-3)) ** 2
+    v = va + vb + floor
+    t = np.abs(d) / np.sqrt(v)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dof = v * v / (va * va / (a.n - 1) + vb * vb / (b.n - 1) + 1e-300)
+    dof = np.clip(np.nan_to_num(dof, nan=1e9, posinf=1e9), 1.0, 1e9)
+    p = 2.0 * sps.t.sf(t, dof)
+    p_limit = 2.0 * sps.norm.sf(z_limit)
+    bad = (p < p_limit).any(axis=1)
+    return float(bad.mean()), t

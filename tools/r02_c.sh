@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-2 third GPU call: the whole GPU suite with the new tests, a fresh Cornell capture, BVH occupancy sweep
+set -u
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/r02c_suite.log 2>&1; echo "suite exit $?" >> gpurun_out/r02c_suite.log
+for tag in main bvh4 bvh5 bvh8; do
+  lib=rpt_b200/lib/librpt_b200_$tag.so; [ $tag = main ] && lib=rpt_b200/lib/librpt_b200.so
+  for wl in teapot dragon; do
+    RPTB_LIB=$PWD/$lib timeout 300 python bench.py --workload $wl --spp 64 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02c_sweep_${wl}_$tag.json 2> gpurun_out/r02c_sweep_${wl}_$tag.err
+  done
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 1 -c 1 -f -o gpurun_out/r02c_cornell \
+    python bench.py --spp 32 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r02c_ncu_cornell.log 2>&1
+ls -la gpurun_out | tail -20
