@@ -269,7 +269,10 @@ public:
     Renderer& max_bounces(uint32_t v) { max_bounces_ = v; return *this; }
     Renderer& num_samples(uint32_t v) { num_samples_ = v; return *this; }
     Renderer& seed(uint64_t v) { seed_ = v; return *this; }
-    Renderer& device(int d) { device_ = d; return *this; }
+    Renderer& device(int d) { device_ = d; ngpus_ = 1; return *this; }
+    // Renderer::sample fans out over GPUs 0..n-1 behind the same call (rptb_scene_create_multi); the image is
+    // bit-identical for any n.  The reference's fan-out is rayon over rows inside `sample` (src/renderer.rs:118-127).
+    Renderer& gpus(int n) { ngpus_ = n < 1 ? 1 : n; device_ = 0; return *this; }
 
     std::vector<uint8_t> render() {  // :96-100
         Buffer buffer(width_, height_, filter_);
@@ -377,7 +380,8 @@ private:
         d.groups = groups.data(); d.ngroups = (uint32_t)groups.size();
         d.environment.kind = RPTB_ENV_COLOR;
         d.environment.color[0] = scene_.environment.x; d.environment.color[1] = scene_.environment.y; d.environment.color[2] = scene_.environment.z;
-        if (rptb_scene_create(&d, device_, &handle_) != RPTB_OK) throw std::runtime_error(rptb_last_error());
+        const int rc = ngpus_ > 1 ? rptb_scene_create_multi(&d, nullptr, ngpus_, &handle_) : rptb_scene_create(&d, device_, &handle_);
+        if (rc != RPTB_OK) throw std::runtime_error(rptb_last_error());
     }
 
     const Scene& scene_;
@@ -386,7 +390,7 @@ private:
     double ev_ = 0.0;
     Filter filter_;
     uint64_t seed_ = 0, next_sample_ = 0;
-    int device_ = 0;
+    int device_ = 0, ngpus_ = 1;
     rptb_scene* handle_ = nullptr;
 };
 

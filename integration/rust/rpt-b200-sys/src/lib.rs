@@ -8,7 +8,7 @@
 //! | RptbKdNode | 32 | | RptbSceneDesc | 128 |
 //! | RptbMesh | 48 | | RptbCamera | 96 |
 //! | RptbObject | 192 | | RptbRenderParams | 64 |
-//! | RptbGroup | 48 | | RptbStats | 72 |
+//! | RptbGroup | 48 | | RptbStats | 88 |
 //! | RptbLight | 248 | | RptbKdTreeOut | 40 |
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
@@ -186,6 +186,8 @@ pub struct RptbStats {
     pub gpu_ms: f64,
     pub launches: u32,
     pub engine: u32,
+    pub bvh_node_visits: u64,
+    pub bvh_tri_tests: u64,
 }
 
 #[repr(C)]
@@ -209,6 +211,10 @@ extern "C" {
     pub fn rptb_last_error() -> *const c_char;
     pub fn rptb_device_count() -> c_int;
     pub fn rptb_scene_create(desc: *const RptbSceneDesc, device: c_int, out: *mut *mut RptbScene) -> c_int;
+    /// The scene replicated on `ndevices` GPUs (`devices` null = 0..ndevices-1): `rptb_render_samples` then fans
+    /// out over them -- the rayon loop of `Renderer::sample` (src/renderer.rs:117-129) behind the same call.
+    pub fn rptb_scene_create_multi(desc: *const RptbSceneDesc, devices: *const c_int, ndevices: c_int, out: *mut *mut RptbScene) -> c_int;
+    pub fn rptb_scene_device_count(scene: *const RptbScene) -> c_int;
     pub fn rptb_scene_destroy(scene: *mut RptbScene);
     pub fn rptb_scene_device_bytes(scene: *const RptbScene) -> u64;
     pub fn rptb_render_samples(
@@ -236,6 +242,17 @@ extern "C" {
         out_object: *mut i32,
         out_normal: *mut f64, // nullable, n x 3
         stats: *mut RptbStats,
+    ) -> c_int;
+    pub fn rptb_illuminate(
+        scene: *mut RptbScene,
+        light: u32,
+        pos: *const f64, // n x 3
+        n: u64,
+        seed: u64,
+        precision: u32,
+        out_intensity: *mut f64, // n x 3
+        out_wi: *mut f64,        // n x 3
+        out_dist: *mut f64,      // n
     ) -> c_int;
     pub fn rptb_build_kdtree(tris: *const f64, ntris: u64, out: *mut RptbKdTreeOut) -> c_int;
     pub fn rptb_build_kdtree_boxes(boxes: *const f64, nboxes: u64, out: *mut RptbKdTreeOut) -> c_int;
@@ -282,7 +299,7 @@ mod tests {
         assert_eq!(size_of::<RptbSceneDesc>(), 128);
         assert_eq!(size_of::<RptbCamera>(), 96);
         assert_eq!(size_of::<RptbRenderParams>(), 64);
-        assert_eq!(size_of::<RptbStats>(), 72);
+        assert_eq!(size_of::<RptbStats>(), 88);
         assert_eq!(size_of::<RptbKdTreeOut>(), 40);
     }
 }

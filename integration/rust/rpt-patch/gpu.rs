@@ -259,14 +259,34 @@ unsafe impl Sync for GpuScene {}
 
 impl GpuScene {
     pub fn new(scene: &Scene, device: i32) -> Result<Self, String> {
+        Self::on_devices(scene, &[device])
+    }
+
+    /// The scene replicated on every GPU of the box (`rptb_device_count`): what `Renderer::sample` wants by
+    /// default -- its rayon loop over rows (src/renderer.rs:118-127) becomes one host thread per GPU inside
+    /// `rptb_render_samples`, each GPU owning the pixel tiles `t % n == i`; same image for any `n`.
+    pub fn on_all_gpus(scene: &Scene) -> Result<Self, String> {
+        let n = unsafe { sys::rptb_device_count() };
+        if n <= 0 {
+            return Err(sys::last_error());
+        }
+        let devices: Vec<i32> = (0..n).collect();
+        Self::on_devices(scene, &devices)
+    }
+
+    pub fn on_devices(scene: &Scene, devices: &[i32]) -> Result<Self, String> {
         let mut flat = FlatScene::new(scene)?;
         let desc = flat.desc(scene);
         let mut handle = std::ptr::null_mut();
-        let rc = unsafe { sys::rptb_scene_create(&desc, device, &mut handle) };
+        let rc = unsafe { sys::rptb_scene_create_multi(&desc, devices.as_ptr(), devices.len() as i32, &mut handle) };
         if rc != sys::RPTB_OK {
             return Err(sys::last_error());
         }
-        Ok(GpuScene { handle }) // `flat` may die now: the library copied everything to the device
+        Ok(GpuScene { handle }) // `flat` may die now: the library copied everything to the device(s)
+    }
+
+    pub fn device_count(&self) -> i32 {
+        unsafe { sys::rptb_scene_device_count(self.handle) }
     }
 
     /// What `Renderer::get_color` returns for every pixel: mean of `iterations` samples x 2^EV,
