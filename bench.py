@@ -8,9 +8,15 @@ Msamples/s = path segments, i.e. trace_ray invocations, per second).
                                                              # reference is Rust, no rustc here)
 
 A "step" is one pass of Renderer::sample over one batch: the BASELINE configs[1] workload,
-Cornell box 800x800, 512 spp per GPU, max_bounces 6 (at N GPUs the image gets 512*N spp and
-every GPU renders 1/N of the pixel tiles: per-GPU work is fixed => weak scaling), followed
-by the single all-reduce of the float3 buffer when N > 1.  Prints ONE JSON line on rank 0.
+Cornell box 800x800, 512 spp per GPU, max_bounces 6.  At N GPUs the image gets 512*N spp and every
+GPU renders 1/N of the 16x8 pixel tiles (per-GPU work fixed => weak scaling) into a compact
+tile-major buffer; ONE all-gather of those shards (NCCL) and a fixed permutation assemble the float3
+image on every rank.  Prints ONE JSON line on rank 0.
+
+Besides the headline (`value`, `e2e`, `roofline`, `cpu_baseline`) the line carries `secondary`: the two BASELINE
+configs quoted on 8 GPUs -- dragon (1920x1080, 1024 spp, max_bounces 2) and glass (1920x1080, 4096 spp,
+max_bounces 12) -- rendered ONCE each at their full size with the pixel tiles split over the N ranks (fixed total
+work => strong scaling), device-timed, with the HBM roofline of the BVH traffic on the dragon.
 """
 from __future__ import annotations
 
@@ -31,6 +37,8 @@ if ROOT not in sys.path:
 
 METRIC = "Msamples/s (path segments = trace_ray invocations per second)"
 UNIT = "Msamples/s"
+CPU_SPP_PER_STEP = 16  # samples per pixel of one CPU-arm step (full resolution, full max_bounces)
+KEYS = ["segments", "rays", "node_visits", "tri_tests", "mesh_hits", "env_lookups", "object_tests", "bvh_node_visits", "bvh_tri_tests"]
 
 
 def parse_args():
@@ -41,12 +49,13 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cornell",
                     choices=["sphere", "cornell", "teapot", "dragon", "glass",
-                             "fractal_spheres", "fractal_teapots", "monomial_glass"],  # the last three: exploration only
+                             "fractal_spheres", "fractal_teapots", "monomial_glass", "dragon_knot"],  # the last four: exploration only
                     help="default = the BASELINE configs[1] workload; anything else is for exploration / profiling")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (exploration only)")
     ap.add_argument("--engine", default="auto", choices=["auto", "megakernel", "wavefront"], help="rptb_engine (exploration only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the dragon / glass strong-scaling block")
     return ap.parse_args()
 
 
@@ -59,8 +68,9 @@ def workload(name: str, spp_override: int = 0):
     return cfg
 
 
-def config_dict(cfg, world: int, extra=None):
-    d = {
+def config_dict(cfg, world: int):
+    """The same dictionary in both arms (the CPU arm renders a bounded sample of exactly this workload)."""
+    return {
         "workload": "%s %dx%d, %d spp per GPU (%d total), max_bounces %d; %s" % (
             cfg.name, cfg.width, cfg.height, cfg.spp, cfg.spp * world, cfg.max_bounces, cfg.note),
         "scene": cfg.name,
@@ -69,13 +79,10 @@ def config_dict(cfg, world: int, extra=None):
         "spp_per_gpu": cfg.spp,
         "spp_total": cfg.spp * world,
         "max_bounces": cfg.max_bounces,
-        "parallelism": "pixel tiles 16x8 round-robin over %d GPU(s); one all-reduce(sum) of the float3 buffer" % world,
+        "parallelism": "pixel tiles 16x8 round-robin over %d GPU(s); one all-gather of the ranks' own tiles (1/N of the float3 image each)" % world,
         "rng": "Philox4x32-10 keyed (seed=1, pixel, sample)",
-        "cache": "L2 flushed between timed steps (256 MiB memset); the scene itself is < 1 MiB and cache-resident by nature",
+        "cache": "L2 flushed between timed steps (256 MiB memset); the Cornell scene itself is 4 KiB and cache-resident by nature",
     }
-    if extra:
-        d.update(extra)
-    return d
 
 
 # ------------------------------------------------------------------ clocks ------------
@@ -92,7 +99,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -138,113 +145,108 @@ class ClockSampler:
 # ------------------------------------------------------------------ roofline ----------
 def algorithmic_bytes(stats: dict, pixels: int) -> float:
     """SURVEY 8(d) per-unit figures with this repo's device layout:
-    64 B object record per Shape::intersect dispatch, 8 B per kd node visited, 4 + 48 B per
-    triangle test (leaf ref + packed triangle), 36 B vertex normals per mesh hit, 32 B
-    material per segment (<= one fetch), 64 B (4 texels x 16 B) per HDRI lookup, 12 B per
-    pixel written."""
+    64 B object record per Shape::intersect dispatch; the structure that was traversed -- 64 B per BVH node fetched
+    (both child boxes) and 48 + 4 B per triangle tested in a BVH leaf, or 8 B per kd node and 4 + 48 B per triangle
+    test on a kd-tree scene; 36 B vertex normals per mesh hit; 32 B material per segment; 64 B (4 texels x 16 B)
+    per HDRI lookup; 12 B per pixel written."""
     return (64.0 * stats["object_tests"] + 8.0 * stats["node_visits"] + 52.0 * stats["tri_tests"]
             + 64.0 * stats.get("bvh_node_visits", 0) + 52.0 * stats.get("bvh_tri_tests", 0)
             + 36.0 * stats["mesh_hits"] + 32.0 * stats["segments"] + 64.0 * stats["env_lookups"] + 12.0 * pixels)
+
+
+BYTES_MODEL = ("64*object_tests + 64*bvh_node_visits + 52*bvh_tri_tests + 8*node_visits + 52*tri_tests + 36*mesh_hits + "
+               "32*segments + 64*env_lookups + 12*pixels (counters of the structure that rendered the step: collect_stats = 1)")
 
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
 
 
-def ncu_traffic(workload_name: str, spp: int, engine: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-    committed ncu capture (profiles/ncu_traffic.json); megakernel launches are scaled from the
-    capture's spp to the workload's (their DRAM traffic is per-sample local-memory traffic)."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+def ncu_record(workload_name: str):
+    """Per-launch figures of the dominant kernel from the committed `ncu --set full` capture of this round
+    (profiles/ncu_kernels.json, written by tools/ncu_kernels_json.py): dram bytes, warp and thread instructions and
+    the segments the captured launch traced -- the per-segment ratios are properties of the kernel."""
     try:
-        rec = json.load(open(path)).get(workload_name)
-        if not isinstance(rec, dict):
-            return None
-        b = float(rec["dram_bytes_per_launch"])
-        if (workload_name == "dragon-proxy") != (engine == 2):
-            return None  # the dragon record is a wavefront trace launch; no capture of the megakernel on that workload yet
-        return b if engine == 2 else b * spp / float(rec["capture_spp"])
+        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernels.json"))).get(workload_name)
+        return rec if isinstance(rec, dict) else None
     except Exception:
         return None
 
 
 # ------------------------------------------------------------------ CPU arm -----------
-def host_threads() -> int:
+def host_cores():
+    """Threads this process may really use: the scheduler affinity, capped by the cgroup CPU quota (a GPU box
+    reports 128 CPUs and grants 16 of them)."""
     try:
-        return len(os.sched_getaffinity(0))
+        aff = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        pass
+    used = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return used, aff, quota
 
 
-def oracle_rate(cfg, budget_s: float = 15.0):
-    """Time the CPU restatement of the same workload on all host threads, on a bounded
-    sample: whole-resolution renders at reduced spp (the rate is spp-independent)."""
+def cpu_arm(cfg, steps: int, warmup: int, budget_s: float = None):
+    """The CPU restatement of the same workload on all usable host threads: every step renders CPU_SPP_PER_STEP
+    samples per pixel of the full-resolution image (the rate does not depend on spp).  With `budget_s`, stops early
+    once that much time has been spent (cpu_baseline leg of the native arm)."""
     from oracle import oracle_py as orc
     from rpt_b200 import api
 
     flat = api.FlatScene(cfg.scene)
     osc = orc.OracleScene(flat)
     r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces).seed(1)
-    cores = host_threads()
-    t0 = time.perf_counter()
-    _, st = osc.render(cfg.camera, r.params(1), nthreads=cores)
-    t1 = time.perf_counter() - t0
-    spp = 1
-    segs, secs = st["segments"], t1
-    if t1 < budget_s / 2:
-        spp = int(max(1, min(96, math.floor(budget_s / max(t1, 1e-3)) - 1)))
+    cores, aff, quota = host_cores()
+    first = 0
+    for _ in range(warmup):
+        osc.render(cfg.camera, r.params(1, first), nthreads=cores)
+        first += 1
+    segs, t, done = 0, 0.0, 0
+    for _ in range(steps):
         t0 = time.perf_counter()
-        _, st = osc.render(cfg.camera, r.params(spp, first_sample=1), nthreads=cores)
-        secs = time.perf_counter() - t0
-        segs = st["segments"]
-    return {
-        "value": segs / secs / 1e6,
-        "unit": UNIT,
-        "cores": cores,
-        "kind": "port",
-        "sample": "%s %dx%d, %d of %d spp, max_bounces %d: %d segments in %.2f s (rpt-restated C++ f64 oracle, "
-                  "OpenMP over rows; rpt itself is Rust and cannot be built here)" % (
-                      cfg.name, cfg.width, cfg.height, spp, cfg.spp, cfg.max_bounces, segs, secs),
-    }
+        _, st = osc.render(cfg.camera, r.params(CPU_SPP_PER_STEP, first), nthreads=cores)
+        t += time.perf_counter() - t0
+        first += CPU_SPP_PER_STEP
+        segs += st["segments"]
+        done += 1
+        if budget_s is not None and t >= budget_s:
+            break
+    value = segs / t / 1e6
+    sample = ("%s %dx%d, max_bounces %d: %d step(s) of %d spp (of %d) at full resolution = %d segments in %.2f s; "
+              "rpt-restated C++ f64 oracle, OpenMP over rows on %d threads (affinity %d, cgroup quota %s); rpt itself is Rust and "
+              "cannot be built here" % (cfg.name, cfg.width, cfg.height, cfg.max_bounces, done, CPU_SPP_PER_STEP, cfg.spp, segs, t,
+                                        cores, aff, "none" if quota is None else "%.1f" % quota))
+    return {"value": value, "unit": UNIT, "cores": cores, "cores_affinity": aff, "cgroup_cpu_quota": quota, "kind": "port",
+            "sample": sample, "steps": done, "seconds": t}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle_py as orc
-    from rpt_b200 import api
-
     cfg = workload(args.workload, args.spp)
-    flat = api.FlatScene(cfg.scene)
-    osc = orc.OracleScene(flat)
-    r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces).seed(1)
-    cores = host_threads()  # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
-    sample_spp = 1  # one sample per pixel of the full-resolution image per step
-    for i in range(args.warmup):
-        osc.render(cfg.camera, r.params(sample_spp, first_sample=i), nthreads=cores)
-    segs, t = 0, 0.0
-    for i in range(args.steps):
-        t0 = time.perf_counter()
-        _, st = osc.render(cfg.camera, r.params(sample_spp, first_sample=args.warmup + i), nthreads=cores)
-        t += time.perf_counter() - t0
-        segs += st["segments"]
-    value = segs / t / 1e6
-    sample = "%s %dx%d, %d of %d spp per step, max_bounces %d (rpt-restated C++ f64 oracle on %d host threads)" % (
-        cfg.name, cfg.width, cfg.height, sample_spp, cfg.spp, cfg.max_bounces, cores)
+    res = cpu_arm(cfg, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1), "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / max(res["steps"], 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(cfg, args.gpus, {"note_reference": "CPU path; n_gpus is echoed, no GPU is used"}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": config_dict(cfg, args.gpus),
+        "note": "CPU path (n_gpus is echoed, no GPU is used); each step is a bounded sample of the workload, see cpu_baseline.sample",
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "cores_affinity", "cgroup_cpu_quota", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
@@ -268,7 +270,7 @@ def run_native(args):
 
     from rpt_b200 import _capi as capi
     from rpt_b200 import api
-    from rpt_b200.distributed import render_shard_device
+    from rpt_b200 import distributed as D
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -278,44 +280,73 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    cfg = workload(args.workload, args.spp)
-    spp_total = cfg.spp * world
-    r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces) \
-        .seed(1).device(local).engine({"auto": capi.ENGINE_AUTO, "megakernel": capi.ENGINE_MEGAKERNEL, "wavefront": capi.ENGINE_WAVEFRONT}[args.engine])
-    flat = api.FlatScene(cfg.scene)
-    npix = cfg.width * cfg.height
+    engine = {"auto": capi.ENGINE_AUTO, "megakernel": capi.ENGINE_MEGAKERNEL, "wavefront": capi.ENGINE_WAVEFRONT}[args.engine]
     stream = torch.cuda.Stream(dev)
+    raw = stream.cuda_stream
     K, W = args.steps, args.warmup
+    peak, peak_src, sm_max_mhz = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
 
+    def allsum(vals, dtype=torch.int64):
+        t = torch.tensor(vals, dtype=dtype, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return t.tolist()
+
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    class Job:
+        """One workload on this rank: renderer, compact shard buffer, gather permutation."""
+
+        def __init__(self, cfg, spp_total):
+            self.cfg, self.spp_total = cfg, spp_total
+            self.r = api.Renderer(cfg.scene, cfg.camera).width(cfg.width).height(cfg.height).max_bounces(cfg.max_bounces) \
+                .seed(1).device(local).engine(engine)
+            self.npix = cfg.width * cfg.height
+            self.shard = torch.zeros(D.shard_tiles(cfg.width, cfg.height, 0, world) * 384, dtype=torch.float32, device=dev)
+            self.perm = torch.from_numpy(D.gather_permutation(cfg.width, cfg.height, world)).to(dev)
+            self.image = None
+
+        def render(self, stats=None, collect_stats=0, spp=None):
+            D.render_shard_device(self.r, spp or self.spp_total, self.shard, rank, world, 0, raw, stats=stats,
+                                  collect_stats=collect_stats, compact=True)
+
+        def assemble(self):
+            self.image = D.gather_tiles(lambda rk, wd: self.shard, self.cfg.width, self.cfg.height, self.perm)
+
+        def counters(self, spp=None):
+            st = capi.Stats()
+            self.render(st, 1, spp)
+            mine = st.as_dict()
+            tot = dict(zip(KEYS, [int(v) for v in allsum([mine[k] for k in KEYS])]))
+            return tot, int(st.launches), int(st.engine)
+
+        def close(self):
+            self.r.close()
+
     with torch.cuda.stream(stream):
-        out = torch.empty(npix * 3, dtype=torch.float32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        raw = stream.cuda_stream
+        cfg = workload(args.workload, args.spp)
+        job = Job(cfg, cfg.spp * world)
+        flat = api.FlatScene(cfg.scene)
+        npix = job.npix
+
+        # un-timed statistics pass: exact segment count of one step + the traversal counters of what renders it
+        total, launches_per_step, engine_used = job.counters()
+        launches_per_step += (1 if world > 1 else 0) + 1  # + NCCL all-gather kernel, + torch's index_select (the permutation)
 
         def step(ev_mid=None):
-            render_shard_device(r, spp_total, out, rank, world, 0, raw)
+            job.render()
             if ev_mid is not None:
                 ev_mid.record()
-            if world > 1:
-                dist.all_reduce(out)
-
-        # un-timed statistics pass: exact segment count of one step + traversal counters
-        st = capi.Stats()
-        render_shard_device(r, spp_total, out, rank, world, 0, raw, stats=st, collect_stats=1)
-        mine = st.as_dict()
-        keys = ["segments", "rays", "node_visits", "tri_tests", "mesh_hits", "env_lookups", "object_tests",
-                "bvh_node_visits", "bvh_tri_tests"]
-        tot = torch.tensor([mine[k] for k in keys], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot)
-        total = dict(zip(keys, [int(v) for v in tot.tolist()]))
-        launches_per_step = int(st.launches)
-        engine = int(st.engine)
+            job.assemble()
 
         for _ in range(W):
             step()
@@ -335,74 +366,137 @@ def run_native(args):
         barrier()
         t_wall = time.perf_counter() - t_wall
         clocks = sampler.stop() if sampler else None
-        step_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
-        kern_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
-        times = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        step_ms, kern_ms = [float(v) for v in times.tolist()]
-        image_mean = float(out.mean().item())
+        # per step: the slowest rank's kernel, the slowest rank's whole step (a rank's step includes waiting in the
+        # collective for the slowest kernel), and the fastest rank's kernel (spread = content imbalance between shards)
+        kern = [e[0].elapsed_time(e[1]) for e in ev]
+        stepms = [e[0].elapsed_time(e[2]) for e in ev]
+        kern_max = allmax(kern)
+        step_max = allmax(stepms)
+        kern_min = [-v for v in allmax([-v for v in kern])]
+        step_ms = sum(step_max)
+        kern_ms = sum(kern_max)
+        image_mean = float(job.image.mean().item())
 
         # ---- e2e: the public call with HOST buffers, copies inside the timed region -----
         e2e = None
         if not args.no_e2e:
-            host = torch.empty(npix * 3, dtype=torch.float32).pin_memory()
             host64 = np.empty((npix, 3), np.float64)
             cam = cfg.camera.to_c()
+            devices = list(range(world))
 
             def e2e_step():
-                ds = api.DeviceScene(flat, local)  # H2D: the flattened scene (host arrays -> HBM)
+                # H2D: the flattened scene (host arrays -> HBM of every GPU); one call renders on all of them and leaves
+                # the image in the caller's double buffer (D2H inside)
+                ds = api.DeviceScene(flat, devices if world > 1 else local)
                 try:
-                    p = r.params(spp_total, 0, rank, world)
-                    if world == 1:
-                        # the reference-facing C-ABI call: host double buffer out (D2H inside)
-                        capi.check(capi.lib().rptb_render_samples(ds.handle, C.byref(cam), C.byref(p),
-                                                                  host64.ctypes.data_as(capi.c_double_p), None),
-                                   "rptb_render_samples")
-                    else:
-                        capi.check(capi.lib().rptb_render_samples_device(ds.handle, C.byref(cam), C.byref(p),
-                                                                         C.c_void_p(out.data_ptr()), C.c_void_p(raw), None),
-                                   "rptb_render_samples_device")
-                        dist.all_reduce(out)
-                        host.copy_(out, non_blocking=True)  # D2H of the assembled image
-                        stream.synchronize()
+                    p = job.r.params(job.spp_total, 0, 0, 1)
+                    capi.check(capi.lib().rptb_render_samples(ds.handle, C.byref(cam), C.byref(p),
+                                                              host64.ctypes.data_as(capi.c_double_p), None), "rptb_render_samples")
                 finally:
                     ds.close()
 
-            e2e_step()  # warm-up
             stream.synchronize()
             barrier()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                e2e_step()
-            stream.synchronize()
+            e2e_s = 0.0
+            if rank == 0:  # the fan-out over the N GPUs lives inside rptb_render_samples: one caller, the other ranks wait
+                e2e_step()  # warm-up
+                t0 = time.perf_counter()
+                for _ in range(K):
+                    e2e_step()
+                e2e_s = time.perf_counter() - t0
             barrier()
-            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            e2e_s = float(te.item())
-            e2e = {
-                "value": total["segments"] * K / e2e_s / 1e6, "unit": UNIT,
-                "h2d_bytes_per_step": int(flat.host_bytes() + C.sizeof(capi.Camera) + C.sizeof(capi.RenderParams)) * world,
-                "d2h_bytes_per_step": int(npix * 3 * 4),
-                "ms_per_step": 1e3 * e2e_s / K,
-                "call": "rptb_scene_create + rptb_render_samples(host double* out) + rptb_scene_destroy per step" if world == 1
-                        else "per rank: rptb_scene_create + rptb_render_samples_device + NCCL all-reduce + D2H to pinned host + destroy",
-                "timer": "host perf_counter between synchronize+barrier, max over ranks",
-                "h2d_source": "pageable host arrays (cudaMemcpy inside rptb_scene_create)",
-            }
+            if rank == 0:
+                e2e = {
+                    "value": total["segments"] * K / e2e_s / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": int(flat.host_bytes() + C.sizeof(capi.Camera) + C.sizeof(capi.RenderParams)) * world,
+                    "d2h_bytes_per_step": int(npix * 3 * 4),
+                    "ms_per_step": 1e3 * e2e_s / K,
+                    "call": ("rptb_scene_create + rptb_render_samples(host double* out) + rptb_scene_destroy per step" if world == 1 else
+                             "rptb_scene_create_multi(%d GPUs) + ONE rptb_render_samples(host double* out) + rptb_scene_destroy per step, "
+                             "called by rank 0 (one host thread per GPU inside the library; the other ranks idle)" % world),
+                    "timer": "host perf_counter around the K calls (each call returns with the image in host memory)",
+                    "h2d_source": "pageable host arrays (cudaMemcpy inside rptb_scene_create*)",
+                    "image_mean": float(host64.mean()),
+                }
+
+        # ---- secondary: BASELINE's 8-GPU configs at their own size, strong scaling ------------------------------
+        secondary = None
+        if args.workload == "cornell" and not args.no_secondary and not args.spp:
+            secondary = {}
+            for name in ("dragon", "glass"):
+                scfg = workload(name)
+                sj = Job(scfg, scfg.spp)  # the image gets scfg.spp samples however many ranks share it
+                probe_spp = max(1, scfg.spp // 64)
+                ctr, _, _ = sj.counters(probe_spp)   # counters per segment at reduced spp (they scale with the sample count)
+                sj.render(spp=probe_spp)             # warm-up of the plain kernel
+                sj.assemble()
+                stream.synchronize()
+                barrier()
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                flush.zero_()
+                st = capi.Stats()
+                e0.record()
+                sj.render(st)  # collect_stats = 0: segments / rays only; the call returns when the kernel has finished
+                e1.record()
+                sj.assemble()
+                e2.record()
+                stream.synchronize()
+                barrier()
+                segs, rays = allsum([int(st.segments), int(st.rays)])
+                t_step, t_kern = allmax([e0.elapsed_time(e2), e0.elapsed_time(e1)])
+                scale = segs / max(ctr["segments"], 1)
+                bytes_all = algorithmic_bytes({k: v * scale for k, v in ctr.items()}, sj.npix)
+                ach = bytes_all / world / (t_kern / 1e3) / 1e9
+                secondary[scfg.name] = {
+                    "config": "%s %dx%d, %d spp total, max_bounces %d; %s" % (scfg.name, scfg.width, scfg.height, scfg.spp, scfg.max_bounces, scfg.note),
+                    "scaling": "strong", "steps": 1, "value": segs / (t_step / 1e3) / 1e6, "unit": UNIT,
+                    "ms_per_step": t_step, "kernel_ms_max_rank": t_kern, "segments": segs, "rays": rays,
+                    "image_mean": float(sj.image.mean().item()), "device_scene_bytes": sj.r.device_scene().device_bytes(),
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "algorithmic_bytes_per_launch": bytes_all / world, "bytes_model": BYTES_MODEL,
+                                 "per_ray": {"bvh_nodes": ctr["bvh_node_visits"] / max(ctr["rays"], 1), "bvh_tris": ctr["bvh_tri_tests"] / max(ctr["rays"], 1),
+                                             "objects": ctr["object_tests"] / max(ctr["rays"], 1)},
+                                 "traffic": (lambda rec: None if not rec else rec["dram_bytes"] * segs / world / max(rec["segments"], 1))(ncu_record(scfg.name)),
+                                 "note": "counters from a %d-spp pass of the counting variant of the same kernel, scaled by segments" % probe_spp},
+                }
+                sj.close()
 
     if rank == 0:
         value = total["segments"] * K / (step_ms / 1e3) / 1e6
-        peak, peak_src = measured_peaks()
-        # dominant kernel: render_kernel<float,16,false>; one launch per step per GPU
         bytes_all = algorithmic_bytes(total, npix)  # summed over ranks (each writes its own pixels)
         kern_s = kern_ms / 1e3 / K
-        achieved = bytes_all / world / kern_s / 1e9  # per GPU
-        issue = None
-        if clocks and clocks.get("sm_mhz"):
-            issue = {"note": "this path is instruction-issue bound, not HBM bound: the whole scene is cache resident",
-                     "segments_per_sm_clock": total["segments"] / world / kern_s / (148 * clocks["sm_mhz"] * 1e6)}
+        achieved_hbm = bytes_all / world / kern_s / 1e9  # per GPU
+        rec = ncu_record(cfg.name)
+        sm_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
+        segs_per_gpu = total["segments"] / world
+        hbm_view = {"achieved_algorithmic_gbs": achieved_hbm, "peak": peak, "unit": "GB/s", "frac_algorithmic": achieved_hbm / peak,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_all / world, "bytes_model": BYTES_MODEL,
+                    "counters_per_step": total}
+        if rec:
+            traffic = rec["dram_bytes"] * segs_per_gpu / max(rec["segments"], 1)
+            hbm_view["dram_frac"] = traffic / kern_s / 1e9 / peak
+        else:
+            traffic = None
+        cache_resident = flat.host_bytes() < (32 << 20)
+        if cache_resident and rec:
+            # a scene that lives in L1/L2 is bound by instruction issue, not by HBM: thread-instructions per second against
+            # 148 SMs x 128 FP32 lanes x the SM clock sampled during the run (the per-segment instruction count is the
+            # kernel's, from this round's ncu capture)
+            tinst = rec["thread_inst"] * segs_per_gpu / max(rec["segments"], 1)
+            ach = tinst / kern_s / 1e9
+            pk = 148 * 128 * sm_mhz * 1e6 / 1e9
+            roofline = {"bound": "issue", "achieved": ach, "peak": pk, "unit": "Gthread-inst/s", "frac": ach / pk, "traffic": traffic,
+                        "peak_source": "148 SMs x 128 lanes x %.0f MHz (median SM clock during the timed region)" % sm_mhz,
+                        "thread_inst_per_segment": rec["thread_inst"] / max(rec["segments"], 1),
+                        "lanes_per_warp_inst": rec["thread_inst"] / max(rec["inst"], 1),
+                        "note": "the whole scene is cache resident (%d B): the HBM view below counts bytes L1/L2 serve" % flat.host_bytes(),
+                        "hbm": hbm_view}
+        else:
+            roofline = {"bound": "hbm", "achieved": achieved_hbm, "peak": peak, "unit": "GB/s", "frac": achieved_hbm / peak, "traffic": traffic,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_all / world, "bytes_model": BYTES_MODEL,
+                        "counters_per_step": total}
+        roofline["kernel"] = ("rptb::render_kernel<float,16,false,FEAT> (megakernel: one launch per step, + chunk resolve)" if engine_used != 2 else
+                              "rptb::wf_trace_kernel (+ wf_shade_kernel; wavefront engine: the duration is the whole step's kernels)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -410,28 +504,27 @@ def run_native(args):
             "config": config_dict(cfg, world),
             "segments_per_step": total["segments"], "rays_per_step": total["rays"],
             "kernel_ms_per_step": kern_ms / K, "wall_s_timed_region": t_wall, "image_mean": image_mean,
+            "step_breakdown_ms": {
+                "kernel_slowest_rank": kern_ms / K, "kernel_fastest_rank": sum(kern_min) / K,
+                "collective_and_assembly": (step_ms - kern_ms) / K,
+                "note": "per step: max over ranks of the render kernel, its spread across ranks (shard content), and what the "
+                        "all-gather + permutation add on top of the slowest kernel",
+            },
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches_per_step * K,
-            "roofline": {
-                "bound": "hbm",
-                "kernel": "rptb::render_kernel<float,16,false,FEAT> (megakernel: one launch per step, + chunk resolve)" if engine != 2 else
-                          "rptb::wf_trace_kernel<false> (+ wf_shade_kernel; wavefront engine: the duration is the whole step's kernels)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(cfg.name, spp_total, engine), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_all / world,
-                "bytes_model": "64*object_tests + 8*node_visits + 52*tri_tests + 64*bvh_node_visits + 52*bvh_tri_tests + 36*mesh_hits + 32*segments + 64*env_lookups + 12*pixels (counters of the structure that rendered the step)",
-                "counters_per_step": total,
-                "secondary": issue,
-            },
+            "roofline": roofline,
         }
+        if secondary:
+            line["secondary"] = secondary
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = oracle_rate(cfg)
+            res = cpu_arm(cfg, 8, 1, budget_s=12.0)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "cores_affinity", "cgroup_cpu_quota", "kind", "sample")}
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    r.close()
+    job.close()
     return 0
 
 

@@ -231,7 +231,12 @@ typedef struct rptb_render_params {
                                node_visits / tri_tests); 2 = a counting pass over the reference-shaped kd-trees whatever
                                the scene was created with (SURVEY 8d's algorithmic work) */
     uint32_t engine;      /* rptb_engine: 0 = pick by scene                   */
-    uint32_t _pad;
+    uint32_t compact_out; /* rptb_render_samples_device only.  0 = out is the full row-major width*height*3 image, other
+                             shards' pixels written as zero.  1 = out holds ONLY this shard's tiles, tile-major: owned tile
+                             k (= tile shard_index + k*shard_count, tiles are 16x8 pixels numbered row-major) occupies
+                             out[k*384 .. k*384+384), pixel j of the tile at (x0 + (j>>5&1)*8 + (j&7), y0 + (j>>6)*4 + (j>>3&3))
+                             -- 1/shard_count of the bytes, so a multi-GPU host all-gathers shards instead of all-reducing
+                             full images (rptb_tile_pixel gives the mapping)                                             */
 } rptb_render_params;
 
 typedef struct rptb_stats {
@@ -287,6 +292,11 @@ int rptb_render_samples(rptb_scene* scene, const rptb_camera* camera,
 int rptb_render_samples_device(rptb_scene* scene, const rptb_camera* camera,
                                const rptb_render_params* params, float* out_rgb_device,
                                void* stream, rptb_stats* stats /* nullable, forces sync */);
+
+/* Pixel index (y*width + x) of element j (0..127) of the k-th tile owned by shard_index of shard_count, or -1 when
+ * that element lies outside a ragged image edge: the layout of compact_out = 1 and of the tile ownership of every
+ * sharded render.  Host side.                                                                              */
+int64_t rptb_tile_pixel(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count, uint32_t k, uint32_t j);
 
 /* Replaces: Renderer::get_closest_hit (src/renderer.rs:211-220) for `n` world
  * rays (n x 6 doubles: origin, dir).  out_t[i] = +inf and out_object[i] = -1

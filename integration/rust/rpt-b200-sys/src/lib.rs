@@ -170,7 +170,7 @@ pub struct RptbRenderParams {
     pub precision: u32,
     pub collect_stats: u32,
     pub engine: u32,
-    pub _pad: u32,
+    pub compact_out: u32,
 }
 
 #[repr(C)]

@@ -314,7 +314,7 @@ impl GpuScene {
         let params = sys::RptbRenderParams {
             width, height, iterations, max_bounces, exposure_value, seed, first_sample,
             shard_index: 0, shard_count: 1, precision: sys::RPTB_PRECISION_F32, collect_stats: 0,
-            engine: sys::RPTB_ENGINE_AUTO, _pad: 0,
+            engine: sys::RPTB_ENGINE_AUTO, compact_out: 0,
         };
         let mut colors = vec![glm::vec3(0.0, 0.0, 0.0); (width * height) as usize];
         // a DVec3 is three contiguous f64: the Vec<Color> is the W*H*3 double buffer the library fills

@@ -150,7 +150,7 @@ class RenderParams(C.Structure):
         ("precision", C.c_uint32),
         ("collect_stats", C.c_uint32),
         ("engine", C.c_uint32),
-        ("_pad", C.c_uint32),
+        ("compact_out", C.c_uint32),
     ]
 
 
@@ -211,6 +211,7 @@ SYMBOLS = [
      [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), c_double_p, C.POINTER(Stats)]),
     ("rptb_render_samples_device", C.c_int,
      [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
+    ("rptb_tile_pixel", C.c_int64, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     ("rptb_closest_hit", C.c_int,
      [C.c_void_p, c_double_p, C.c_uint64, C.c_double, C.c_uint32, c_double_p, c_i32_p, c_double_p,
       C.POINTER(Stats)]),

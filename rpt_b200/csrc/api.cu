@@ -596,16 +596,22 @@ int rptb_render_samples_device(rptb_scene* s, const rptb_camera* cam, const rptb
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : s->stream;
     rc = wait_busy(s, stream);
     if (rc != RPTB_OK) return rc;
-    const size_t nvals = (size_t)p->width * p->height * 3;
+    const bool compact = p->compact_out != 0;
+    size_t nvals = (size_t)p->width * p->height * 3;
+    if (compact) {
+        const uint32_t sc = p->shard_count ? p->shard_count : 1u;
+        const uint32_t ntiles = ((p->width + 15u) / 16u) * ((p->height + 7u) / 8u);
+        nvals = (size_t)(ntiles > p->shard_index ? (ntiles - p->shard_index + sc - 1u) / sc : 0u) * 384u;
+    }
     uint32_t launches = 0;
     if (stats) CU(cudaEventRecord(s->ev0, stream));
     if (p->precision == RPTB_PRECISION_F32) {
-        rc = render_launch(s, cam, p, out_dev, nullptr, stream, stats != nullptr, false, &launches);
+        rc = render_launch(s, cam, p, out_dev, nullptr, stream, stats != nullptr, compact, &launches);
         if (rc != RPTB_OK) return rc;
     } else {
         rc = ensure_out(s, nvals);
         if (rc != RPTB_OK) return rc;
-        rc = render_launch(s, cam, p, nullptr, s->out64, stream, stats != nullptr, false, &launches);
+        rc = render_launch(s, cam, p, nullptr, s->out64, stream, stats != nullptr, compact, &launches);
         if (rc != RPTB_OK) return rc;
         CU(launch_convert_f64_to_f32(s->out64, out_dev, nvals, stream));
         launches++;
@@ -733,6 +739,18 @@ int rptb_closest_hit(rptb_scene* s, const double* rays, uint64_t n, double t_min
     }
     cleanup();
     return RPTB_OK;
+}
+
+int64_t rptb_tile_pixel(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count, uint32_t k, uint32_t j) {
+    const uint32_t sc = shard_count ? shard_count : 1u;
+    const uint32_t tiles_x = (width + 15u) / 16u, tiles_y = (height + 7u) / 8u;
+    const uint64_t tile = (uint64_t)shard_index + (uint64_t)k * sc;
+    if (width == 0 || height == 0 || j >= 128u || shard_index >= sc || tile >= (uint64_t)tiles_x * tiles_y) return -1;
+    const uint32_t tx = (uint32_t)(tile % tiles_x), ty = (uint32_t)(tile / tiles_x);
+    const uint32_t warp = j >> 5, lane = j & 31u;
+    const uint32_t x = tx * 16u + (warp & 1u) * 8u + (lane & 7u), y = ty * 8u + (warp >> 1) * 4u + (lane >> 3);
+    if (x >= width || y >= height) return -1;
+    return (int64_t)y * width + x;
 }
 
 int rptb_illuminate(rptb_scene* s, uint32_t light, const double* pos, uint64_t n, uint64_t seed, uint32_t precision,

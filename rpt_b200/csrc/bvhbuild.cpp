@@ -154,10 +154,15 @@ std::unique_ptr<Node> build(std::vector<Prim>& prims, uint32_t first, uint32_t c
 }
 
 // Round a box outward and pad it: the f32 triangle test works on o + t d evaluated in float, which can
-// land a few ulps outside the exact triangle.
+// land a few ulps outside the exact triangle, and the slab test evaluates (b - o)/d as b*(1/d) - o*(1/d), whose
+// rounding error is ~6e-8 |o| in space whatever the box.  The pad therefore scales with the larger of the box's own
+// coordinate and the MESH's extent (g_root_mag, set per build): it covers ray origins out to ~60 mesh extents from
+// the local origin on every box, including boxes that hug a coordinate plane (where |b| alone would give no pad).
+float g_root_mag = 0.0f;
+#pragma omp threadprivate(g_root_mag)
 void pad(const Box& b, float* lo, float* hi) {
     for (int a = 0; a < 3; a++) {
-        const float mag = std::fmax(std::fmax(std::fabs(b.lo[a]), std::fabs(b.hi[a])), 1e-3f);
+        const float mag = std::fmax(std::fmax(std::fmax(std::fabs(b.lo[a]), std::fabs(b.hi[a])), g_root_mag), 1e-3f);
         const float eps = 4e-6f * mag;
         lo[a] = std::nextafterf(b.lo[a] - eps, -INFINITY);
         hi[a] = std::nextafterf(b.hi[a] + eps, INFINITY);
@@ -195,11 +200,13 @@ int32_t child_code(const Node& n, std::vector<BvhNodeDev>& out, uint32_t depth, 
 namespace rptb {
 
 // tris: ntris x 18 doubles (v1 v2 v3 n1 n2 n3).  `order[k]` = original index of the k-th triangle in leaf
-// order.  Needs more than BVH_LEAF_MAX triangles (the root must be an inner node; smaller meshes are one kd
-// leaf and never come here) and fewer than 2^28.  Returns 0, or -1 for a mesh outside that range.
+// order.  1 <= ntris < 2^28; returns 0, or -1 outside that range.  The root is always an inner node: a mesh the
+// SAH would leave as one leaf (a caller-supplied kd-tree may split over four triangles or fewer) becomes a root
+// whose two children are the halves of that leaf (the same leaf twice for a single triangle -- the second test of a
+// triangle can never tighten the hit, `time >= h.t` rejects it).
 int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& nodes, std::vector<uint32_t>& order,
                    uint32_t& depth) {
-    if (ntris <= (uint64_t)BVH_LEAF_MAX || ntris >= (1ull << 28)) return -1;
+    if (ntris == 0 || ntris >= (1ull << 28)) return -1;
     std::vector<Prim> prims(ntris);
     for (uint64_t i = 0; i < ntris; i++) {
         const double* t = tris + 18 * i;
@@ -226,7 +233,20 @@ int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& 
     root = build(prims, 0, (uint32_t)ntris, 0);
     nodes.clear();
     depth = 0;
-    if (root->count) return -1;
+    g_root_mag = 0.0f;
+    for (int a = 0; a < 3; a++) g_root_mag = std::fmax(g_root_mag, std::fmax(std::fabs(root->box.lo[a]), std::fabs(root->box.hi[a])));
+    if (root->count) {  // the whole mesh is one leaf: give the root two leaf children
+        const uint32_t n = root->count, h = n > 1 ? n / 2 : 1;
+        for (int k = 0; k < 2; k++) {
+            auto kid = std::make_unique<Node>();
+            kid->first = (k == 0 || n == 1) ? 0 : h;
+            kid->count = n == 1 ? 1 : (k == 0 ? h : n - h);
+            kid->box.reset();
+            for (uint32_t i = kid->first; i < kid->first + kid->count; i++) kid->box.grow(prims[i].box);
+            root->kid[k] = std::move(kid);
+        }
+        root->count = 0;
+    }
     emit_inner(*root, nodes, 0, depth);
     order.resize(ntris);
     for (uint64_t i = 0; i < ntris; i++) order[i] = prims[i].id;

@@ -106,3 +106,26 @@ def test_no_gpu_means_no_device_error_not_a_fallback():
     r = api.Renderer(scenes.sphere_scene().scene, api.Camera.default()).width(8).height(8)
     with pytest.raises(capi.RptbError):
         r.render()
+
+
+def test_tile_pixel_is_the_ownership_map_of_sharded_renders():
+    """rptb_tile_pixel: element j of the k-th tile owned by shard s of n <-> pixel.  Over all shards it is a bijection
+    onto the image (ragged edges included) and agrees with rpt_b200.distributed.tile_owner."""
+    from rpt_b200.distributed import tile_owner
+
+    lib = capi.lib()
+    for (w, h, n) in ((37, 21, 1), (37, 21, 3), (64, 16, 8), (5, 3, 2)):
+        own = tile_owner(w, h, n)
+        seen = np.full(w * h, -1, np.int64)
+        ntiles = ((w + 15) // 16) * ((h + 7) // 8)
+        for s in range(n):
+            mine = (ntiles - s + n - 1) // n if ntiles > s else 0
+            for k in range(mine):
+                for j in range(128):
+                    p = lib.rptb_tile_pixel(w, h, s, n, k, j)
+                    if p >= 0:
+                        assert seen[p] == -1
+                        seen[p] = s
+            assert lib.rptb_tile_pixel(w, h, s, n, mine, 0) == -1      # past this shard's last tile
+        assert (seen == own.ravel()).all()
+    assert lib.rptb_tile_pixel(16, 8, 0, 1, 0, 128) == -1 and lib.rptb_tile_pixel(0, 8, 0, 1, 0, 0) == -1

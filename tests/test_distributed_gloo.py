@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from rpt_b200 import api, scenes
-from rpt_b200.distributed import assemble, tile_owner
+from rpt_b200.distributed import assemble, gather_permutation, gather_tiles, shard_tiles, tile_owner
 
 
 def _free_port():
@@ -44,6 +44,24 @@ def _worker(rank, world, port, w, h, spp, mb, q):
         return torch.from_numpy(img.copy())
 
     out = assemble(shard)
+
+    # the other assembly: every rank contributes ONLY its own tiles, tile-major (what compact_out = 1 renders into), one
+    # all-gather, a fixed permutation.  The compact buffer is cut out of the oracle's shard image with rptb_tile_pixel.
+    from rpt_b200 import _capi as capi
+
+    def compact(rk, wd):
+        img, _ = osc.render(cfg.camera, r.params(spp, 0, rk, wd), nthreads=2)
+        n = shard_tiles(w, h, rk, wd)
+        buf = np.zeros((n * 128, 3))
+        for k in range(n):
+            for j in range(128):
+                p = capi.lib().rptb_tile_pixel(w, h, rk, wd, k, j)
+                if p >= 0:
+                    buf[k * 128 + j] = img[p]
+        return torch.from_numpy(buf.reshape(-1))
+
+    out2 = gather_tiles(compact, w, h)
+    assert torch.equal(out2, out)
     segs = torch.tensor([seen["segments"]], dtype=torch.int64)
     dist.all_reduce(segs)
     if rank == 0:
@@ -76,3 +94,18 @@ def test_sharded_render_equals_full_render_gloo(orc, world):
 def test_assemble_without_process_group_is_identity():
     t = torch.arange(6, dtype=torch.float32)
     assert assemble(lambda rk, wd: t) is t
+
+
+def test_gather_permutation_matches_tile_pixel():
+    from rpt_b200 import _capi as capi
+
+    for (w, h, n) in ((50, 27, 3), (33, 9, 2), (16, 8, 1)):
+        perm = gather_permutation(w, h, n)
+        per = shard_tiles(w, h, 0, n) * 128
+        assert len(np.unique(perm)) == w * h
+        for s_ in range(n):
+            for k in range(shard_tiles(w, h, s_, n)):
+                for j in range(128):
+                    p = capi.lib().rptb_tile_pixel(w, h, s_, n, k, j)
+                    if p >= 0:
+                        assert perm[p] == s_ * per + k * 128 + j

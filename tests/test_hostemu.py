@@ -415,3 +415,40 @@ def test_bvh_with_exactly_zero_direction_components(orc, name):
         t0, o0, _, _ = o.closest_hit(rays)
         assert (ob == o0).mean() >= 0.9995
         assert ((ob >= 0) == (bvh == 1)).mean() >= 0.9995                             # any-hit agrees with closest-hit
+
+
+def test_bvh_over_a_handful_of_triangles_behind_a_split_kd_root(orc):
+    """a caller-supplied kd-tree may split over four triangles or fewer; the default accel (BVH) must take
+    such a mesh (the root becomes an inner node over two leaf halves) instead of failing scene creation."""
+    from rpt_b200.api import Camera, Light, Material, Mesh, Object, Scene, hex_color, vec3
+
+    for ntris in (1, 2, 3, 4):
+        tris = []
+        for k in range(ntris):
+            x = 0.7 * k
+            v = [[x, 0, 0], [x + 0.5, 0, 0.1 * k], [x, 0.6, 0]]
+            n = [0, 0, 1]
+            tris.append(np.array(v + [n, n, n], dtype=np.float64).reshape(-1))
+        tris = np.array(tris)
+        mesh = Mesh(tris)
+        if ntris >= 2:   # force a split root: left leaf = first triangle(s), right leaf = the rest (an inclusive partition may repeat)
+            nodes = (capi.KdNode * 3)()
+            nodes[0].split, nodes[0].kind, nodes[0].left, nodes[0].right = 0.6, 0, 1, 2
+            nodes[1].kind, nodes[1].first_ref, nodes[1].num_refs = 3, 0, 1
+            nodes[2].kind, nodes[2].first_ref, nodes[2].num_refs = 3, 1, ntris - 1
+            mesh.nodes, mesh.refs = nodes, np.arange(ntris, dtype=np.uint32)
+        scene = Scene()
+        scene.add(Object(mesh).material(Material.diffuse(hex_color(0xFFFFFF))))
+        scene.add(Light.Point(vec3(5, 5, 5), vec3(0, 0, 3)))
+        flat = api.FlatScene(scene, accel=capi.ACCEL_BVH)
+        e = emu.EmuScene(flat)
+        rng = np.random.default_rng(ntris)
+        o = np.concatenate([rng.uniform(-0.5, 3.0, (4000, 2)), np.full((4000, 1), 2.0)], axis=1)
+        rays = np.concatenate([o, np.tile([0.0, 0.0, -1.0], (4000, 1)) + rng.normal(0, 0.05, (4000, 3))], axis=1)
+        tb, ob, _, sb = e.closest_hit(rays, precision=capi.PRECISION_F32)
+        t0, o0, _, _ = orc.OracleScene(flat).closest_hit(rays)
+        assert (ob == o0).mean() > 0.999 and (o0 >= 0).any()
+        hit = (ob == o0) & (o0 >= 0)
+        assert np.abs(tb[hit] - t0[hit]).max() < 1e-5
+        if ntris >= 2:
+            assert e.features & 64 and sb["bvh_node_visits"] > 0
