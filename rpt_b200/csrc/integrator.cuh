@@ -16,8 +16,11 @@
 // whose path ended regenerates its next camera ray at the top of the same loop
 // instead of idling until the longest path of the warp finishes (persistent-lane
 // path regeneration).  The per-level clamp `min(indirect, 100)` makes the estimator
-// non-linear, so each level's (local radiance, throughput) is kept on a small
-// per-thread stack and unwound when the path ends -- exactly the reference's value.
+// non-linear.  The f64 parity gate keeps each level's (local radiance, throughput) on a small
+// per-thread stack and unwinds it when the path ends -- literally the reference's recursion.  The
+// f32 product path needs no stack: a level is the map x -> a + min(w x, 100) of the radiance x coming
+// back from below, and such maps compose into one of the same shape, A + min(W x, C), so the path carries
+// nine floats forward and the value is exact (see `render_thread`).
 #pragma once
 #include "shading.cuh"
 
@@ -111,15 +114,23 @@ enum : int {
 struct DeviceWarp {
     static __device__ __forceinline__ unsigned activemask() { return __activemask(); }
     static __device__ __forceinline__ bool all(unsigned m, bool p) { return __all_sync(m, p); }
+    static __device__ __forceinline__ bool any(unsigned m, bool p) { return __any_sync(m, p); }
     static __device__ __forceinline__ uint32_t reduce_add(unsigned m, uint32_t v) { return __reduce_add_sync(m, v); }
     static __device__ __forceinline__ bool is_leader(unsigned m, uint32_t lane) { return (int)lane == __ffs(m) - 1; }
     static __device__ __forceinline__ void add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 };
 #endif
 
+// The generator the megakernel draws from: f64 the oracle's, f32 the shared-memory ring (rng.cuh)
+template <class R>
+struct MegaRng { typedef Rng<R> type; };
+template <>
+struct MegaRng<float> { typedef RngRing type; };
+
+// `rng_ring`: RNG_RING * RENDER_THREADS words of shared memory (f32 on the device; null otherwise)
 template <class R, int MAXD, bool STATS, int FEAT, class W>
 RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const uint32_t block_x, const uint32_t block_y,
-                          const uint32_t thread_x) {
+                          const uint32_t thread_x, uint32_t* rng_ring = nullptr) {
     const uint32_t tile = a.shard_index + block_x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const uint32_t warp = thread_x >> 5, lane = thread_x & 31u;
@@ -141,8 +152,9 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
 
     PathCounters pc = {0, 0, 0, 0, {0, 0, 0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    Level<R> stack[MAXD];
-    Rng<R> rng;
+    Level<R> stack[M<R>::literal ? MAXD : 1];  // f64 gate only
+    typename MegaRng<R>::type rng;
+    rng.bind(rng_ring ? rng_ring + thread_x : nullptr, RENDER_THREADS);
     rng.init(a.seed, pix, a.first_sample);
 
     // current ray
@@ -164,14 +176,17 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
     const size_t pstride = (size_t)a.ntiles_mine * RENDER_THREADS;
     int depth = 0;
     int status = ST_FRESH;
-    // f32 only: the path's radiance accumulated forwards (A + T (.) L), the running minimum of
-    // the throughput prefixes, and whether the forward value is usable (see the finish step)
-    Vec3<R> fwdA = {(R)0, (R)0, (R)0}, fwdT = {(R)1, (R)1, (R)1}, fwdTmin = {(R)1, (R)1, (R)1};
-    bool fwd_ok = true;
+    // f32 only: trace_ray's value as a function of the radiance x that comes back from below the deepest level
+    // reached so far, per channel:  L(x) = fwdA + min(fwdT x, fwdC).  A level contributes x -> a + min(w x, 100)
+    // (renderer.rs:153-167: a = Le + direct light, w = f |cos| / pdf >= 0), and for W >= 0
+    //     A + min(W (a + min(w x, 100)), C)  =  (A + W a) + min(W w x, min(100 W, C - W a)),
+    // so the composite keeps its shape: exact per-level clamps with nine floats and no stack.
+    const R clamp_inf = M<R>::inf();
+    Vec3<R> fwdA = {(R)0, (R)0, (R)0}, fwdT = {(R)1, (R)1, (R)1}, fwdC = {clamp_inf, clamp_inf, clamp_inf};
     uint32_t slot = Ks;  // every lane starts with a camera ray
 
     while (true) {
-        rng.ensure();  // converged here: one Philox block serves all 32 lanes
+        rng.template ensure<W>(wmask);  // converged here: the lanes that are short of draws compute their Philox blocks together
         const bool light_slot = slot < Ks;
         bool active = false;  // this lane sends a ray through the trace site in this slot
 
@@ -220,22 +235,24 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
                 if (bounce) {  // renderer.rs:157-164
                     const Vec3<R> f = bsdf<R, FEAT>(mat, n, wo, wi);
                     const R abscos = M<R>::abs(dot(wi, n));
-                    Level<R>& lv = stack[depth];
-                    lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
                     if constexpr (M<R>::literal) {
+                        Level<R>& lv = stack[depth];
+                        lv.local[0] = color.x; lv.local[1] = color.y; lv.local[2] = color.z;
                         lv.f[0] = f.x; lv.f[1] = f.y; lv.f[2] = f.z;
                         lv.inv_pdf = (R)1 / pdf;
                         lv.abscos = abscos;
                     } else {
                         // exp() underflows in f32 long before it does in f64: a pdf of exactly 0 can only
-                        // pair with a direction whose true weight is negligible -> weight 0, not 0/0
+                        // pair with a direction whose true weight is negligible -> weight 0, not 0/0.  The same for
+                        // a weight that is not >= 0 (NaN from 0/0 in the BSDF): the composition below needs W >= 0.
                         const R k = pdf > (R)0 ? abscos / pdf : (R)0;
-                        const Vec3<R> w = {f.x * k, f.y * k, f.z * k};
-                        lv.w[0] = w.x; lv.w[1] = w.y; lv.w[2] = w.z;
-                        // forward accumulation: Y0 = sum_k T_k (.) local_k  with T_{k+1} = T_k (.) w_k
-                        fwd_ok = fwd_ok && color.x >= (R)0 && color.y >= (R)0 && color.z >= (R)0;
-                        fwdTmin = {M<R>::min(fwdTmin.x, fwdT.x), M<R>::min(fwdTmin.y, fwdT.y), M<R>::min(fwdTmin.z, fwdT.z)};
-                        fwdA = fwdA + cmul(fwdT, color);
+                        Vec3<R> w = {f.x * k, f.y * k, f.z * k};
+                        w = {w.x >= (R)0 ? w.x : (R)0, w.y >= (R)0 ? w.y : (R)0, w.z >= (R)0 ? w.z : (R)0};
+                        // compose this level (a = color, w) under the levels above it
+                        const Vec3<R> Wa = cmul(fwdT, color);
+                        fwdC = {M<R>::min((R)100 * fwdT.x, fwdC.x - Wa.x), M<R>::min((R)100 * fwdT.y, fwdC.y - Wa.y),
+                                M<R>::min((R)100 * fwdT.z, fwdC.z - Wa.z)};
+                        fwdA = fwdA + Wa;
                         fwdT = cmul(fwdT, w);
                         // an exactly zero weight (direction sampled below an opaque surface): the whole
                         // subtree is multiplied by 0 -- do not trace it
@@ -250,31 +267,26 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
                     }
                 }
                 if (!bounce) {
-                    // (after a zero-weight sample: depth was not advanced, fwdT is 0 and fwdA already
-                    // holds this vertex's colour, so both the forward sum and the unwind stay exact)
+                    // (after a zero-weight sample: depth was not advanced; f32: fwdT is 0 and fwdA already holds
+                    // this vertex's colour, so the composite evaluates to it whatever Lterm is; f64: the level at
+                    // stack[depth] is not unwound, Lterm = color is the value of this vertex)
                     Lterm = color;
                     status = ST_FINISH;
                 }
             }
             if (status == ST_FINISH) {
                 Vec3<R> L = Lterm;
-                bool fast = false;
                 if constexpr (!M<R>::literal) {
-                    // trace_ray's value is local_0 + min(w_0 (.) (local_1 + min(w_1 (.) ...)), 100).  If no
-                    // clamp engages it equals the forward sum Y0 = A + T (.) Lterm.  Every clamped
-                    // operand satisfies w_k Y_{k+1} <= Y0 / T_k (all terms >= 0), so Y0 <= 100 min_k T_k
-                    // proves that none engaged; otherwise (or on NaN/negative terms) unwind exactly.
-                    const Vec3<R> y0 = fwdA + cmul(fwdT, Lterm);
-                    fast = fwd_ok && Lterm.x >= (R)0 && Lterm.y >= (R)0 && Lterm.z >= (R)0 &&
-                           y0.x <= (R)100 * fwdTmin.x && y0.y <= (R)100 * fwdTmin.y && y0.z <= (R)100 * fwdTmin.z;
-                    if (fast) L = y0;
+                    // the composite of every level's clamp, applied to what came back from the last ray
+                    // (0 * inf cannot occur: fwdT = 0 pairs with a finite Lterm = colour of the last vertex)
+                    L = {fwdA.x + M<R>::min(fwdT.x * Lterm.x, fwdC.x), fwdA.y + M<R>::min(fwdT.y * Lterm.y, fwdC.y),
+                         fwdA.z + M<R>::min(fwdT.z * Lterm.z, fwdC.z)};
                     fwdA = {(R)0, (R)0, (R)0};
                     fwdT = {(R)1, (R)1, (R)1};
-                    fwdTmin = {(R)1, (R)1, (R)1};
-                    fwd_ok = true;
-                }
-                if (!fast)
+                    fwdC = {clamp_inf, clamp_inf, clamp_inf};
+                } else {
                     for (int k = depth - 1; k >= 0; k--) L = unwind(stack[k], L);
+                }
                 acc0 += (double)L.x;
                 acc1 += (double)L.y;
                 acc2 += (double)L.z;
@@ -404,7 +416,12 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
 #ifdef __CUDACC__
 template <class R, int MAXD, bool STATS, int FEAT = F_ALL>
 __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) render_kernel(const __grid_constant__ SceneView<R> sv, const __grid_constant__ RenderArgs<R> a) {
-    render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x);
+    if constexpr (M<R>::literal) {
+        render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x);
+    } else {
+        __shared__ uint32_t rng_ring[RNG_RING * RENDER_THREADS];  // 4 KB: every thread's 8 buffered draws, one bank per lane
+        render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x, rng_ring);
+    }
 }
 #endif
 

@@ -101,7 +101,10 @@ template <>
 struct Rng<double> {
     Philox p;
     RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) { p.init(seed, pix, sample); }
+    RPTB_HD void bind(uint32_t*, uint32_t) {}
     RPTB_HD void ensure() {}
+    template <class W>
+    RPTB_HD void ensure(unsigned) {}
     RPTB_HD double gen() { return (double)(p.next_u64() >> 11) * (1.0 / 9007199254740992.0); }
     RPTB_HD double u52() { return (double)(p.next_u64() >> 12) * (1.0 / 4503599627370496.0); }
     // Rng::gen_bool(p): Bernoulli -> u64 < p * 2^64
@@ -170,6 +173,9 @@ struct Rng<float> {
         if (avail <= 2) push_block();
         if (avail <= 2) push_block();
     }
+    template <class W>
+    RPTB_HD void ensure(unsigned) { ensure(); }
+    RPTB_HD void bind(uint32_t*, uint32_t) {}
     RPTB_HD uint32_t next32() {
         if (avail == 0) push_block();  // rare: a slot consumed more than the FIFO held
         const uint32_t v = q0;
@@ -194,9 +200,88 @@ struct Rng<float> {
     }
 };
 
+// The megakernel's f32 generator: the same stream as Rng<float> (high word of every 64-bit draw), buffered in an
+// 8-entry ring per thread that lives in SHARED memory on the device (entry i of thread t at ring[i * stride + t]:
+// one bank per lane, no conflicts; a ring in registers would need shuffling moves per draw and four more live
+// registers in a kernel that already spills).  What this buys (ncu, Cornell, round 2): with the 4-entry register FIFO
+// a slot that drew more than the FIFO held refilled it inside whatever rejection loop it was in -- the ~60-instruction
+// Philox block ran at 7.4 of 32 lanes and was 27 % of the kernel's warp instructions.  ensure() now tops every lane
+// up to >= 6 entries where the warp is converged, and all lanes that need a block compute it together.
+constexpr uint32_t RNG_RING = 8;
+struct RngRing {
+    uint32_t key0, key1, block, pixel, samp_lo, samp_hi;
+    uint32_t head, avail;
+    uint32_t* ring;     // device: shared memory; host emulation: `own`
+    uint32_t stride;
+#ifdef __CUDA_ARCH__
+    // (a local object of device code only: it never crosses the host/device boundary, so the layouts may differ)
+    __device__ void bind(uint32_t* shared_ring, uint32_t shared_stride) { ring = shared_ring; stride = shared_stride; }
+#else
+    uint32_t own[RNG_RING];
+    void bind(uint32_t* shared_ring, uint32_t shared_stride) {
+        if (shared_ring) { ring = shared_ring; stride = shared_stride; }
+        else { ring = own; stride = 1; }
+    }
+#endif
+    RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) {
+        key0 = (uint32_t)seed;
+        key1 = (uint32_t)(seed >> 32);
+        block = 0;
+        pixel = pix;
+        samp_lo = (uint32_t)sample;
+        samp_hi = (uint32_t)(sample >> 32);
+        head = 0;
+        avail = 0;
+    }
+    RPTB_HD uint32_t& at(uint32_t i) { return ring[(i & (RNG_RING - 1u)) * stride]; }
+    RPTB_HD void push_block() {  // requires avail <= RNG_RING - 2
+#ifdef __CUDA_ARCH__
+        const uint4 v = Philox::block_call(block, pixel, samp_lo, samp_hi, key0, key1);
+        const uint32_t a = v.y, b = v.w;
+#else
+        uint32_t o[4];
+        Philox::block10(block, pixel, samp_lo, samp_hi, key0, key1, o);
+        const uint32_t a = o[1], b = o[3];
+#endif
+        block++;
+        at(head + avail) = a;
+        at(head + avail + 1u) = b;
+        avail += 2;
+    }
+    // W = the warp policy of integrator.cuh (real votes on the device, a single lane in host emulation)
+    template <class W>
+    RPTB_HD void ensure(unsigned mask) {
+        while (W::any(mask, avail <= 5u)) {
+            if (avail <= RNG_RING - 2u) push_block();
+        }
+    }
+    RPTB_HD uint32_t next32() {
+        if (avail == 0) push_block();  // rare: a slot consumed more than six draws
+        const uint32_t v = at(head);
+        head++;
+        avail--;
+        return v;
+    }
+    RPTB_HD float gen() { return (float)(next32() >> 8) * (1.0f / 16777216.0f); }
+    RPTB_HD float u52() { return gen(); }
+    RPTB_HD bool bernoulli(float prob) {
+        const uint32_t v = next32();
+        if (prob >= 1.0f) return true;
+        return v < (uint32_t)((uint64_t)((double)prob * 18446744073709551616.0) >> 32);
+    }
+    RPTB_HD bool coin() { return (next32() >> 31) != 0; }
+    RPTB_HD uint64_t below(uint64_t n) {
+#ifdef __CUDA_ARCH__
+        return (uint64_t)__umulhi(next32(), (uint32_t)n);
+#else
+        return ((uint64_t)next32() * (uint32_t)n) >> 32;
+#endif
+    }
+};
+
 // Rng::gen_range(lo..hi) -> UniformFloat::sample_single
-template <class R>
-RPTB_HD R gen_range(Rng<R>& r, R lo, R hi) {
+template <class R, class RNG>
+RPTB_HD R gen_range(RNG& r, R lo, R hi) {
     const R scale = hi - lo;
     while (true) {
         const R v12 = (R)1 + r.u52();
@@ -205,34 +290,34 @@ RPTB_HD R gen_range(Rng<R>& r, R lo, R hi) {
     }
 }
 // Uniform::new(-1, 1).sample
-template <class R>
-RPTB_HD R uniform_pm1(Rng<R>& r) { return r.u52() * (R)2 + (R)(-1); }
+template <class R, class RNG>
+RPTB_HD R uniform_pm1(RNG& r) { return r.u52() * (R)2 + (R)(-1); }
 
 // Rng::gen_bool(p).  p >= 1 returns true (the reference's ALWAYS_TRUE case) but still
 // consumes one draw so that the number of draws per vertex is material-independent.
-template <class R>
-RPTB_HD bool gen_bool(Rng<R>& r, R prob) { return r.bernoulli(prob); }
+template <class R, class RNG>
+RPTB_HD bool gen_bool(RNG& r, R prob) { return r.bernoulli(prob); }
 
 // Uniform::from(0..n) for usize
-template <class R>
-RPTB_HD uint64_t uniform_usize(Rng<R>& r, uint64_t n) { return r.below(n); }
+template <class RNG>
+RPTB_HD uint64_t uniform_usize(RNG& r, uint64_t n) { return r.below(n); }
 
 // rand_distr::UnitDisc: rejection from the square, boundary inclusive
-template <class R>
-RPTB_HD void unit_disc(Rng<R>& r, R& x, R& y) {
+template <class R, class RNG>
+RPTB_HD void unit_disc(RNG& r, R& x, R& y) {
     while (true) {
-        x = uniform_pm1(r);
-        y = uniform_pm1(r);
+        x = uniform_pm1<R>(r);
+        y = uniform_pm1<R>(r);
         if (x * x + y * y <= (R)1) return;
     }
 }
 // rand_distr::UnitCircle: von Neumann's method
-template <class R>
-RPTB_HD void unit_circle(Rng<R>& r, R& x, R& y) {
+template <class R, class RNG>
+RPTB_HD void unit_circle(RNG& r, R& x, R& y) {
     R x1, x2, sum;
     while (true) {
-        x1 = uniform_pm1(r);
-        x2 = uniform_pm1(r);
+        x1 = uniform_pm1<R>(r);
+        x2 = uniform_pm1<R>(r);
         sum = x1 * x1 + x2 * x2;
         if (sum < (R)1) break;
     }

@@ -121,8 +121,8 @@ RPTB_D Frame<R> local_to_world(Vec3<R> n) {
 }
 
 // PIT sample of the Beckmann microfacet normal (material.rs:244-254)
-template <class R>
-RPTB_D Vec3<R> beckmann_sample(R m2, Vec3<R> n, Rng<R>& rng) {
+template <class R, class RNG>
+RPTB_D Vec3<R> beckmann_sample(R m2, Vec3<R> n, RNG& rng) {
     R sin_t, cos_t;
     const R u = rng.gen();
     if (M<R>::literal) {
@@ -156,8 +156,8 @@ RPTB_D R beckmann_pdf(R m2, Vec3<R> n, Vec3<R> h) {
 }
 
 // Material::sample_f (material.rs:224-313).  Returns false for `None` (TIR ends the path).
-template <class R, int FEAT = F_ALL>
-RPTB_D bool sample_f(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Rng<R>& rng, Vec3<R>& wi_out, R& pdf_out) {
+template <class R, int FEAT = F_ALL, class RNG>
+RPTB_D bool sample_f(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, RNG& rng, Vec3<R>& wi_out, R& pdf_out) {
     constexpr bool TR = (FEAT & F_TRANSP) != 0;
     const R m2 = m.roughness * m.roughness;
     const R r0 = (m.index - (R)1) / (m.index + (R)1);
@@ -212,8 +212,8 @@ RPTB_D bool sample_f(const MaterialRec<R>& m, Vec3<R> n, Vec3<R> wo, Rng<R>& rng
 
 // ------------------------------------------------------------- light shapes ---
 // Shape::sample of the light's object -> (point, normal, pdf per unit area)
-template <class R, int FEAT = F_ALL>
-RPTB_D void shape_sample(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> target, Rng<R>& rng, Vec3<R>& v,
+template <class R, int FEAT = F_ALL, class RNG>
+RPTB_D void shape_sample(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R> target, RNG& rng, Vec3<R>& v,
                          Vec3<R>& n, R& p) {
     if (ob.has_transform) target = xform_point(ob.inv, target);  // shape.rs:140
     bool done = false;
@@ -303,8 +303,8 @@ RPTB_D void shape_sample(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R>
 }
 
 // Light::illuminate (light.rs:23-47) for the non-ambient kinds
-template <class R, int FEAT = F_ALL>
-RPTB_D void illuminate(const SceneView<R>& sv, const LightRec<R>& l, Vec3<R> pos, Rng<R>& rng, Vec3<R>& intensity,
+template <class R, int FEAT = F_ALL, class RNG>
+RPTB_D void illuminate(const SceneView<R>& sv, const LightRec<R>& l, Vec3<R> pos, RNG& rng, Vec3<R>& intensity,
                        Vec3<R>& wi, R& dist) {
     const Vec3<R> color = {l.color[0], l.color[1], l.color[2]};
     if (l.kind == LIGHT_POINT) {

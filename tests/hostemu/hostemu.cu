@@ -113,6 +113,7 @@ void illuminations(const SceneView<R>& sv, uint32_t light, const double* pos, ui
 struct HostLane {
     static __host__ __device__ unsigned activemask() { return 1u; }
     static __host__ __device__ bool all(unsigned, bool p) { return p; }
+    static __host__ __device__ bool any(unsigned, bool p) { return p; }
     static __host__ __device__ uint32_t reduce_add(unsigned, uint32_t v) { return v; }
     static __host__ __device__ bool is_leader(unsigned, uint32_t) { return true; }
     static __host__ __device__ void add(unsigned long long* p, unsigned long long v) {

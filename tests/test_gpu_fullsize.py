@@ -13,7 +13,11 @@ with the survey's criterion in full, on linear RGB:
     (3) image mean within 0.5 %.
 
 N is 16-64 samples per pixel, chosen from a one-sample timing of the oracle on this box's host cores so that the
-CPU side of one config stays near a minute (the box may have anything from 16 to 128 usable cores).
+CPU side of one config stays near a minute (the box may have anything from 16 to 128 usable cores).  The dragon
+configs cost the oracle ~150 kd nodes and ~420 triangle tests per ray in f64 (12 s per sample per pixel on 16 cores),
+so they are compared on every 4th / 8th 16x8-pixel tile of the full-size image (the interleaved tile shards every
+sharded render uses: 518 400 / 259 200 pixels spread over the whole frame) -- same camera, same pixel footprint,
+same everything, a quarter / an eighth of the CPU time.
 """
 import ctypes as C
 import os
@@ -30,12 +34,12 @@ pytestmark = pytest.mark.gpu
 F32 = capi.PRECISION_F32
 
 CONFIGS = {
-    # name: (scene factory, width, height, max_bounces, max spp)
-    "cornell": (scenes.cornell_scene, 800, 800, 6, 64),
-    "teapot": (scenes.teapot_scene, 1920, 1080, 0, 64),
-    "dragon": (scenes.dragon_scene, 1920, 1080, 2, 32),
-    "glass": (scenes.glass_scene, 1920, 1080, 12, 64),
-    "dragon_knot": (scenes.dragon_knot_scene, 1920, 1080, 2, 16),
+    # name: (scene factory, width, height, max_bounces, max spp, tile stride: compare the tiles t % stride == 0)
+    "cornell": (scenes.cornell_scene, 800, 800, 6, 64, 1),
+    "teapot": (scenes.teapot_scene, 1920, 1080, 0, 64, 1),
+    "dragon": (scenes.dragon_scene, 1920, 1080, 2, 32, 4),
+    "glass": (scenes.glass_scene, 1920, 1080, 12, 64, 1),
+    "dragon_knot": (scenes.dragon_knot_scene, 1920, 1080, 2, 16, 8),
 }
 ORACLE_BUDGET_S = float(os.environ.get("RPTB_FULLSIZE_BUDGET", "45"))  # per oracle render (there are two per config)
 
@@ -61,7 +65,7 @@ def _gpu_call(ds, cam, p):
 
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_survey_8d_criterion_at_full_size(orc, gpu_ok, name):
-    make, w, h, mb, max_spp = CONFIGS[name]
+    make, w, h, mb, max_spp, stride = CONFIGS[name]
     cfg = make()
     assert (cfg.width, cfg.height, cfg.max_bounces) == (w, h, mb)  # the BASELINE.json size, not a thumbnail
     flat = api.FlatScene(cfg.scene)
@@ -69,22 +73,28 @@ def test_survey_8d_criterion_at_full_size(orc, gpu_ok, name):
     cam = cfg.camera.to_c()
     threads = _host_threads()
 
+    from rpt_b200.distributed import tile_owner
+    own = (tile_owner(w, h, stride) == 0).reshape(-1)   # the pixels both sides render (all of them when stride == 1)
+
     def rparams(seed, iterations, first_sample=0):
         r = api.Renderer(cfg.scene, cfg.camera).width(w).height(h).max_bounces(mb).seed(seed).precision(F32)
-        return r.params(iterations, first_sample)
+        return r.params(iterations, first_sample, 0, stride)
 
     # ---- the oracle, seed 1, as N one-sample batches (mean + per-pixel variance); N from a one-sample timing
-    o1 = util.Moments(w * h)
+    npx = int(own.sum())
+    o1 = util.Moments(npx)
     t0 = time.perf_counter()
     img, st = osc.render(cfg.camera, rparams(1, 1, 0), nthreads=threads)
     t1 = time.perf_counter() - t0
-    o1.add(img)
+    assert (img[~own] == 0).all()
+    o1.add(img[own])
     n = int(min(max_spp, max(16, ORACLE_BUDGET_S // max(t1, 1e-3))))
     for s in range(1, n):
         img, _ = osc.render(cfg.camera, rparams(1, 1, s), nthreads=threads)
-        o1.add(img)
+        o1.add(img[own])
     # ---- the oracle, seed 2: the seed-to-seed noise floor of criterion (1)
     o2, _ = osc.render(cfg.camera, rparams(2, n), nthreads=threads)
+    o2 = o2[own]
     cl = lambda a: np.clip(a, 0.0, 1.0)
     noise = util.rmse(cl(o1.mean), cl(o2))
     assert noise > 0
@@ -92,12 +102,15 @@ def test_survey_8d_criterion_at_full_size(orc, gpu_ok, name):
     with api.DeviceScene(flat) as ds:
         # one call on the oracle's own streams: what Renderer::render does
         g1, st1 = _gpu_call(ds, cam, rparams(1, n))
+        assert (g1[~own] == 0).all()
+        g1 = g1[own]
         # independent seed, as batches
-        g3 = util.Moments(w * h)
+        g3 = util.Moments(npx)
         for s in range(n):
             img, _ = _gpu_call(ds, cam, rparams(3, 1, s))
-            g3.add(img)
+            g3.add(img[own])
         g3_one, _ = _gpu_call(ds, cam, rparams(3, n))
+        g3_one = g3_one[own]
     assert np.isfinite(g1).all() and np.isfinite(g3.mean).all()
     # the batches ARE the n-sample render (each batch is rounded to f32 on its own: 1e-6 relative)
     assert np.abs(g3.mean - g3_one).max() <= 2e-6 * max(1.0, np.abs(g3_one).max())
@@ -106,9 +119,9 @@ def test_survey_8d_criterion_at_full_size(orc, gpu_ok, name):
     indep = util.rmse(cl(g3.mean), cl(o1.mean))
     zfrac, _ = util.z_outlier_fraction(g3, o1)
     mean_rel = abs(g3.mean.mean() - o1.mean.mean()) / o1.mean.mean()
-    print("\n[fullsize %s] %dx%d mb %d, N = %d spp (oracle %.2f s per sample on %d threads): noise %.5f, rmse same-seed %.5f (%.3f x), "
+    print("\n[fullsize %s] %dx%d mb %d, every %s tile = %d pixels, N = %d spp (oracle %.2f s per sample on %d threads): noise %.5f, rmse same-seed %.5f (%.3f x), "
           "independent %.5f (%.3f x), |z|>4 fraction %.2e, mean diff %.3f %%, gpu %.1f ms"
-          % (name, w, h, mb, n, t1, threads, noise, same_seed, same_seed / noise, indep, indep / noise, zfrac, 100 * mean_rel, st1["gpu_ms"]))
+          % (name, w, h, mb, "" if stride == 1 else "%dth" % stride, npx, n, t1, threads, noise, same_seed, same_seed / noise, indep, indep / noise, zfrac, 100 * mean_rel, st1["gpu_ms"]))
     assert same_seed <= 0.25 * noise        # same streams: nearly the same image
     assert indep <= 1.25 * noise            # (1)
     assert zfrac <= 1e-3                    # (2)
