@@ -21,6 +21,9 @@ oracle: $(ORACLE)
 $(OBJDIR)/kernels_f32.o: $(CSRC)/kernels_f32.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) --use_fast_math -c $< -o $@ 2> $(OBJDIR)/kernels_f32.ptxas.log || (cat $(OBJDIR)/kernels_f32.ptxas.log; false)
+$(OBJDIR)/kernels_vx.o: $(CSRC)/kernels_vx.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) --use_fast_math -c $< -o $@ 2> $(OBJDIR)/kernels_vx.ptxas.log || (cat $(OBJDIR)/kernels_vx.ptxas.log; false)
 # the parity gate keeps products and sums separately rounded, like the reference's f64 code
 $(OBJDIR)/kernels_f64.o: $(CSRC)/kernels_f64.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -41,7 +44,7 @@ $(OBJDIR)/objparse.o: $(CSRC)/objparse.cpp
 	@mkdir -p $(OBJDIR)
 	$(CXX) -std=c++17 -O3 -fPIC -Wall -c $< -o $@
 
-$(LIB): $(OBJDIR)/kernels_f32.o $(OBJDIR)/kernels_f64.o $(OBJDIR)/film.o $(OBJDIR)/api.o $(OBJDIR)/kdbuild.o $(OBJDIR)/bvhbuild.o $(OBJDIR)/objparse.o
+$(LIB): $(OBJDIR)/kernels_f32.o $(OBJDIR)/kernels_vx.o $(OBJDIR)/kernels_f64.o $(OBJDIR)/film.o $(OBJDIR)/api.o $(OBJDIR)/kdbuild.o $(OBJDIR)/bvhbuild.o $(OBJDIR)/objparse.o
 	@mkdir -p rpt_b200/lib
 	$(NVCC) -shared $(ARCH) -o $@ $^ -Xcompiler -fopenmp -lgomp -cudart shared
 

@@ -364,7 +364,12 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
         } else {
             const int rc = ensure_partial(s, a);
             if (rc != RPTB_OK) return rc;
-            CU(launch_render_f32(s->view32, a, (int)p->collect_stats, s->features, stream, launches));
+            a.ks = s->sampled_lights;
+            // the vertex-at-once schedule (integrator_vx.cuh) renders every scene it has ray slots for; RPTB_VX=0 keeps the
+            // slot schedule (A/B runs).  A counting pass over the reference-shaped kd-trees (collect_stats = 2) is the slot engine's.
+            static const bool vx_off = getenv("RPTB_VX") != nullptr && std::strcmp(getenv("RPTB_VX"), "0") == 0;
+            if (!vx_off && vx_supported(a.ks) && p->collect_stats != 2) CU(launch_render_vx_f32(s->view32, a, (int)p->collect_stats, s->features, stream, launches));
+            else CU(launch_render_f32(s->view32, a, (int)p->collect_stats, s->features, stream, launches));
         }
     } else {
         RenderArgs<double> a;

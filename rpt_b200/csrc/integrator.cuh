@@ -115,6 +115,11 @@ struct DeviceWarp {
     static __device__ __forceinline__ unsigned activemask() { return __activemask(); }
     static __device__ __forceinline__ bool all(unsigned m, bool p) { return __all_sync(m, p); }
     static __device__ __forceinline__ bool any(unsigned m, bool p) { return __any_sync(m, p); }
+    static constexpr uint32_t width = 32u;
+    static __device__ __forceinline__ unsigned ballot(unsigned m, bool p) { return __ballot_sync(m, p); }
+    static __device__ __forceinline__ uint32_t rank(unsigned votes, uint32_t lane) { return (uint32_t)__popc(votes & ((1u << lane) - 1u)); }
+    static __device__ __forceinline__ uint32_t popc(unsigned v) { return (uint32_t)__popc(v); }
+    static __device__ __forceinline__ void sync(unsigned m) { __syncwarp(m); }
     static __device__ __forceinline__ uint32_t reduce_add(unsigned m, uint32_t v) { return __reduce_add_sync(m, v); }
     static __device__ __forceinline__ bool is_leader(unsigned m, uint32_t lane) { return (int)lane == __ffs(m) - 1; }
     static __device__ __forceinline__ void add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }

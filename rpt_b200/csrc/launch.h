@@ -37,6 +37,12 @@ size_t wavefront_struct_size();
 cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float>& args, const WfBuffers* bufs,
                               bool stats, bool use_bvh, cudaStream_t stream, uint32_t* pinned, uint32_t* launches);
 
+// ---- the vertex-at-once f32 megakernel (integrator_vx.cuh; its own translation unit, kernels_vx.cu) -----------------
+// stats as in launch_render_f32.  args.ks must be <= VX_MAX_SHADOW (vx_supported).
+cudaError_t launch_render_vx_f32(const SceneView<float>& sv, const RenderArgs<float>& args, int stats, int features,
+                                 cudaStream_t stream, uint32_t* launches);
+bool vx_supported(uint32_t sampled_lights);
+
 // max_bounces the render kernels are instantiated for
 constexpr uint32_t MAX_BOUNCES_SUPPORTED = 64;
 

@@ -212,7 +212,8 @@ struct RenderArgs {
     // compact = 1: `out` holds ntiles_mine * 128 * 3 values in tile-major order (owned tile k, thread j of the
     // CTA -> out[(k * 128 + j) * 3]); nothing is written for other shards' pixels.  The multi-device handle
     // copies exactly its own pixels back this way (api.cu); 0 = the full row-major width * height * 3 image.
-    uint32_t compact, _pad;
+    uint32_t compact;
+    uint32_t ks;  // sampled (non-ambient) lights of the scene: the vertex-at-once engine's shadow ray slots (integrator_vx.cuh)
 };
 
 // chunk = max(64, ceil(iterations / 32)) samples, so at most 32 chunks

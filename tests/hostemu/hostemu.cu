@@ -20,6 +20,7 @@
 
 #include "../../rpt_b200/csrc/flatten.h"
 #include "../../rpt_b200/csrc/integrator.cuh"
+#include "../../rpt_b200/csrc/integrator_vx.cuh"
 #include "../../rpt_b200/csrc/launch.h"
 
 using namespace rptb;
@@ -114,6 +115,11 @@ struct HostLane {
     static __host__ __device__ unsigned activemask() { return 1u; }
     static __host__ __device__ bool all(unsigned, bool p) { return p; }
     static __host__ __device__ bool any(unsigned, bool p) { return p; }
+    static constexpr uint32_t width = 1u;
+    static __host__ __device__ unsigned ballot(unsigned, bool p) { return p ? 1u : 0u; }
+    static __host__ __device__ uint32_t rank(unsigned, uint32_t) { return 0u; }
+    static __host__ __device__ uint32_t popc(unsigned v) { uint32_t c = 0; while (v) { c += v & 1u; v >>= 1; } return c; }
+    static __host__ __device__ void sync(unsigned) {}
     static __host__ __device__ uint32_t reduce_add(unsigned, uint32_t v) { return v; }
     static __host__ __device__ bool is_leader(unsigned, uint32_t) { return true; }
     static __host__ __device__ void add(unsigned long long* p, unsigned long long v) {
@@ -139,6 +145,46 @@ void run_grid(const SceneView<R>& sv, const RenderArgs<R>& a) {
         for (int64_t bx = 0; bx < (int64_t)a.ntiles_mine; bx++)
             for (uint32_t t = 0; t < (uint32_t)RENDER_THREADS; t++) resolve_chunks_thread<R>(a, (uint32_t)bx, t);
     }
+}
+
+// The vertex-at-once engine (integrator_vx.cuh), one lane at a time: the "warp" is one lane wide, so the compacted work
+// list of a mesh holds just this lane's rays -- what a lane computes for a ray is what any lane of a real warp would.
+template <bool STATS, int FEAT>
+void run_grid_vx(const SceneView<float>& sv, const RenderArgs<float>& a) {
+    const int64_t nblocks = (int64_t)a.ntiles_mine * a.ngroups;
+    const size_t words = vx_shared_words(a.ks + 1u);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < nblocks; b++) {
+        std::vector<float4> smem((words + 3) / 4);  // 16-byte aligned
+        const uint32_t bx = (uint32_t)(b % a.ntiles_mine), by = (uint32_t)(b / a.ntiles_mine);
+        for (uint32_t t = 0; t < (uint32_t)RENDER_THREADS; t++)
+            render_thread_vx<STATS, FEAT, HostLane>(sv, a, bx, by, t, reinterpret_cast<uint32_t*>(smem.data()));
+    }
+    if (a.nchunks > 1) {
+#pragma omp parallel for schedule(static)
+        for (int64_t bx = 0; bx < (int64_t)a.ntiles_mine; bx++)
+            for (uint32_t t = 0; t < (uint32_t)RENDER_THREADS; t++) resolve_chunks_thread<float>(a, (uint32_t)bx, t);
+    }
+}
+
+// launch_render_vx_f32's dispatch (kernels_vx.cu).  Returns the FEAT it ran, tagged with bit 30.
+inline int run_render_vx(const SceneView<float>& sv, const RenderArgs<float>& a, int stats, int features) {
+    const int base = features & F_ALL;
+    const bool small = (features & F_SMALL) != 0, ext = (features & F_EXT) != 0, bvh = (features & F_BVH) != 0;
+    int f;
+    if (stats == 1 && bvh) { run_grid_vx<true, F_EVERY | F_BVH>(sv, a); f = F_EVERY | F_BVH; }
+    else if (stats) { run_grid_vx<true, F_EVERY>(sv, a); f = F_EVERY; }
+    else if (ext && bvh) { run_grid_vx<false, F_EVERY | F_BVH>(sv, a); f = F_EVERY | F_BVH; }
+    else if (ext) { run_grid_vx<false, F_EVERY>(sv, a); f = F_EVERY; }
+    else if (bvh && base == F_TREE) { run_grid_vx<false, F_TREE | F_BVH>(sv, a); f = F_TREE | F_BVH; }
+    else if (bvh) { run_grid_vx<false, F_ALL | F_BVH>(sv, a); f = F_ALL | F_BVH; }
+    else if (base == 0 && small) { run_grid_vx<false, F_SMALL>(sv, a); f = F_SMALL; }
+    else if (base == 0) { run_grid_vx<false, 0>(sv, a); f = 0; }
+    else if (base == F_TREE) { run_grid_vx<false, F_TREE>(sv, a); f = F_TREE; }
+    else if (base == (F_TRANSP | F_HDRI) && small) { run_grid_vx<false, F_TRANSP | F_HDRI | F_SMALL>(sv, a); f = F_TRANSP | F_HDRI | F_SMALL; }
+    else if (base == (F_TRANSP | F_HDRI)) { run_grid_vx<false, F_TRANSP | F_HDRI>(sv, a); f = F_TRANSP | F_HDRI; }
+    else { run_grid_vx<false, F_ALL>(sv, a); f = F_ALL; }
+    return f;
 }
 
 // The instantiation launch_render_impl (launch_impl.cuh) would launch for these features -- keep in step with it.
@@ -181,8 +227,8 @@ int run_render(const SceneView<R>& sv, const RenderArgs<R>& a, int stats, int fe
 }
 
 template <class R>
-int render_impl(const SceneView<R>& sv, const rptb_camera* cam, const rptb_render_params* p, int features, double* out_rgb,
-                rptb_stats* stats) {
+int render_impl(const SceneView<R>& sv, const rptb_camera* cam, const rptb_render_params* p, int features, uint32_t sampled_lights,
+                double* out_rgb, rptb_stats* stats) {
     RenderArgs<R> a;
     fill_args(cam, p, a);
     const size_t nvals = (size_t)p->width * p->height * 3;
@@ -195,7 +241,16 @@ int render_impl(const SceneView<R>& sv, const rptb_camera* cam, const rptb_rende
     a.partial = partial.empty() ? nullptr : partial.data();
     a.counters = &counters;
     int feat = -1;
-    if (a.ntiles_mine > 0) feat = run_render<R>(sv, a, (int)p->collect_stats, features);
+    if (a.ntiles_mine > 0) {
+        bool vx = false;
+        if constexpr (!M<R>::literal) {  // api.cu, render_launch: the vertex-at-once engine unless RPTB_VX=0 or a kd counting pass
+            const char* e = getenv("RPTB_VX");
+            a.ks = sampled_lights;
+            vx = !(e && std::strcmp(e, "0") == 0) && sampled_lights <= VX_MAX_SHADOW && p->collect_stats != 2;
+            if (vx) feat = run_render_vx(sv, a, (int)p->collect_stats, features);
+        }
+        if (!vx) feat = run_render<R>(sv, a, (int)p->collect_stats, features);
+    }
     for (size_t i = 0; i < nvals; i++) out_rgb[i] = (double)out[i];
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -267,10 +322,10 @@ int hostemu_render(const hostemu_scene* s, const rptb_camera* cam, const rptb_re
     if (!s || !cam || !p || !out_rgb || p->width == 0 || p->height == 0 || p->iterations == 0 ||
         p->max_bounces > MAX_BOUNCES_SUPPORTED)
         return -1;
-    if (p->precision == RPTB_PRECISION_F64) return render_impl<double>(s->v64, cam, p, F_ALL | (s->features & F_EXT), out_rgb, stats);
+    if (p->precision == RPTB_PRECISION_F64) return render_impl<double>(s->v64, cam, p, F_ALL | (s->features & F_EXT), s->hs.sampled_lights, out_rgb, stats);
     int feats = s->features;
     if ((feats & F_EXT) && !ext_bvh) feats &= ~F_BVH;
-    return render_impl<float>(s->v32, cam, p, feats, out_rgb, stats);
+    return render_impl<float>(s->v32, cam, p, feats, s->hs.sampled_lights, out_rgb, stats);
 }
 
 int hostemu_bvh_check(const hostemu_scene* s, uint32_t mesh, uint64_t* out) {
