@@ -278,8 +278,12 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device and rpt_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # a barrier the waiting ranks sit in on the CPU: while rank 0 drives all N GPUs through ONE rptb_render_samples
+        # call (e2e leg), an NCCL barrier kernel spinning on the other ranks' GPUs would time-slice against its kernels
+        cpu_group = dist.new_group(backend="gloo")
     engine = {"auto": capi.ENGINE_AUTO, "megakernel": capi.ENGINE_MEGAKERNEL, "wavefront": capi.ENGINE_WAVEFRONT}[args.engine]
     stream = torch.cuda.Stream(dev)
     raw = stream.cuda_stream
@@ -289,6 +293,10 @@ def run_native(args):
     def barrier():
         if world > 1:
             dist.barrier()
+
+    def cpu_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     def allsum(vals, dtype=torch.int64):
         t = torch.tensor(vals, dtype=dtype, device=dev)
@@ -397,14 +405,16 @@ def run_native(args):
 
             stream.synchronize()
             barrier()
+            torch.cuda.synchronize()
+            cpu_barrier()
             e2e_s = 0.0
-            if rank == 0:  # the fan-out over the N GPUs lives inside rptb_render_samples: one caller, the other ranks wait
+            if rank == 0:  # the fan-out over the N GPUs lives inside rptb_render_samples: one caller, the other ranks wait (on the CPU)
                 e2e_step()  # warm-up
                 t0 = time.perf_counter()
                 for _ in range(K):
                     e2e_step()
                 e2e_s = time.perf_counter() - t0
-            barrier()
+            cpu_barrier()
             if rank == 0:
                 e2e = {
                     "value": total["segments"] * K / e2e_s / 1e6, "unit": UNIT,

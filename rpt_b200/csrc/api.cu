@@ -183,7 +183,6 @@ struct rptb_scene {
     size_t wf_bytes = 0;
     double* partial = nullptr;      // per-chunk pixel sums of the megakernel (nchunks > 1)
     size_t partial_bytes = 0;
-    uint32_t* wf_pinned = nullptr;  // page-locked word for the step loop's termination check
     // A render enqueued on a caller's stream returns before it has run, while it still uses the scratch above
     // (partial, counters, out64, wf_mem).  `busy` is recorded behind it; the next call on ANY stream -- and every
     // stream-ordered free or reallocation of scratch on `stream` -- first waits for it.
@@ -351,24 +350,19 @@ int render_launch(rptb_scene* s, const rptb_camera* cam, const rptb_render_param
                 CU(cudaStreamSynchronize(s->stream));  // the render may run on a caller's stream
                 s->wf_bytes = need;
             }
-            if (!s->wf_pinned) CU(cudaHostAlloc((void**)&s->wf_pinned, sizeof(uint32_t), cudaHostAllocDefault));
             std::vector<char> bufs(wavefront_struct_size());
-            float blo[3], binv[3];
-            for (int r = 0; r < 3; r++) {
-                const double ext = s->whi[r] - s->wlo[r];
-                blo[r] = (float)s->wlo[r];
-                binv[r] = (float)(ext > 0 && std::isfinite(ext) ? 1.0 / ext : 0.0);
-            }
-            wavefront_carve(s->wf_mem, npix, G, s->sampled_lights, maxd, blo, binv, (WfBuffers*)bufs.data());
-            CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, (s->features & F_BVH) != 0, stream, s->wf_pinned, launches));
+            wavefront_carve(s->wf_mem, npix, G, s->sampled_lights, maxd, (WfBuffers*)bufs.data());
+            CU(run_wavefront_f32(s->view32, a, (const WfBuffers*)bufs.data(), p->collect_stats != 0, (s->features & F_BVH) != 0, stream, launches));
         } else {
             const int rc = ensure_partial(s, a);
             if (rc != RPTB_OK) return rc;
             a.ks = s->sampled_lights;
-            // the vertex-at-once schedule (integrator_vx.cuh) renders every scene it has ray slots for; RPTB_VX=0 keeps the
-            // slot schedule (A/B runs).  A counting pass over the reference-shaped kd-trees (collect_stats = 2) is the slot engine's.
-            static const bool vx_off = getenv("RPTB_VX") != nullptr && std::strcmp(getenv("RPTB_VX"), "0") == 0;
-            if (!vx_off && vx_supported(a.ks) && p->collect_stats != 2) CU(launch_render_vx_f32(s->view32, a, (int)p->collect_stats, s->features, stream, launches));
+            // RPTB_VX=1 selects the vertex-at-once schedule (integrator_vx.cuh) where it has ray slots for the scene's lights.
+            // Measured on one B200 (profiles/r02_vx_vs_slot.md): it loses to the slot schedule on every BASELINE config but
+            // glass (+8 %), so the slot schedule stays the default.  A counting pass over the reference-shaped kd-trees
+            // (collect_stats = 2) is always the slot engine's.
+            static const bool vx_on = getenv("RPTB_VX") != nullptr && std::strcmp(getenv("RPTB_VX"), "1") == 0;
+            if (vx_on && vx_supported(a.ks) && p->collect_stats != 2) CU(launch_render_vx_f32(s->view32, a, (int)p->collect_stats, s->features, stream, launches));
             else CU(launch_render_f32(s->view32, a, (int)p->collect_stats, s->features, stream, launches));
         }
     } else {
@@ -476,7 +470,6 @@ void destroy_replica(rptb_scene* s) {
     if (s->counters) cudaFreeAsync(s->counters, s->stream);
     if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
     if (s->partial) cudaFreeAsync(s->partial, s->stream);
-    if (s->wf_pinned) cudaFreeHost(s->wf_pinned);
     if (s->stage) cudaFreeHost(s->stage);
     if (s->out32) cudaFreeAsync(s->out32, s->stream);
     if (s->out64) cudaFreeAsync(s->out64, s->stream);

@@ -152,8 +152,14 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
     const R xn = ((R)(2u * x + 1u) - (R)a.width) / dim;
     const R yn = ((R)(2u * (a.height - y) - 1u) - (R)a.height) / dim;
 
-    uint32_t Ks = 0;  // lights that need a shadow ray (warp-uniform)
-    for (uint32_t i = 0; i < sv.nlights; i++) Ks += scene_light<FEAT>(sv, i).kind != LIGHT_AMBIENT ? 1u : 0u;
+    uint32_t Ks = 0;        // lights that need a shadow ray (warp-uniform)
+    uint32_t draw_hint = 0;  // 4 bits per sampled light (the first 8): draws its sample typically takes
+    for (uint32_t i = 0; i < sv.nlights; i++) {
+        const LightRec<R>& l = scene_light<FEAT>(sv, i);
+        if (l.kind == LIGHT_AMBIENT) continue;
+        if (Ks < 8u) draw_hint |= light_draws_hint(l) << (4u * Ks);
+        Ks++;
+    }
 
     PathCounters pc = {0, 0, 0, 0, {0, 0, 0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -191,8 +197,15 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
     uint32_t slot = Ks;  // every lane starts with a camera ray
 
     while (true) {
-        rng.template ensure<W>(wmask);  // converged here: the lanes that are short of draws compute their Philox blocks together
         const bool light_slot = slot < Ks;
+        {   // converged here: the lanes that are short of draws for this slot compute their Philox blocks together
+            uint32_t need = 0;
+            if (status == ST_VERTEX && !dead) {
+                if (light_slot) need = slot < 8u ? (draw_hint >> (4u * slot)) & 15u : 4u;
+                else if ((uint32_t)depth < a.max_bounces) need = 4u;  // gen_bool + Beckmann (1 + UnitCircle) or UnitDisc
+            }
+            rng.template ensure<W>(wmask, need);
+        }
         bool active = false;  // this lane sends a ray through the trace site in this slot
 
         if (light_slot) {

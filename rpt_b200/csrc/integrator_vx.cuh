@@ -134,8 +134,10 @@ RPTB_D void vx_trace(const SceneView<float>& sv, const VxShared& S, const uint32
                 count += W::popc(m);
             }
             W::sync(wmask);
-            for (uint32_t b = 0; b < count; b += W::width) {
-                const uint32_t it = b + lane;
+            // (a warp at the image's edge has fewer than 32 lanes: stride by the lanes that exist, index by rank among them)
+            const uint32_t nact = W::popc(wmask), myrank = W::rank(wmask, lane);
+            for (uint32_t b = 0; b < count; b += nact) {
+                const uint32_t it = b + myrank;
                 if (it < count) {
                     const uint32_t id = work[it];  // slot * 128 + owner thread: possibly another lane's ray
                     const bool any = (id / T) != seg;
@@ -212,6 +214,8 @@ RPTB_D void render_thread_vx(const SceneView<float>& sv, const RenderArgs<float>
     const R xn = ((R)(2u * x + 1u) - (R)a.width) / dim;
     const R yn = ((R)(2u * (a.height - y) - 1u) - (R)a.height) / dim;
     const uint32_t Ks = a.ks, k1 = Ks + 1u;  // sampled (non-ambient) lights; ray slots
+    uint32_t lights_need = 0;  // draws the light samples of one vertex typically take (refill hint, rng.cuh)
+    for (uint32_t i = 0; i < sv.nlights; i++) lights_need += light_draws_hint(scene_light<FEAT>(sv, i));
     const VxShared S = vx_carve(smem, k1);
 
     PathCounters pc = {0, 0, 0, 0, {0, 0, 0, 0, 0}};
@@ -266,7 +270,7 @@ RPTB_D void render_thread_vx(const SceneView<float>& sv, const RenderArgs<float>
         Vec3<R> w = {(R)0, (R)0, (R)0};  // weight f |cos| / pdf of the bounce
 
         // ================= sample_lights: every light's sample, in list order (renderer.rs:177-204) ==========
-        rng.template ensure<W>(wmask);
+        rng.template ensure<W>(wmask, status == ST_VERTEX && !dead ? lights_need : 0u);
         if (status == ST_VERTEX) {
             const MaterialRec<R> mat = sv.materials[mat_id];
             uint32_t jj = 0;
@@ -299,7 +303,7 @@ RPTB_D void render_thread_vx(const SceneView<float>& sv, const RenderArgs<float>
             }
         }
         // ================= Material::sample_f: the bounce (renderer.rs:156-164) ==============================
-        rng.template ensure<W>(wmask);
+        rng.template ensure<W>(wmask, status == ST_VERTEX && !dead && depth < a.max_bounces ? 4u : 0u);
         if (status == ST_VERTEX) {
             bool bounce = false;
             if (depth < a.max_bounces && !dead) {
@@ -332,7 +336,7 @@ RPTB_D void render_thread_vx(const SceneView<float>& sv, const RenderArgs<float>
         const uint32_t s_cam = ending ? s + 1u : s;
         const bool want_cam = (status == ST_FRESH || ending) && s_cam < s_end;
         if (want_cam) rng.init(a.seed, pix, a.first_sample + s_cam);
-        rng.template ensure<W>(wmask);
+        rng.template ensure<W>(wmask, want_cam ? (a.cam.aperture > (R)0 ? 4u : 2u) : 0u);
         if (want_cam) {
             const R dx = gen_range(rng, (R)-1 / dim, (R)1 / dim);
             const R dy = gen_range(rng, (R)-1 / dim, (R)1 / dim);

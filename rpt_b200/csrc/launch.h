@@ -28,14 +28,13 @@ struct WfBuffers;
 // bytes of device memory the engine needs for (npaths, Ks sampled lights, maxd levels)
 size_t wavefront_bytes(uint32_t npaths, uint32_t Ks, uint32_t maxd);
 // carve `mem` (wavefront_bytes big, 256-byte aligned) into the engine's arrays
-void wavefront_carve(void* mem, uint32_t npix, uint32_t G, uint32_t Ks, uint32_t maxd, const float* bounds_lo,
-                     const float* bounds_inv_extent, WfBuffers* out);
+void wavefront_carve(void* mem, uint32_t npix, uint32_t G, uint32_t Ks, uint32_t maxd, WfBuffers* out);
 uint32_t wavefront_groups(uint32_t npix, uint32_t nchunks);
 size_t wavefront_struct_size();
-// run Renderer::sample with the wavefront schedule; blocks until the image is in args.out
-// (the step loop is driven from the host).  `pinned` = 4 bytes of page-locked host memory.
+// run Renderer::sample with the wavefront schedule: everything is enqueued on `stream` (the step loop is a CUDA graph
+// WHILE node re-armed on the device); the call does not wait
 cudaError_t run_wavefront_f32(const SceneView<float>& sv, const RenderArgs<float>& args, const WfBuffers* bufs,
-                              bool stats, bool use_bvh, cudaStream_t stream, uint32_t* pinned, uint32_t* launches);
+                              bool stats, bool use_bvh, cudaStream_t stream, uint32_t* launches);
 
 // ---- the vertex-at-once f32 megakernel (integrator_vx.cuh; its own translation unit, kernels_vx.cu) -----------------
 // stats as in launch_render_f32.  args.ks must be <= VX_MAX_SHADOW (vx_supported).

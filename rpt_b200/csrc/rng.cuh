@@ -104,7 +104,7 @@ struct Rng<double> {
     RPTB_HD void bind(uint32_t*, uint32_t) {}
     RPTB_HD void ensure() {}
     template <class W>
-    RPTB_HD void ensure(unsigned) {}
+    RPTB_HD void ensure(unsigned, uint32_t) {}
     RPTB_HD double gen() { return (double)(p.next_u64() >> 11) * (1.0 / 9007199254740992.0); }
     RPTB_HD double u52() { return (double)(p.next_u64() >> 12) * (1.0 / 4503599627370496.0); }
     // Rng::gen_bool(p): Bernoulli -> u64 < p * 2^64
@@ -174,7 +174,7 @@ struct Rng<float> {
         if (avail <= 2) push_block();
     }
     template <class W>
-    RPTB_HD void ensure(unsigned) { ensure(); }
+    RPTB_HD void ensure(unsigned, uint32_t) { ensure(); }
     RPTB_HD void bind(uint32_t*, uint32_t) {}
     RPTB_HD uint32_t next32() {
         if (avail == 0) push_block();  // rare: a slot consumed more than the FIFO held
@@ -205,8 +205,8 @@ struct Rng<float> {
 // one bank per lane, no conflicts; a ring in registers would need shuffling moves per draw and four more live
 // registers in a kernel that already spills).  What this buys (ncu, Cornell, round 2): with the 4-entry register FIFO
 // a slot that drew more than the FIFO held refilled it inside whatever rejection loop it was in -- the ~60-instruction
-// Philox block ran at 7.4 of 32 lanes and was 27 % of the kernel's warp instructions.  ensure() now tops every lane
-// up to >= 6 entries where the warp is converged, and all lanes that need a block compute it together.
+// Philox block ran at 7.4 of 32 lanes and was 27 % of the kernel's warp instructions.  ensure() tops a lane up to
+// what it is about to draw where the warp is converged, and all lanes that need a block compute it together.
 constexpr uint32_t RNG_RING = 8;
 struct RngRing {
     uint32_t key0, key1, block, pixel, samp_lo, samp_hi;
@@ -248,11 +248,15 @@ struct RngRing {
         at(head + avail + 1u) = b;
         avail += 2;
     }
-    // W = the warp policy of integrator.cuh (real votes on the device, a single lane in host emulation)
+    // W = the warp policy of integrator.cuh (real votes on the device, a single lane in host emulation).  `need` = how
+    // many draws this lane expects to take before the next converged point (0 for a lane that will draw nothing): the
+    // lanes that are short compute their blocks together, nobody generates draws on speculation -- a path that ends
+    // after two draws (a camera ray that leaves the scene) costs one Philox block, not a ring full.
     template <class W>
-    RPTB_HD void ensure(unsigned mask) {
-        while (W::any(mask, avail <= 5u)) {
-            if (avail <= RNG_RING - 2u) push_block();
+    RPTB_HD void ensure(unsigned mask, uint32_t need) {
+        // (a block is two entries: a lane can take one while avail <= RNG_RING - 2)
+        while (W::any(mask, avail < need && avail <= RNG_RING - 2u)) {
+            if (avail < need && avail <= RNG_RING - 2u) push_block();
         }
     }
     RPTB_HD uint32_t next32() {

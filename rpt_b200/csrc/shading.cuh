@@ -302,6 +302,19 @@ RPTB_D void shape_sample(const SceneView<R>& sv, const ObjectRec<R>& ob, Vec3<R>
     }
 }
 
+// How many draws Light::illuminate typically takes (a hint for the generator's refill, rng.cuh): none for point and
+// directional lights; UnitDisc for a sphere (2 per try), index + rejection pairs for a mesh, 3 for a cube, more below a group.
+template <class R>
+RPTB_D uint32_t light_draws_hint(const LightRec<R>& l) {
+    if (l.kind != LIGHT_OBJECT) return 0u;
+    switch (l.object.kind) {
+        case SHAPE_SPHERE: return 4u;
+        case SHAPE_CUBE: return 3u;
+        case SHAPE_MESH: return 5u;
+        default: return 6u;
+    }
+}
+
 // Light::illuminate (light.rs:23-47) for the non-ambient kinds
 template <class R, int FEAT = F_ALL, class RNG>
 RPTB_D void illuminate(const SceneView<R>& sv, const LightRec<R>& l, Vec3<R> pos, RNG& rng, Vec3<R>& intensity,

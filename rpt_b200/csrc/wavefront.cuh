@@ -86,46 +86,11 @@ struct WfBuffers {
     WfHit* hits;      // npaths * (Ks + 1)
     uint32_t* list;   // compact list of live ray slots
     uint32_t* count;  // [0] rays emitted this step, [1] fetch cursor of the trace kernel
-    // ray sorting (coherence): Morton keys of the listed rays and the double buffers of the radix sort
-    uint32_t* keys;
-    uint32_t* keys_alt;
-    uint32_t* list_alt;
-    void* sort_tmp;
-    size_t sort_tmp_bytes;
-    float bounds_lo[3], bounds_inv[3];  // world bounds of the kd-tree meshes (key quantisation)
     // npaths = npix * G: every owned pixel slot has G paths in flight, path (slot, g) sums the sample
     // chunks g, g + G, g + 2G, ... one after the other (the chunk sums are resolved in chunk order, so
     // the image does not depend on G -- which is chosen per launch to keep ~2M paths in flight)
     uint32_t npaths, npix, G, Ks, maxd;
 };
-
-// Sort key of a ray: [shadow?:1][Morton code of the origin, 9 bits per axis, with the direction octant
-// spliced in below its top 15 bits].  Rays that start in the same cell and head the same way descend the
-// same part of the tree: neighbouring lanes then share nodes (L1 hits) and leave the descent loop
-// together.  Unused list entries get the maximal key and sort to the end.
-RPTB_D uint32_t wf_spread3(uint32_t v) {  // 9 bits -> every third bit
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-__global__ void wf_key_kernel(const WfBuffers b, uint32_t capacity) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= capacity) return;
-    uint32_t key = 0xFFFFFFFFu;
-    if (i < b.count[0]) {
-        const WfRay r = b.rays[b.list[i]];
-        const float fx = fminf(fmaxf((r.ox - b.bounds_lo[0]) * b.bounds_inv[0], 0.f), 1.f);
-        const float fy = fminf(fmaxf((r.oy - b.bounds_lo[1]) * b.bounds_inv[1], 0.f), 1.f);
-        const float fz = fminf(fmaxf((r.oz - b.bounds_lo[2]) * b.bounds_inv[2], 0.f), 1.f);
-        const uint32_t qx = min((uint32_t)(fx * 512.f), 511u), qy = min((uint32_t)(fy * 512.f), 511u), qz = min((uint32_t)(fz * 512.f), 511u);
-        const uint32_t morton = (wf_spread3(qx) << 2) | (wf_spread3(qy) << 1) | wf_spread3(qz);  // 27 bits
-        const uint32_t oct = (r.dx < 0.f ? 4u : 0u) | (r.dy < 0.f ? 2u : 0u) | (r.dz < 0.f ? 1u : 0u);
-        key = ((r.any ? 1u : 0u) << 30) | ((morton >> 12) << 15) | (oct << 12) | (morton & 0xFFFu);
-    }
-    b.keys[i] = key;
-}
 
 RPTB_D void wf_pixel_of(const RenderArgs<float>& a, uint32_t slot, uint32_t& x, uint32_t& y) {
     const uint32_t k = slot / RENDER_THREADS, tid = slot % RENDER_THREADS;

@@ -117,7 +117,7 @@ struct HostLane {
     static __host__ __device__ bool any(unsigned, bool p) { return p; }
     static constexpr uint32_t width = 1u;
     static __host__ __device__ unsigned ballot(unsigned, bool p) { return p ? 1u : 0u; }
-    static __host__ __device__ uint32_t rank(unsigned, uint32_t) { return 0u; }
+    static __host__ __device__ uint32_t rank(unsigned, uint32_t) { return 0u; }  // lanes below me among the voters: none
     static __host__ __device__ uint32_t popc(unsigned v) { uint32_t c = 0; while (v) { c += v & 1u; v >>= 1; } return c; }
     static __host__ __device__ void sync(unsigned) {}
     static __host__ __device__ uint32_t reduce_add(unsigned, uint32_t v) { return v; }
@@ -246,7 +246,7 @@ int render_impl(const SceneView<R>& sv, const rptb_camera* cam, const rptb_rende
         if constexpr (!M<R>::literal) {  // api.cu, render_launch: the vertex-at-once engine unless RPTB_VX=0 or a kd counting pass
             const char* e = getenv("RPTB_VX");
             a.ks = sampled_lights;
-            vx = !(e && std::strcmp(e, "0") == 0) && sampled_lights <= VX_MAX_SHADOW && p->collect_stats != 2;
+            vx = e && std::strcmp(e, "1") == 0 && sampled_lights <= VX_MAX_SHADOW && p->collect_stats != 2;
             if (vx) feat = run_render_vx(sv, a, (int)p->collect_stats, features);
         }
         if (!vx) feat = run_render<R>(sv, a, (int)p->collect_stats, features);

@@ -452,3 +452,20 @@ def test_bvh_over_a_handful_of_triangles_behind_a_split_kd_root(orc):
         assert np.abs(tb[hit] - t0[hit]).max() < 1e-5
         if ntris >= 2:
             assert e.features & 64 and sb["bvh_node_visits"] > 0
+
+
+@pytest.mark.parametrize("name", ["cornell", "teapot", "glass", "dragon", "sphere"])
+def test_vertex_at_once_engine_is_the_slot_engine_bit_for_bit(orc, monkeypatch, name):
+    """integrator_vx.cuh (RPTB_VX=1: all rays of a path vertex staged at once, BVH traversals compacted into a work list)
+    performs, per path, exactly the slot engine's operations in exactly its order: same images to the last bit, same
+    segment and ray counts -- run one lane at a time here; tests/test_gpu_vx.py compares real warps on the GPU."""
+    size = {"cornell": (48, 48, 70, 6), "teapot": (64, 36, 8, 0), "glass": (48, 27, 16, 12), "dragon": (64, 36, 8, 2), "sphere": (48, 27, 16, 2)}[name]
+    w, h, spp, mb = size
+    cfg = scenes.glass_scene(64, 32) if name == "glass" else (scenes.dragon_scene(level=0) if name == "dragon" else scenes.CONFIGS[name]())
+    e = emu.EmuScene(api.FlatScene(cfg.scene, accel=capi.ACCEL_BVH))
+    monkeypatch.setenv("RPTB_VX", "0")
+    a, sa, fa = e.render(cfg.camera, _params(cfg, w, h, spp, mb))
+    monkeypatch.setenv("RPTB_VX", "1")
+    b, sb, fb = e.render(cfg.camera, _params(cfg, w, h, spp, mb))
+    np.testing.assert_array_equal(a, b)
+    assert sa["segments"] == sb["segments"] and sa["rays"] == sb["rays"] and fa == fb

@@ -1,7 +1,10 @@
 """Summarise one `ncu --set full` capture as markdown: key metrics, stall reasons and (when the object file the
 capture ran is still in build/obj) the per-source-line hot spots of tools/ncu_lines.py.
 
-    python tools/ncu_summary.py <report.ncu-rep> "<title>" [> profiles/rNN_<what>.md]
+    python tools/ncu_summary.py <report.ncu-rep> "<title>" [<object file the capture ran | - >] [> profiles/rNN_<what>.md]
+
+The source-line section needs the VERY object file the captured kernel came from (its SASS offsets are the join key):
+pass the copy saved next to the capture, or `-` to leave the section out.
 """
 import csv, io, os, subprocess, sys
 
@@ -42,16 +45,17 @@ def main():
         print("| %s | %.3f |" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
     # the raw page has the demangled short name only: rebuild the mangled one for render_kernel<R, MAXD, STATS, FEAT>
     import re
-    obj = os.path.join(ROOT, "build", "obj", "kernels_f32.o")
+    obj = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "build", "obj", "kernels_f32.o")
     name = d.get("Kernel Name", ("", ""))[0]
-    mangled = sys.argv[3] if len(sys.argv) > 3 else None
+    mangled = None
     m = re.match(r"void render_kernel<(float|double), (\d+), (\d+), (\d+)>", name)
-    if not mangled and m:
+    if m and obj != "-":
         mangled = "_ZN4rptb13render_kernelI%sLi%sELb%sELi%sEEEvNS_9SceneViewIT_EENS_10RenderArgsIS2_EE" % (
             "f" if m.group(1) == "float" else "d", m.group(2), m.group(3), m.group(4))
-        if m.group(1) == "double":
-            obj = os.path.join(ROOT, "build", "obj", "kernels_f64.o")
-    if mangled:
+    m = re.match(r"void render_kernel_vx<(\d+), (\d+)>", name)
+    if m and obj != "-":
+        mangled = "_ZN4rptb16render_kernel_vxILb%sELi%sEEEvNS_9SceneViewIfEENS_10RenderArgsIfEE" % (m.group(1), m.group(2))
+    if mangled and os.path.exists(obj):
         tool = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, obj, mangled, "30"], capture_output=True, text=True)
         print("\n## Source-level hot spots (ncu SASS counters joined with nvdisasm line info, tools/ncu_lines.py)\n\n```")
         print((tool.stdout or tool.stderr).rstrip())
