@@ -26,6 +26,7 @@
 namespace {
 
 using rptb::BvhNodeDev;
+using rptb::Bvh8Node;
 
 struct Box {
     float lo[3], hi[3];
@@ -195,6 +196,42 @@ int32_t child_code(const Node& n, std::vector<BvhNodeDev>& out, uint32_t depth, 
     return emit_inner(n, out, depth, max_depth);
 }
 
+// ---- the eight-wide form: collapse the binary tree --------------------------------------------------------------
+// Starting from a node's two children, the inner child with the largest surface area is replaced by its own two
+// children until there are eight (or only leaves are left): the usual greedy collapse.  Leaves are kept as they are.
+int32_t emit8(const Node& n, std::vector<Bvh8Node>& out, uint32_t depth, uint32_t& max_depth) {
+    const size_t me = out.size();
+    out.emplace_back();
+    max_depth = std::max(max_depth, depth);
+    const Node* kids[8];
+    int nk = 2;
+    kids[0] = n.kid[0].get();
+    kids[1] = n.kid[1].get();
+    while (nk < 8) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int i = 0; i < nk; i++)
+            if (!kids[i]->count && kids[i]->box.half_area() > best_area) best_area = kids[i]->box.half_area(), best = i;
+        if (best < 0) break;
+        const Node* open = kids[best];
+        kids[best] = open->kid[0].get();
+        kids[nk++] = open->kid[1].get();
+    }
+    Bvh8Node node;
+    std::memset(&node, 0, sizeof(node));
+    for (int i = 0; i < 8; i++) {
+        rptb::Bvh8Child& c = node.c[i];
+        if (i >= nk) {
+            c.code = rptb::BVH8_EMPTY;
+            continue;
+        }
+        pad(kids[i]->box, c.lo, c.hi);
+        c.code = kids[i]->count ? ~(int32_t)((kids[i]->first << 3) | (kids[i]->count - 1u)) : emit8(*kids[i], out, depth + 1, max_depth);
+    }
+    out[me] = node;
+    return (int32_t)me;
+}
+
 }  // namespace
 
 namespace rptb {
@@ -205,7 +242,7 @@ namespace rptb {
 // whose two children are the halves of that leaf (the same leaf twice for a single triangle -- the second test of a
 // triangle can never tighten the hit, `time >= h.t` rejects it).
 int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& nodes, std::vector<uint32_t>& order,
-                   uint32_t& depth) {
+                   uint32_t& depth, std::vector<Bvh8Node>* nodes8) {
     if (ntris == 0 || ntris >= (1ull << 28)) return -1;
     std::vector<Prim> prims(ntris);
     for (uint64_t i = 0; i < ntris; i++) {
@@ -248,6 +285,11 @@ int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& 
         root->count = 0;
     }
     emit_inner(*root, nodes, 0, depth);
+    if (nodes8) {
+        nodes8->clear();
+        uint32_t depth8 = 0;
+        emit8(*root, *nodes8, 0, depth8);
+    }
     order.resize(ntris);
     for (uint64_t i = 0; i < ntris; i++) order[i] = prims[i].id;
     return 0;

@@ -359,6 +359,201 @@ RPTB_D bool bvh_intersect(const MeshRec<double>&, Vec3<double>, Vec3<double>, do
     return false;  // the f64 gate never uses the BVH
 }
 
+// ------------------------------------------------- the eight-wide BVH --------
+// Per-lane (scalar) traversal of the collapsed tree: test infrastructure for the builder (tests/hostemu checks its hits
+// against the binary tree's) -- the product traverses Bvh8Node with groups of eight lanes, below.
+template <bool STATS>
+RPTB_D bool bvh8_intersect_scalar(const MeshRec<float>& m, Vec3<float> o, Vec3<float> d, float tmin, bool any, Hit<float>& h,
+                                  TravStats& ts) {
+    const Vec3<float> inv = {slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z)};
+    const Vec3<float> oi = {o.x * inv.x, o.y * inv.y, o.z * inv.z};
+    int32_t stack[8 * BVH8_STACK];
+    int sp = 0;
+    stack[sp++] = 0;
+    bool hit = false;
+    while (sp > 0) {
+        const int32_t cur = stack[--sp];
+        if (cur >= 0) {
+            if (STATS) ts.bvh_nodes += 4;
+            const Bvh8Node& n = m.bvh8_nodes[cur];
+            for (int k = 0; k < 8; k++) {
+                const Bvh8Child& c = n.c[k];
+                if (c.code == BVH8_EMPTY) continue;
+                const float x0 = fmaf(c.lo[0], inv.x, -oi.x), x1 = fmaf(c.hi[0], inv.x, -oi.x);
+                const float y0 = fmaf(c.lo[1], inv.y, -oi.y), y1 = fmaf(c.hi[1], inv.y, -oi.y);
+                const float z0 = fmaf(c.lo[2], inv.z, -oi.z), z1 = fmaf(c.hi[2], inv.z, -oi.z);
+                const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+                const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), h.t));
+                if (tn <= tf && sp < 8 * BVH8_STACK) stack[sp++] = c.code;
+            }
+            continue;
+        }
+        const uint32_t code = (uint32_t)~cur;
+        const uint32_t first = code >> 3, count = (code & 7u) + 1u;
+        for (uint32_t k = first; k < first + count; k++) {
+            if (STATS) ts.bvh_tris++;
+            const float4* q = m.bvh_tri48 + 3 * (size_t)k;
+            const float4 q0 = ldg(q);
+            const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+            if (fabsf(cosine) < 1e-8f) continue;
+            const float time = fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+            if (time < tmin || time >= h.t) continue;
+            const float4 q1 = ldg(q + 1), q2 = ldg(q + 2);
+            const float px = fmaf(time, d.x, o.x), py = fmaf(time, d.y, o.y), pz = fmaf(time, d.z, o.z);
+            const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
+            const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
+            if (1.0f - v - w >= 0.0f && v >= 0.0f && w >= 0.0f) {
+                h.t = time; h.bv = v; h.bw = w; h.aux = ldg(m.bvh_ids + k);
+                hit = true;
+            }
+        }
+        if (any && hit) return true;
+    }
+    return hit;
+}
+
+#if defined(__CUDACC__) && !defined(RPTB_HOST_EMU)
+// ---- traversal by groups of eight lanes ---------------------------------------------------------------------------
+// ncu (round 2, dragon configs): with one ray per lane the binary-BVH node loop ran at 5-6 of 32 lanes however the
+// rays were scheduled -- the rays of a warp that enter a mesh at all are few, and their traversal lengths spread over
+// two orders of magnitude, so a warp spends its time walking the one or two longest rays with everybody else idle.
+// The idle width is therefore spent INSIDE a ray: the warp's rays that pass the mesh's root box are compacted (warp
+// vote) into this per-warp block of shared memory, and each group of eight lanes takes one ray at a time off that list
+// (an atomic cursor in shared memory: the four groups balance themselves).  Per node, lane k of the group loads child k
+// (one coalesced 256-byte request per group), tests its box, and three votes later the group knows which children are
+// hit, which is nearest, and in what order the others go on the group's stack (shared memory, nearest on top).  A leaf's
+// <= 4 triangles are tested one per lane.  A ray walks ~3x fewer, fatter steps than in the binary tree, and four rays
+// advance per warp instruction instead of "the slowest of 32".
+struct __align__(16) CoopWarp {
+    float4 ra[32];   // compacted rays, mesh-local: origin, closest t so far
+    float4 rb[32];   // direction
+    float4 res[32];  // answer: t (< 0: no hit; -2: stack overflow, redo with the binary tree), bv, bw, triangle id bits
+    uint2 stack[4][BVH8_STACK];  // per group: (child code, entry t bits)
+    uint32_t next;   // cursor into the list
+    uint32_t _pad[3];
+};
+
+template <bool STATS>
+__device__ __forceinline__ void bvh8_group_trace(const MeshRec<float>& m, CoopWarp& cw, const uint32_t count, const bool any,
+                                                 const uint32_t lane, TravStats& ts) {
+    const float tmin = 1e-12f;
+    const uint32_t k = lane & 7u, gbase = lane & ~7u;
+    const unsigned gmask = 0xFFu << gbase;
+    uint2* const stack = cw.stack[lane >> 3];
+    while (true) {
+        uint32_t it = 0;
+        if (k == 0u) it = atomicAdd(&cw.next, 1u);
+        it = __shfl_sync(gmask, it, gbase);
+        if (it >= count) break;
+        const float4 A = cw.ra[it], B = cw.rb[it];
+        const Vec3<float> o = {A.x, A.y, A.z}, d = {B.x, B.y, B.z};
+        const Vec3<float> inv = {slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z)};
+        const Vec3<float> oi = {o.x * inv.x, o.y * inv.y, o.z * inv.z};
+        float ht = A.w;  // everything below that is not per-child is identical in the eight lanes of the group
+        bool hit = false, overflow = false, done = false;
+        int32_t cur = 0;
+        int sp = 0;
+        while (!done) {
+            bool pop = false;
+            if (cur >= 0) {
+                if (STATS && k == 0u) ts.bvh_nodes += 4;  // 256 bytes = four 64-byte units of the bytes model
+                const float4* c = reinterpret_cast<const float4*>(&m.bvh8_nodes[cur].c[k]);
+                const float4 c0 = ldg(c), c1 = ldg(c + 1);  // lo.x lo.y lo.z hi.x | hi.y hi.z code pad
+                const int32_t code = __float_as_int(c1.z);
+                const float x0 = fmaf(c0.x, inv.x, -oi.x), x1 = fmaf(c0.w, inv.x, -oi.x);
+                const float y0 = fmaf(c0.y, inv.y, -oi.y), y1 = fmaf(c1.x, inv.y, -oi.y);
+                const float z0 = fmaf(c0.z, inv.z, -oi.z), z1 = fmaf(c1.y, inv.z, -oi.z);
+                const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+                const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ht));
+                const bool hc = code != BVH8_EMPTY && tn <= tf;
+                const unsigned hm = (__ballot_sync(gmask, hc) >> gbase) & 0xFFu;
+                if (hm == 0u) {
+                    pop = true;
+                } else {
+                    const uint32_t key = hc ? __float_as_uint(tn) : 0xFFFFFFFFu;  // tn >= tmin > 0: the bits order like the value
+                    const uint32_t kmin = __reduce_min_sync(gmask, key);
+                    const unsigned nm = (__ballot_sync(gmask, key == kmin) >> gbase) & 0xFFu;
+                    const int nl = __ffs(nm) - 1;  // the nearest child's lane
+                    const int32_t ncode = __shfl_sync(gmask, code, gbase + nl);
+                    const int nh = __popc(hm);
+                    if (nh > 1) {
+                        if (sp + nh - 1 > BVH8_STACK) {
+                            overflow = true;
+                            done = true;
+                        } else {
+                            // position on the stack: the farther, the deeper (so the nearest of the rest is popped first)
+                            uint32_t rank = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const uint32_t kj = __shfl_sync(gmask, key, gbase + j);
+                                if (j != nl && ((hm >> j) & 1u) && (kj > key || (kj == key && j > (int)k))) rank++;
+                            }
+                            if (hc && (int)k != nl) stack[sp + rank] = make_uint2((uint32_t)code, key);
+                            sp += nh - 1;
+                            __syncwarp(gmask);
+                        }
+                    }
+                    cur = ncode;
+                }
+            } else {
+                // leaf: ~cur = (first << 3) | (count - 1); one triangle per lane (Triangle::intersect as in tri_intersect)
+                const uint32_t code = (uint32_t)~cur;
+                const uint32_t first = code >> 3, cnt = (code & 7u) + 1u;
+                if (STATS && k == 0u) ts.bvh_tris += cnt;
+                uint32_t key = 0xFFFFFFFFu;
+                float bv = 0.0f, bw = 0.0f;
+                if (k < cnt) {
+                    const float4* q = m.bvh_tri48 + 3 * (size_t)(first + k);
+                    const float4 q0 = ldg(q);
+                    const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+                    if (!(fabsf(cosine) < 1e-8f)) {
+                        const float time = __fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+                        if (!(time < tmin || time >= ht)) {
+                            const float4 q1 = ldg(q + 1), q2 = ldg(q + 2);
+                            const float px = fmaf(time, d.x, o.x), py = fmaf(time, d.y, o.y), pz = fmaf(time, d.z, o.z);
+                            const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
+                            const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
+                            if (1.0f - v - w >= 0.0f && v >= 0.0f && w >= 0.0f) {
+                                key = __float_as_uint(time);
+                                bv = v;
+                                bw = w;
+                            }
+                        }
+                    }
+                }
+                const uint32_t kmin = __reduce_min_sync(gmask, key);
+                if (kmin != 0xFFFFFFFFu) {
+                    const unsigned wm = (__ballot_sync(gmask, key == kmin) >> gbase) & 0xFFu;
+                    ht = __uint_as_float(kmin);
+                    hit = true;
+                    if ((int)k == __ffs(wm) - 1)  // the first of equal times wins, like the binary tree's leaf loop
+                        cw.res[it] = make_float4(ht, bv, bw, __uint_as_float(ldg(m.bvh_ids + first + k)));
+                }
+                if (any && hit) done = true;
+                else pop = true;
+            }
+            if (pop && !done) {
+                while (true) {
+                    if (sp == 0) {
+                        done = true;
+                        break;
+                    }
+                    sp--;
+                    const uint2 e = stack[sp];  // one address for the eight lanes: a broadcast
+                    if (__uint_as_float(e.y) < ht) {  // entered before the closest hit so far
+                        cur = (int32_t)e.x;
+                        break;
+                    }
+                }
+            }
+        }
+        if (overflow && k == 0u) cw.res[it].x = -2.0f;
+        __syncwarp(gmask);
+    }
+}
+
+#endif
+
 // ------------------------------------------------------------ kd traversal -----
 RPTB_D KdNodeDev load_node(const KdNodeDev* p) {
     const uint2 v = ldg(reinterpret_cast<const uint2*>(p));
@@ -735,6 +930,75 @@ RPTB_D void closest_hit(const SceneView<R>& sv, Vec3<R> o, Vec3<R> d, R tmin, bo
         }
     }
 }
+
+#if defined(__CUDACC__) && !defined(RPTB_HOST_EMU)
+// get_closest_hit (renderer.rs:211-220) for the warp: every lane with `active` holds a world ray (ro, rd) and its
+// h.t = tmax.  Analytic shapes, one-leaf meshes and kd-trees of shapes are intersected by the lane that owns the ray;
+// a mesh with a BVH is entered through the lane-group traversal above.  Called by ALL 32 lanes of a full warp.
+template <bool STATS, int FEAT>
+__device__ __forceinline__ void closest_hit_coop(const SceneView<float>& sv, const bool active, const Vec3<float> ro, const Vec3<float> rd,
+                                                 const float tmin, const bool any, Hit<float>& h, TravStats& ts, const uint32_t lane,
+                                                 CoopWarp& cw) {
+    h.obj = -1;
+    h.aux = 0;
+    h.bv = h.bw = 0.0f;
+    if constexpr ((FEAT & F_GROUP) != 0) h.child = 0;
+    const uint32_t n = sv.nobjects;
+    for (uint32_t i = 0; i < n; i++) {
+        const ObjectRec<float>& ob = sv.objects[i];
+        const bool live = active && !(any && h.obj >= 0);  // a shadow ray ends at its first hit
+        if (ob.kind == SHAPE_MESH && !sv.meshes[ob.mesh].root_is_leaf) {  // warp-uniform
+            const MeshRec<float>& mm = sv.meshes[ob.mesh];
+            bool pred = live;
+            Vec3<float> o = ro, d = rd;
+            if (pred) {
+                if (STATS) ts.object_tests++;
+                if (ob.has_transform) {
+                    o = xform_point(ob.inv, ro);
+                    d = xform_dir(ob.inv, rd);
+                }
+                // root cull: BoundingBox::intersect of KdTree::bounds (kdtree.rs:130-134) against [tmin, closest so far]
+                const Vec3<float> iv = {slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z)};
+                const float x1 = (mm.bmin[0] - o.x) * iv.x, x2 = (mm.bmax[0] - o.x) * iv.x;
+                const float y1 = (mm.bmin[1] - o.y) * iv.y, y2 = (mm.bmax[1] - o.y) * iv.y;
+                const float z1 = (mm.bmin[2] - o.z) * iv.z, z2 = (mm.bmax[2] - o.z) * iv.z;
+                const float l0 = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+                const float h0 = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+                pred = !(fmaxf(l0, tmin) > fminf(h0, h.t));
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pred);
+            if (m != 0u) {
+                const uint32_t pos = (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if (pred) {
+                    cw.ra[pos] = make_float4(o.x, o.y, o.z, h.t);
+                    cw.rb[pos] = make_float4(d.x, d.y, d.z, 0.0f);
+                    cw.res[pos] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+                }
+                if (lane == 0u) cw.next = 0u;
+                __syncwarp();
+                bvh8_group_trace<STATS>(mm, cw, (uint32_t)__popc(m), any, lane, ts);
+                __syncwarp();
+                if (pred) {
+                    const float4 r = cw.res[pos];
+                    if (r.x == -2.0f) {  // the group's stack overflowed (a pathological tree): the binary BVH has no such limit
+                        if (bvh_intersect<STATS>(mm, o, d, tmin, any, h, ts)) h.obj = (int)i;
+                    } else if (r.x >= 0.0f) {
+                        h.t = r.x;
+                        h.bv = r.y;
+                        h.bw = r.z;
+                        h.aux = __float_as_uint(r.w);
+                        h.obj = (int)i;
+                    }
+                }
+                __syncwarp();  // the answers are read before the next mesh reuses the block
+            }
+        } else if (live) {
+            if (STATS) ts.object_tests++;
+            if (object_intersect<float, STATS, FEAT>(sv, ob, ro, rd, tmin, any, h, ts)) h.obj = (int)i;
+        }
+    }
+}
+#endif
 
 // f32 only: start the next ray a few ulps off the surface, on the side it leaves from.
 // The reference restarts exactly at the hit point with t_min = 1e-12, which only works

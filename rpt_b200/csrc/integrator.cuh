@@ -129,13 +129,16 @@ struct DeviceWarp {
 // The generator the megakernel draws from: f64 the oracle's, f32 the shared-memory ring (rng.cuh)
 template <class R>
 struct MegaRng { typedef Rng<R> type; };
+#if !RPTB_RNG_FIFO
 template <>
 struct MegaRng<float> { typedef RngRing type; };
+#endif
 
-// `rng_ring`: RNG_RING * RENDER_THREADS words of shared memory (f32 on the device; null otherwise)
+// `rng_ring`: RNG_RING * RENDER_THREADS words of shared memory (f32 on the device; null otherwise).
+// `coop`: this warp's CoopWarp block (geometry.cuh) when meshes are traversed by lane groups (F_BVH on the device), else null.
 template <class R, int MAXD, bool STATS, int FEAT, class W>
 RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const uint32_t block_x, const uint32_t block_y,
-                          const uint32_t thread_x, uint32_t* rng_ring = nullptr) {
+                          const uint32_t thread_x, uint32_t* rng_ring = nullptr, void* coop = nullptr) {
     const uint32_t tile = a.shard_index + block_x * a.shard_count;
     const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const uint32_t warp = thread_x >> 5, lane = thread_x & 31u;
@@ -354,7 +357,19 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
         Hit<R> h;
         h.t = tmax;
         h.obj = -1;
-        if (active) {
+        bool traced = false;
+#if defined(__CUDACC__) && !defined(RPTB_HOST_EMU)
+        if constexpr (!M<R>::literal && (FEAT & F_BVH) != 0 && W::width == 32u) {
+            // meshes through the eight-wide BVH, eight lanes per ray (every lane of the warp takes part, with or without a ray
+            // of its own); a warp at the image's edge, with fewer than 32 lanes, keeps the per-lane binary traversal
+            if (coop != nullptr && wmask == 0xffffffffu) {
+                if (active) pc.rays++;
+                closest_hit_coop<STATS, FEAT>(sv, active, ro, rd, tmin, light_slot, h, pc.ts, lane, *static_cast<CoopWarp*>(coop));
+                traced = true;
+            }
+        }
+#endif
+        if (!traced && active) {
             pc.rays++;
             closest_hit<R, STATS, FEAT>(sv, ro, rd, tmin, light_slot, h, pc.ts);
         }
@@ -438,7 +453,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
         render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x);
     } else {
         __shared__ uint32_t rng_ring[RNG_RING * RENDER_THREADS];  // 4 KB: every thread's 8 buffered draws, one bank per lane
-        render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x, rng_ring);
+#ifndef RPTB_HOST_EMU
+        if constexpr ((FEAT & F_BVH) != 0) {
+            __shared__ CoopWarp coop[RENDER_THREADS / 32];  // 3 KB per warp: compacted rays, answers, the lane groups' stacks
+            render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x, rng_ring, &coop[threadIdx.x >> 5]);
+        } else
+#endif
+        {
+            render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x, rng_ring);
+        }
     }
 }
 #endif
@@ -517,6 +540,50 @@ __global__ void closest_hit_kernel(const SceneView<R> sv, const double* __restri
         }
     }
 }
+
+#if defined(__CUDACC__) && !defined(RPTB_HOST_EMU)
+// The same query through the product path's mesh traversal: every warp takes 32 rays, meshes are entered by lane groups
+// over the eight-wide BVH (geometry.cuh, closest_hit_coop).  f32 scenes with a BVH.
+template <bool STATS, int FEAT>
+__global__ void __launch_bounds__(128) closest_hit_coop_kernel(const SceneView<float> sv, const double* __restrict__ rays, uint64_t n,
+                                                               double tmin_d, double* __restrict__ out_t, int32_t* __restrict__ out_obj,
+                                                               double* __restrict__ out_n, DeviceCounters* counters) {
+    __shared__ CoopWarp coop[4];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;  // nobody leaves: the traversal needs whole warps
+    TravStats ts = {0, 0, 0, 0, 0};
+    Vec3<float> o = {0.f, 0.f, 0.f}, d = {0.f, 0.f, 1.f};
+    if (active) {
+        const double* r = rays + 6 * i;
+        o = {(float)r[0], (float)r[1], (float)r[2]};
+        d = {(float)r[3], (float)r[4], (float)r[5]};
+    }
+    Hit<float> h;
+    h.t = INFINITY;
+    closest_hit_coop<STATS, FEAT>(sv, active, o, d, (float)tmin_d, false, h, ts, threadIdx.x & 31u, coop[threadIdx.x >> 5]);
+    if (active) {
+        out_obj[i] = h.obj;
+        out_t[i] = h.obj >= 0 ? (double)h.t : (double)INFINITY;
+        if (out_n) {
+            Vec3<float> nn = {0.f, 0.f, 0.f};
+            if (h.obj >= 0) nn = finalize_hit<float, FEAT>(sv, sv.objects[h.obj], o, d, h).n;
+            out_n[3 * i] = (double)nn.x;
+            out_n[3 * i + 1] = (double)nn.y;
+            out_n[3 * i + 2] = (double)nn.z;
+        }
+    }
+    if (counters) {
+        if (active) atomicAdd(&counters->rays, 1ull);
+        if (STATS) {
+            atomicAdd(&counters->node_visits, (unsigned long long)ts.node_visits);
+            atomicAdd(&counters->tri_tests, (unsigned long long)ts.tri_tests);
+            atomicAdd(&counters->object_tests, (unsigned long long)ts.object_tests);
+            atomicAdd(&counters->bvh_node_visits, (unsigned long long)ts.bvh_nodes);
+            atomicAdd(&counters->bvh_tri_tests, (unsigned long long)ts.bvh_tris);
+        }
+    }
+}
+#endif
 
 // ---- point-wise Material::bsdf / sample_f ------------------------------------------------
 template <class R>

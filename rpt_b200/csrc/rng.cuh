@@ -208,6 +208,12 @@ struct Rng<float> {
 // Philox block ran at 7.4 of 32 lanes and was 27 % of the kernel's warp instructions.  ensure() tops a lane up to
 // what it is about to draw where the warp is converged, and all lanes that need a block compute it together.
 constexpr uint32_t RNG_RING = 8;
+#ifndef RPTB_RNG_FILL
+#define RPTB_RNG_FILL 0
+#endif
+#ifndef RPTB_RNG_FIFO
+#define RPTB_RNG_FIFO 0  // A/B switch: 1 = the megakernel keeps round 1's 4-entry register FIFO (Rng<float>)
+#endif
 struct RngRing {
     uint32_t key0, key1, block, pixel, samp_lo, samp_hi;
     uint32_t head, avail;
@@ -255,9 +261,17 @@ struct RngRing {
     template <class W>
     RPTB_HD void ensure(unsigned mask, uint32_t need) {
         // (a block is two entries: a lane can take one while avail <= RNG_RING - 2)
+#if RPTB_RNG_FILL
+        // A/B switch: top every lane up to >= 6 entries whatever it is about to draw
+        (void)need;
+        while (W::any(mask, avail <= 5u)) {
+            if (avail <= RNG_RING - 2u) push_block();
+        }
+#else
         while (W::any(mask, avail < need && avail <= RNG_RING - 2u)) {
             if (avail < need && avail <= RNG_RING - 2u) push_block();
         }
+#endif
     }
     RPTB_HD uint32_t next32() {
         if (avail == 0) push_block();  // rare: a slot consumed more than six draws

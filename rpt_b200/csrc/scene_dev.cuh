@@ -76,6 +76,21 @@ struct BvhNodeDev {
     int32_t child0, child1;
     uint32_t _pad[2];
 };
+// The same tree collapsed to eight children per node, for traversal by GROUPS OF EIGHT LANES (geometry.cuh,
+// bvh8_group_trace): lane k of a group fetches child k -- the group reads the 256-byte node as one coalesced
+// request -- tests its box, and the group's votes pick the nearest.  A child is 32 bytes: its box (rounded outward,
+// padded like the binary node's) and a code: >= 0 inner node, BVH8_EMPTY no child, otherwise a leaf with the
+// binary tree's code ~((first << 3) | (count - 1)) (the leaves, hence bvh_tri48 / bvh_ids, are the binary tree's).
+struct Bvh8Child {
+    float lo[3], hi[3];
+    int32_t code;
+    uint32_t _pad;
+};
+struct Bvh8Node {
+    Bvh8Child c[8];
+};
+constexpr int32_t BVH8_EMPTY = (int32_t)0x80000000;
+constexpr int BVH8_STACK = 48;     // entries of a group's traversal stack in shared memory (overflow -> the ray falls back to the binary BVH)
 constexpr int BVH_STACK = 96;      // traversal stack entries; the builder keeps the depth below it (bvhbuild.cpp)
 constexpr int BVH_LEAF_MAX = 4;    // triangles per leaf (3 bits in the leaf code would allow 8)
 
@@ -86,6 +101,7 @@ struct MeshRec {
     const float4* tri48;  // f32 only (null for double)
     const float4* leaf_planes;  // f32, kd-tree meshes only: tri48[3*refs[k]] for every leaf ref k (planes in leaf order)
     const BvhNodeDev* bvh_nodes;  // f32, when the scene was created with the BVH (F_BVH): node 0 is the root
+    const Bvh8Node* bvh8_nodes;   // the same tree, eight children per node (node 0 = root), for the lane-group traversal
     const float4* bvh_tri48;      // tri48 permuted into BVH leaf order (a leaf's triangles are contiguous)
     const uint32_t* bvh_ids;      // original triangle index of each BVH-order triangle (normals, Hit::aux)
     const R* verts;       // 9 per triangle

@@ -328,6 +328,41 @@ int hostemu_render(const hostemu_scene* s, const rptb_camera* cam, const rptb_re
     return render_impl<float>(s->v32, cam, p, feats, s->hs.sampled_lights, out_rgb, stats);
 }
 
+// The eight-wide collapse of mesh `mesh` against its binary BVH, ray by ray (mesh-local rays, n x 6 doubles): the scalar
+// walk of Bvh8Node (geometry.cuh, bvh8_intersect_scalar) must find the binary tree's hits.  out_t / out_tri are n x 2
+// (binary, eight-wide); out_info = {8-wide nodes, max children used, empty child slots, binary node visits, 8-wide node visits}.
+int hostemu_bvh8_probe(const hostemu_scene* s, uint32_t mesh, const double* rays, uint64_t n, int any, double* out_t, int64_t* out_tri,
+                       uint64_t* out_info) {
+    if (mesh >= s->hs.t32.meshes.size()) return -1;
+    const MeshRec<float>& m = s->v32.meshes[mesh];
+    if (!m.bvh_nodes || !m.bvh8_nodes) return -1;
+    const HostMesh& hm = s->hs.meshes[mesh];
+    uint64_t used_max = 0, empty = 0;
+    for (const Bvh8Node& nd : hm.bvh8_nodes) {
+        uint64_t used = 0;
+        for (int k = 0; k < 8; k++) used += nd.c[k].code != BVH8_EMPTY;
+        used_max = std::max(used_max, used);
+        empty += 8 - used;
+    }
+    unsigned long long v2 = 0, v8 = 0;
+#pragma omp parallel for schedule(static) reduction(+ : v2, v8)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const double* r = rays + 6 * i;
+        const Vec3<float> o = {(float)r[0], (float)r[1], (float)r[2]}, d = {(float)r[3], (float)r[4], (float)r[5]};
+        for (int w = 0; w < 2; w++) {
+            TravStats ts = {0, 0, 0, 0, 0};
+            Hit<float> h;
+            h.t = INFINITY; h.obj = -1; h.aux = 0xFFFFFFFFu; h.bv = h.bw = 0.0f;
+            const bool hit = w == 0 ? bvh_intersect<true>(m, o, d, 1e-12f, any != 0, h, ts) : bvh8_intersect_scalar<true>(m, o, d, 1e-12f, any != 0, h, ts);
+            out_t[2 * i + w] = hit ? (double)h.t : (double)INFINITY;
+            out_tri[2 * i + w] = hit ? (int64_t)h.aux : -1;
+            (w == 0 ? v2 : v8) += ts.bvh_nodes;
+        }
+    }
+    out_info[0] = hm.bvh8_nodes.size(); out_info[1] = used_max; out_info[2] = empty; out_info[3] = v2; out_info[4] = v8 / 4;
+    return 0;
+}
+
 int hostemu_bvh_check(const hostemu_scene* s, uint32_t mesh, uint64_t* out) {
     const HostMesh& hm = s->hs.meshes[mesh];
     for (int i = 0; i < 6; i++) out[i] = 0;

@@ -469,3 +469,44 @@ def test_vertex_at_once_engine_is_the_slot_engine_bit_for_bit(orc, monkeypatch, 
     b, sb, fb = e.render(cfg.camera, _params(cfg, w, h, spp, mb))
     np.testing.assert_array_equal(a, b)
     assert sa["segments"] == sb["segments"] and sa["rays"] == sb["rays"] and fa == fb
+
+
+@pytest.mark.parametrize("name", ["teapot", "pegasus", "knot", "tiny"])
+def test_eight_wide_bvh_is_the_binary_bvh_collapsed(name):
+    """bvhbuild.cpp, emit8: the Bvh8Node tree the lane groups traverse on the GPU (geometry.cuh, bvh8_group_trace) holds
+    the binary tree's leaves under fewer, fatter nodes: a scalar walk of it finds, ray for ray, the binary tree's
+    closest hit (same t; the same triangle unless two triangles tie exactly) and the same any-hit verdict, with a
+    third of the node visits."""
+    from rpt_b200.api import Material, Mesh, Object, Scene, hex_color
+    if name == "teapot":
+        tris = scenes.teapot_triangles()
+    elif name == "pegasus":
+        tris = scenes.pegasus_proxy(0)
+    elif name == "knot":
+        tris = scenes.knot_proxy(330, 82)
+    else:
+        tris = scenes.teapot_triangles()[:3]
+    scene = Scene()
+    scene.add(Object(Mesh(tris)).material(Material.diffuse(hex_color(0xFFFFFF))))
+    e = emu.EmuScene(api.FlatScene(scene, accel=capi.ACCEL_BVH))
+    v = tris[:, :9].reshape(-1, 3)
+    lo, hi = v.min(0), v.max(0)
+    rng = np.random.default_rng(3)
+    n = 40000
+    o = rng.uniform(lo - 0.5 * (hi - lo), hi + 0.5 * (hi - lo), (n, 3))
+    tgt = rng.uniform(lo, hi, (n, 3))
+    d = util.normalize(tgt - o) * rng.uniform(0.5, 2.0, (n, 1))   # un-normalised directions, like rays under a Transformed
+    d[:50, 0] = 0.0                                                # axis-aligned components (slab_rcp)
+    rays = np.concatenate([o, d], axis=1)
+    if name == "tiny":
+        # a mesh the kd builder leaves as one leaf never gets a BVH: nothing to compare
+        assert e.bvh8_probe(0, rays) is None
+        return
+    t, tri, info = e.bvh8_probe(0, rays)
+    assert (np.isfinite(t[:, 0]) == np.isfinite(t[:, 1])).all() and np.isfinite(t[:, 0]).mean() > 0.2
+    hit = np.isfinite(t[:, 0])
+    np.testing.assert_array_equal(t[hit, 0], t[hit, 1])
+    assert (tri[hit, 0] == tri[hit, 1]).mean() > 0.999
+    assert info["max_children"] == 8 and info["visits8"] < 0.6 * info["visits2"], info   # (the scalar walk is unordered: the lane groups go front to back)
+    ta, tria, _ = e.bvh8_probe(0, rays, any_hit=True)
+    assert (np.isfinite(ta[:, 0]) == np.isfinite(ta[:, 1])).all() and (np.isfinite(ta[:, 0]) == hit).all()
