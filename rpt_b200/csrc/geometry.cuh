@@ -270,6 +270,12 @@ RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, 
 // products infinite and their difference NaN, and fminf/fmaxf over ONE NaN plane silently shrink the interval
 // (a box the ray is inside of gets culled).  A component of magnitude < 1e-30 is treated as +-1e-30: every
 // product stays finite, and the error this makes in t is far below the padding of the boxes.
+#ifndef RPTB_BVH_PREFETCH
+#define RPTB_BVH_PREFETCH 1
+#endif
+#ifndef RPTB_COOP_MAX
+#define RPTB_COOP_MAX 0  // rays of a warp entering a mesh at or below which they are traversed by lane groups (0 = never: see closest_hit_coop)
+#endif
 RPTB_D float slab_rcp(float x) { return M<float>::rcp(fabsf(x) < 1e-30f ? copysignf(1e-30f, x) : x); }
 
 RPTB_D BvhNodeDev load_bvh_node(const BvhNodeDev* p) {
@@ -309,6 +315,12 @@ RPTB_D bool bvh_intersect(const MeshRec<float>& m, Vec3<float> o, Vec3<float> d,
             const float bn = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), tmin));
             const float bf = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), h.t));
             const bool ha = an <= af, hb = bn <= bf;
+#if defined(__CUDA_ARCH__) && RPTB_BVH_PREFETCH
+            // the loop is bound by the latency of one dependent node fetch per step (ncu: long_scoreboard on top): ask L1 for
+            // both children's lines now, whichever is taken first (the other usually follows from the stack)
+            if (ha && n.child0 >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.bvh_nodes + n.child0));
+            if (hb && n.child1 >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.bvh_nodes + n.child1));
+#endif
             if (ha && hb) {
                 const bool a_first = an <= bn;
                 stack[sp++] = a_first ? n.child1 : n.child0;
@@ -967,7 +979,10 @@ __device__ __forceinline__ void closest_hit_coop(const SceneView<float>& sv, con
                 pred = !(fmaxf(l0, tmin) > fminf(h0, h.t));
             }
             const unsigned m = __ballot_sync(0xffffffffu, pred);
-            if (m != 0u) {
+            if (__popc(m) > RPTB_COOP_MAX) {
+                // many rays of the warp enter the mesh (coherent camera or shadow rays): one ray per lane fills the warp
+                if (pred && bvh_intersect<STATS>(mm, o, d, tmin, any, h, ts)) h.obj = (int)i;
+            } else if (m != 0u) {
                 const uint32_t pos = (uint32_t)__popc(m & ((1u << lane) - 1u));
                 if (pred) {
                     cw.ra[pos] = make_float4(o.x, o.y, o.z, h.t);

@@ -212,7 +212,12 @@ constexpr uint32_t RNG_RING = 8;
 #define RPTB_RNG_FILL 0
 #endif
 #ifndef RPTB_RNG_FIFO
-#define RPTB_RNG_FIFO 0  // A/B switch: 1 = the megakernel keeps round 1's 4-entry register FIFO (Rng<float>)
+// 1 = the slot engine keeps the 4-entry register FIFO (Rng<float>), 0 = it draws from the ring below.  Measured on one
+// B200 with everything else equal (gpurun r02h, Msamples/s, FIFO / ring topped up to 6 / ring topped up on demand):
+// cornell 5 676 / 5 252 / 4 919, glass 20 553 / 14 676 / 15 590, sphere 9 284 / 9 638 / 8 908 -- the ring does raise the
+// lanes per Philox instruction (7.4 -> 11.2, ncu) but its shared-memory traffic and vote loops cost more than that saves,
+// so the FIFO is the default and the ring is what the vertex-at-once engine (integrator_vx.cuh) uses.
+#define RPTB_RNG_FIFO 1
 #endif
 struct RngRing {
     uint32_t key0, key1, block, pixel, samp_lo, samp_hi;
