@@ -59,12 +59,14 @@ examples: build/sphere_cpp build/fractal_spheres_cpp
 build/%_cpp: examples/%.cpp include/rpt.hpp include/rpt_b200.h $(LIB)
 	$(CXX) -std=c++17 -O2 -Wall -o $@ $< -Lrpt_b200/lib -lrpt_b200 -Wl,-rpath,'$$ORIGIN/../rpt_b200/lib'
 
-# test infrastructure: the device geometry functions compiled for the host (tests/hostemu/hostemu.cu)
+# test infrastructure: the device geometry functions compiled for the host (tests/hostemu/hostemu.cu).  -Bsymbolic: the
+# library is loaded next to librpt_b200.so (RTLD_GLOBAL), whose copies of the inline flatteners were compiled with other
+# switches (RPTB_BUILD_BVH8) -- hostemu must call its own
 HOSTEMU := tests/hostemu/_build/libhostemu.so
 hostemu: $(HOSTEMU)
 $(HOSTEMU): tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp $(CSRC)/bvhbuild.cpp $(HDRS)
 	@mkdir -p $(dir $@)
-	nvcc -std=c++17 -O2 -DRPTB_HOST_EMU -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fopenmp,-ffp-contract=off -shared -o $@ tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp $(CSRC)/bvhbuild.cpp -lgomp
+	nvcc -std=c++17 -O2 -DRPTB_HOST_EMU -DRPTB_BUILD_BVH8=1 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fopenmp,-ffp-contract=off -shared -Xlinker -Bsymbolic -o $@ tests/hostemu/hostemu.cu $(CSRC)/kdbuild.cpp $(CSRC)/bvhbuild.cpp -lgomp
 
 clean:
 	rm -rf build $(LIB) $(ORACLE) tests/hostemu/_build

@@ -531,7 +531,7 @@ inline int flatten_scene(const rptb_scene_desc* d, HostScene& hs, std::string& e
         }
         if (!leaf && want_bvh) {  // the f32 path's own BVH over the same triangles (bvhbuild.cpp)
             uint32_t bvh_depth = 0;
-            if (build_bvh_host(d->meshes[i].tris, d->meshes[i].ntris, hm.bvh_nodes, hm.bvh_ids, bvh_depth, &hm.bvh8_nodes) != 0)
+            if (build_bvh_host(d->meshes[i].tris, d->meshes[i].ntris, hm.bvh_nodes, hm.bvh_ids, bvh_depth, RPTB_BUILD_BVH8 ? &hm.bvh8_nodes : nullptr) != 0)
                 return flat_fail(err, RPTB_ERR_UNSUPPORTED, "mesh %u: cannot build a BVH over %llu triangles", i, (unsigned long long)d->meshes[i].ntris);
             if (bvh_depth + 2 >= (uint32_t)BVH_STACK)
                 return flat_fail(err, RPTB_ERR_UNSUPPORTED, "mesh %u: BVH depth %u exceeds the traversal stack (%d)", i, bvh_depth, BVH_STACK);

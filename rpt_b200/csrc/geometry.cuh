@@ -270,12 +270,6 @@ RPTB_D bool tri_intersect(const MeshRec<float>& m, uint32_t tri, Vec3<float> o, 
 // products infinite and their difference NaN, and fminf/fmaxf over ONE NaN plane silently shrink the interval
 // (a box the ray is inside of gets culled).  A component of magnitude < 1e-30 is treated as +-1e-30: every
 // product stays finite, and the error this makes in t is far below the padding of the boxes.
-#ifndef RPTB_BVH_PREFETCH
-#define RPTB_BVH_PREFETCH 1
-#endif
-#ifndef RPTB_COOP_MAX
-#define RPTB_COOP_MAX 0  // rays of a warp entering a mesh at or below which they are traversed by lane groups (0 = never: see closest_hit_coop)
-#endif
 RPTB_D float slab_rcp(float x) { return M<float>::rcp(fabsf(x) < 1e-30f ? copysignf(1e-30f, x) : x); }
 
 RPTB_D BvhNodeDev load_bvh_node(const BvhNodeDev* p) {

@@ -359,7 +359,7 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
         h.obj = -1;
         bool traced = false;
 #if defined(__CUDACC__) && !defined(RPTB_HOST_EMU)
-        if constexpr (!M<R>::literal && (FEAT & F_BVH) != 0 && W::width == 32u) {
+        if constexpr (!M<R>::literal && (FEAT & F_BVH) != 0 && W::width == 32u && RPTB_COOP_MAX > 0) {
             // meshes through the eight-wide BVH, eight lanes per ray (every lane of the warp takes part, with or without a ray
             // of its own); a warp at the image's edge, with fewer than 32 lanes, keeps the per-lane binary traversal
             if (coop != nullptr && wmask == 0xffffffffu) {
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, render_min_blocks(FEAT)) rende
     } else {
         __shared__ uint32_t rng_ring[RNG_RING * RENDER_THREADS];  // 4 KB: every thread's 8 buffered draws, one bank per lane
 #ifndef RPTB_HOST_EMU
-        if constexpr ((FEAT & F_BVH) != 0) {
+        if constexpr ((FEAT & F_BVH) != 0 && RPTB_COOP_MAX > 0) {
             __shared__ CoopWarp coop[RENDER_THREADS / 32];  // 3 KB per warp: compacted rays, answers, the lane groups' stacks
             render_thread<R, MAXD, STATS, FEAT, DeviceWarp>(sv, a, blockIdx.x, blockIdx.y, threadIdx.x, rng_ring, &coop[threadIdx.x >> 5]);
         } else

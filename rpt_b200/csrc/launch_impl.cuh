@@ -65,15 +65,17 @@ cudaError_t launch_closest_hit_impl(const SceneView<R>& sv, const double* rays, 
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
     // stats == 1: counters of the structure the product path traverses; stats == 2: the reference-shaped kd-trees
-    // (a scene with a BVH is queried the way it is rendered: meshes through the eight-wide tree, eight lanes per ray)
-    if constexpr (!M<R>::literal) {
+    // (with the lane-group traversal compiled in, a scene with a BVH is queried the way it is rendered)
+    if constexpr (!M<R>::literal && RPTB_COOP_MAX > 0) {
         if (stats != 2 && (features & F_BVH)) {
             if (stats) closest_hit_coop_kernel<true, F_EVERY | F_BVH><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
             else closest_hit_coop_kernel<false, F_EVERY | F_BVH><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
             return cudaGetLastError();
         }
     }
-    if (stats) closest_hit_kernel<R, true, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    if (!M<R>::literal && stats == 1 && (features & F_BVH)) closest_hit_kernel<R, true, F_EVERY | F_BVH><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    else if (stats) closest_hit_kernel<R, true, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
+    else if (!M<R>::literal && (features & F_BVH)) closest_hit_kernel<R, false, F_EVERY | F_BVH><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
     else closest_hit_kernel<R, false, F_EVERY><<<grid, 128, 0, stream>>>(sv, rays, n, tmin, out_t, out_obj, out_n, counters);
     return cudaGetLastError();
 }

@@ -41,6 +41,24 @@ enum : int {
     F_BVH = 64 /* f32 only: meshes are traversed through their BVH (MeshRec::bvh_*) instead of the reference-shaped kd-tree */
 };
 
+// Two experiments of round 2 on the mesh configs, both measured slower than what they were meant to improve and
+// therefore off (one B200, Msamples/s, teapot / dragon-proxy / dragon-knot; gpurun r02h, r02i):
+//   RPTB_BVH_PREFETCH  prefetch.global.L1 of both children's lines once their boxes are hit: 13 586 / 1 450 / 781 against
+//                      14 982 / 1 635 / 887 without -- the loop is latency bound, but the extra requests cost more than
+//                      the early lines save
+//   RPTB_COOP_MAX      the warp's rays that enter a mesh are traversed by groups of eight lanes over the eight-wide tree
+//                      when there are at most this many of them (closest_hit_coop): always 3 370 / 744 / 331; at most 4:
+//                      14 271 / 1 269 / 720; at most 8: 13 902 / 1 231 / 711.  0 = never, and the code is compiled out
+#ifndef RPTB_BVH_PREFETCH
+#define RPTB_BVH_PREFETCH 0
+#endif
+#ifndef RPTB_COOP_MAX
+#define RPTB_COOP_MAX 0
+#endif
+#ifndef RPTB_BUILD_BVH8
+#define RPTB_BUILD_BVH8 (RPTB_COOP_MAX > 0)  // the eight-wide tree is built and uploaded only when something traverses it (tests/hostemu does)
+#endif
+
 constexpr int KD_STACK = 64;          // max kd-tree depth the traversal stack holds
 constexpr int GROUP_STACK = 32;       // same, for a kd-tree over whole shapes (a few thousand children at most)
 constexpr int MAX_CONST_OBJECTS = 96;  // tables up to this size live in __constant__ memory
