@@ -43,7 +43,8 @@ constexpr int RENDER_THREADS = 128;  // 4 warps: a 16x8 pixel tile
 #define RPTB_MIN_BLOCKS_GLASS 5  // F_TRANSP | F_HDRI, no trees (glass: flat, 19.2-19.4 G for 5/6/8)
 #endif
 #ifndef RPTB_MIN_BLOCKS_BVH
-#define RPTB_MIN_BLOCKS_BVH 6    // F_BVH (the BVH loop keeps 1/d, o/d and a two-box node live): 80 registers; not tuned on hardware yet
+#define RPTB_MIN_BLOCKS_BVH 8    // F_BVH: the node loop is latency bound at 5-6 lanes, more resident warps help more than the spills of the 64-register
+                                 // build hurt (r02j, Msamples/s for 6 / 7 / 8: teapot 16 527 / 16 870 / 16 971, dragon-proxy 1 666 / 1 750 / 1 798, knot 901 / 961 / 999)
 #endif
 #ifndef RPTB_MIN_BLOCKS_EXT
 #define RPTB_MIN_BLOCKS_EXT 4    // F_EVERY (two nested traversal stacks in local memory): not tuned on hardware yet

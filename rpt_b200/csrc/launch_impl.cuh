@@ -16,7 +16,8 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
     }
     if (args.ntiles_mine > 0) {
         const dim3 grid(args.ntiles_mine, args.ngroups), block(RENDER_THREADS);
-        if (args.max_bounces <= 16) {
+        // (MAXD sizes the f64 gate's level stack; the f32 path composes the clamps forward and has no depth limit of its own)
+        if (args.max_bounces <= 16 || !M<R>::literal) {
             // pick the instantiation compiled for exactly the features this scene has (tree scenes do not
             // take the parameter-space tables: teapot 5762 without vs 5181 Msamples/s with)
             const int base = features & F_ALL;
@@ -41,12 +42,11 @@ cudaError_t launch_render_impl(const SceneView<R>& sv, const RenderArgs<R>& args
             else if (base == (F_TRANSP | F_HDRI)) render_kernel<R, 16, false, F_TRANSP | F_HDRI><<<grid, block, 0, stream>>>(sv, args);
             else render_kernel<R, 16, false><<<grid, block, 0, stream>>>(sv, args);
         } else {
-            // deep paths (max_bounces > 16): one general instantiation per structure
-            const bool bvh = !M<R>::literal && (features & F_BVH) && stats != 2;
-            if (stats && bvh) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY | F_BVH><<<grid, block, 0, stream>>>(sv, args);
-            else if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
-            else if (bvh) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY | F_BVH><<<grid, block, 0, stream>>>(sv, args);
-            else render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            // f64 gate, deep paths (max_bounces > 16): the level stack sized for MAX_BOUNCES_SUPPORTED
+            if constexpr (M<R>::literal) {
+                if (stats) render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+                else render_kernel<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY><<<grid, block, 0, stream>>>(sv, args);
+            }
         }
         nl++;
         if (args.nchunks > 1) {

@@ -139,16 +139,10 @@ struct Rng<double> {
 // Philox block then runs once for 32 lanes instead of once per lane per call site.
 // gen_bool / Uniform(0..n) decide on the high word alone; the decision differs from the
 // 64-bit one with probability <= n * 2^-32 per draw (f32 mode only).
-#ifndef RPTB_FIFO6
-#define RPTB_FIFO6 0
-#endif
 template <>
 struct Rng<float> {
     uint32_t key0, key1, block, pixel, samp_lo, samp_hi;
     uint32_t q0, q1, q2, q3;
-#if RPTB_FIFO6
-    uint32_t q4, q5;  // A/B: a 6-entry FIFO (a mesh-light sample takes 5 draws half of the time)
-#endif
     uint32_t avail;
     RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) {
         key0 = (uint32_t)seed;
@@ -158,12 +152,9 @@ struct Rng<float> {
         samp_lo = (uint32_t)sample;
         samp_hi = (uint32_t)(sample >> 32);
         q0 = q1 = q2 = q3 = 0;
-#if RPTB_FIFO6
-        q4 = q5 = 0;
-#endif
         avail = 0;
     }
-    RPTB_HD void push_block() {  // requires avail <= 2 (<= 4 with the 6-entry FIFO)
+    RPTB_HD void push_block() {  // requires avail <= 2
 #ifdef __CUDA_ARCH__
         const uint4 v = Philox::block_call(block, pixel, samp_lo, samp_hi, key0, key1);
         const uint32_t a = v.y, b = v.w;
@@ -175,13 +166,7 @@ struct Rng<float> {
         block++;
         if (avail == 0) { q0 = a; q1 = b; }
         else if (avail == 1) { q1 = a; q2 = b; }
-#if RPTB_FIFO6
-        else if (avail == 2) { q2 = a; q3 = b; }
-        else if (avail == 3) { q3 = a; q4 = b; }
-        else { q4 = a; q5 = b; }
-#else
         else { q2 = a; q3 = b; }
-#endif
         avail += 2;
     }
     RPTB_HD void ensure() {
@@ -189,26 +174,12 @@ struct Rng<float> {
         if (avail <= 2) push_block();
     }
     template <class W>
-    RPTB_HD void ensure(unsigned, uint32_t need) {
-#if RPTB_FIFO6
-        // as many blocks as this slot is expected to draw (`need`, integrator.cuh), at the converged point
-        if (avail < need && avail <= 4) push_block();
-        if (avail < need && avail <= 4) push_block();
-        if (avail < need && avail <= 4) push_block();
-#else
-        (void)need;
-        ensure();
-#endif
-    }
+    RPTB_HD void ensure(unsigned, uint32_t) { ensure(); }  // (a 6-entry FIFO refilled to the slot's expected draws was measured too: Cornell 4 841 vs 5 673)
     RPTB_HD void bind(uint32_t*, uint32_t) {}
     RPTB_HD uint32_t next32() {
         if (avail == 0) push_block();  // rare: a slot consumed more than the FIFO held
         const uint32_t v = q0;
-#if RPTB_FIFO6
-        q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5;
-#else
         q0 = q1; q1 = q2; q2 = q3;
-#endif
         avail--;
         return v;
     }

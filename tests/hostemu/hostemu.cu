@@ -193,17 +193,12 @@ template <class R>
 int run_render(const SceneView<R>& sv, const RenderArgs<R>& a, int stats, int features) {  // launch_render_impl's dispatch
     const int base = features & F_ALL;
     const bool small = (features & F_SMALL) != 0, ext = (features & F_EXT) != 0;
-    if (a.max_bounces > 16) {
-        if constexpr (!M<R>::literal)
-            if ((features & F_BVH) && stats != 2) {
-                if (stats) run_grid<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY | F_BVH>(sv, a);
-                else run_grid<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY | F_BVH>(sv, a);
-                return F_EVERY | F_BVH;
-            }
-        if (stats) run_grid<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY>(sv, a);
-        else run_grid<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY>(sv, a);
-        return F_EVERY;
-    }
+    if constexpr (M<R>::literal)
+        if (a.max_bounces > 16) {  // f64 gate only: the level stack sized for MAX_BOUNCES_SUPPORTED (the f32 path has no stack)
+            if (stats) run_grid<R, (int)MAX_BOUNCES_SUPPORTED, true, F_EVERY>(sv, a);
+            else run_grid<R, (int)MAX_BOUNCES_SUPPORTED, false, F_EVERY>(sv, a);
+            return F_EVERY;
+        }
     if constexpr (!M<R>::literal)
         if (stats == 1 && (features & F_BVH)) { run_grid<R, 16, true, F_EVERY | F_BVH>(sv, a); return F_EVERY | F_BVH; }
     if (stats) { run_grid<R, 16, true, F_EVERY>(sv, a); return F_EVERY; }

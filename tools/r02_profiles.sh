@@ -12,3 +12,10 @@ for wl in cornell dragon teapot glass; do
 done
 cp build/obj/kernels_f32.o gpurun_out/r02_final_kernels_f32.o
 ls -la gpurun_out | grep r02_final
+for tag in b9 b10; do
+  for wl in dragon dragon_knot teapot; do
+    RPTB_LIB=$PWD/rpt_b200/lib/librpt_b200_$tag.so timeout 300 python bench.py --workload $wl --spp 64 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02k_${wl}_$tag.json 2> gpurun_out/r02k_${wl}_$tag.err
+  done
+done
+timeout 900 python bench.py > gpurun_out/r02k_bench_default.json 2> gpurun_out/r02k_bench_default.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02k_bench_reference.json 2> gpurun_out/r02k_bench_reference.err
