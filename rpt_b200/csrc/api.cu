@@ -120,6 +120,51 @@ cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t stream) {
     }
     return cudaMallocFromPoolAsync(p, bytes, pool, stream);
 }
+// Page-locked staging for the device -> host copy of rptb_render_samples: one buffer per device, kept for the life of the
+// process (it is at most one image large).  cudaHostAlloc / cudaFreeHost cost milliseconds each -- with a scene created and
+// destroyed per Renderer::render() call they were a quarter of the end-to-end overhead (tools/gpu_e2e_multi.py).
+struct StageCache {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool in_use = false;
+};
+StageCache g_stage[64];
+
+// Returns a page-locked buffer of at least `bytes`; *cached = it must go back with stage_release (else cudaFreeHost).
+cudaError_t stage_acquire(int dev, size_t bytes, void** out, size_t* out_bytes, bool* cached) {
+    *cached = false;
+    if (dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        StageCache& c = g_stage[dev];
+        if (!c.in_use) {
+            if (c.bytes < bytes) {
+                if (c.p) cudaFreeHost(c.p);
+                c.p = nullptr;
+                c.bytes = 0;
+                const cudaError_t e = cudaHostAlloc(&c.p, bytes, cudaHostAllocDefault);
+                if (e != cudaSuccess) return e;
+                c.bytes = bytes;
+            }
+            c.in_use = true;
+            *out = c.p;
+            *out_bytes = c.bytes;
+            *cached = true;
+            return cudaSuccess;
+        }
+    }
+    *out_bytes = bytes;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault);  // a second scene rendering on the same device at the same time
+}
+void stage_release(int dev, void* p, bool cached) {
+    if (!p) return;
+    if (!cached) {
+        cudaFreeHost(p);
+        return;
+    }
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    if (dev >= 0 && dev < 64 && g_stage[dev].p == p) g_stage[dev].in_use = false;
+}
+
 void pool_scene_born(int dev) {
     if (dev < 0 || dev >= 64) return;
     std::lock_guard<std::mutex> lk(g_pool_mutex);
@@ -191,6 +236,7 @@ struct rptb_scene {
     // page-locked staging for the device -> host copy of rptb_render_samples
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    bool stage_cached = false;
     // rptb_scene_create_multi: the replicas on the other devices (this handle is replica 0)
     std::vector<rptb_scene*> peers;
 };
@@ -394,11 +440,10 @@ int ensure_out(rptb_scene* s, size_t nvals) {
 
 int ensure_stage(rptb_scene* s, size_t bytes) {
     if (s->stage_bytes >= bytes) return RPTB_OK;
-    if (s->stage) cudaFreeHost(s->stage);
+    stage_release(s->device, s->stage, s->stage_cached);
     s->stage = nullptr;
     s->stage_bytes = 0;
-    CU(cudaHostAlloc(&s->stage, bytes, cudaHostAllocDefault));
-    s->stage_bytes = bytes;
+    CU(stage_acquire(s->device, bytes, &s->stage, &s->stage_bytes, &s->stage_cached));
     return RPTB_OK;
 }
 
@@ -465,12 +510,13 @@ int render_shard_to_host(rptb_scene* s, const rptb_camera* cam, const rptb_rende
 
 void destroy_replica(rptb_scene* s) {
     DeviceGuard g(s->device);
-    cudaDeviceSynchronize();  // renders may have been enqueued on a caller's stream
+    if (s->busy_pending && s->busy) cudaEventSynchronize(s->busy);  // a render may still run on a caller's stream
+    if (s->stream) cudaStreamSynchronize(s->stream);
     s->arena.release();
     if (s->counters) cudaFreeAsync(s->counters, s->stream);
     if (s->wf_mem) cudaFreeAsync(s->wf_mem, s->stream);
     if (s->partial) cudaFreeAsync(s->partial, s->stream);
-    if (s->stage) cudaFreeHost(s->stage);
+    stage_release(s->device, s->stage, s->stage_cached);
     if (s->out32) cudaFreeAsync(s->out32, s->stream);
     if (s->out64) cudaFreeAsync(s->out64, s->stream);
     if (s->stream) cudaStreamSynchronize(s->stream);
