@@ -236,3 +236,22 @@ def test_flatten_kdtree_of_shapes_shares_meshes_and_keeps_child_order():
     assert flat.objects[0].kind == 5 and flat.objects[0].has_transform == 1 and flat.objects[0].mesh == 0
     assert flat.objects[1].kind == 3 and flat.objects[1].mesh == 0   # the same mesh record as the instances
     assert flat.host_bytes() > 22 * 184
+
+
+def test_bench_arms_share_one_config_and_count_real_cores():
+    """bench.py: the CPU arm's `config` is the GPU arm's (the driver compares them), the core count honours the cgroup
+    quota, and the bytes model adds the BVH counters."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cfg = bench.workload("cornell")
+    a, b = bench.config_dict(cfg, 1), bench.config_dict(bench.workload("cornell"), 1)
+    assert a == b and a["spp_per_gpu"] == 512 and a["width"] == 800 and a["max_bounces"] == 6
+    assert bench.config_dict(cfg, 8)["spp_total"] == 4096
+    used, aff, quota = bench.host_cores()
+    assert 1 <= used <= aff and (quota is None or used <= max(1, int(quota + 0.5)))
+    st = {k: 0 for k in bench.KEYS}
+    st.update(segments=10, bvh_node_visits=3, bvh_tri_tests=2, object_tests=4)
+    assert bench.algorithmic_bytes(st, 5) == 64 * 4 + 64 * 3 + 52 * 2 + 32 * 10 + 12 * 5
