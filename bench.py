@@ -445,12 +445,16 @@ def run_native(args):
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 flush.zero_()
                 st = capi.Stats()
+                ssampler = ClockSampler(world) if rank == 0 else None
+                if ssampler:
+                    ssampler.start()
                 e0.record()
                 sj.render(st)  # collect_stats = 0: segments / rays only; the call returns when the kernel has finished
                 e1.record()
                 sj.assemble()
                 e2.record()
                 stream.synchronize()
+                sclocks = ssampler.stop() if ssampler else None
                 barrier()
                 segs, rays = allsum([int(st.segments), int(st.rays)])
                 t_step, t_kern = allmax([e0.elapsed_time(e2), e0.elapsed_time(e1)])
@@ -462,6 +466,7 @@ def run_native(args):
                     "scaling": "strong", "steps": 1, "value": segs / (t_step / 1e3) / 1e6, "unit": UNIT,
                     "ms_per_step": t_step, "kernel_ms_max_rank": t_kern, "segments": segs, "rays": rays,
                     "image_mean": float(sj.image.mean().item()), "device_scene_bytes": sj.r.device_scene().device_bytes(),
+                    "clocks": sclocks,
                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                  "algorithmic_bytes_per_launch": bytes_all / world, "bytes_model": BYTES_MODEL,
                                  "per_ray": {"bvh_nodes": ctr["bvh_node_visits"] / max(ctr["rays"], 1), "bvh_tris": ctr["bvh_tri_tests"] / max(ctr["rays"], 1),

@@ -268,8 +268,8 @@ struct ArenaPut {
 // Uploads the flattened scene to s->device (the current device).  `release` = drop the host copies of the big
 // arrays as they are handed over (the last -- or only -- replica).
 int scene_bind_device(HostScene& hs, rptb_scene* s, bool release) {
-    pool_scene_born(s->device);
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    pool_scene_born(s->device);  // (paired with pool_scene_gone in destroy_replica, which keys on the stream's existence)
     s->arena.stream = s->stream;
     ArenaPut put{s->arena};
     if (!bind_scene(hs, put, release, s->view32, s->view64, s->f32_bytes)) CU(put.error);
