@@ -157,13 +157,15 @@ inline M4 inverse4(const M4& a) {
 
 // ------------------------------------------------------------ Philox -------
 // Philox4x32-10 (Salmon et al., SC'11).  key = (seed_lo, seed_hi),
-// counter = (block, pixel, sample_lo, sample_hi).  Each block yields two u64
-// draws: (x0 | x1<<32) then (x2 | x3<<32).
+// counter = (block, pixel, sample_lo, sample_hi).  A stream of u64 draws is two
+// Philox streams side by side: draw 4b + w = (word w of block b) << 32 | (word w
+// of block b | 2^31) -- the product's f32 kernels, which keep only the high half
+// of a draw, then need the first stream alone (rpt_b200/csrc/rng.cuh).
 struct Philox {
     uint32_t key[2];
     uint32_t ctr[4];
-    uint32_t out[4];
-    int have;  // number of unread u64 in out (0..2)
+    uint64_t out[4];
+    int have;  // number of unread u64 in out (0..4)
     static inline void round(uint32_t c[4], const uint32_t k[2]) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
@@ -190,13 +192,15 @@ struct Philox {
     }
     uint64_t next_u64() {
         if (have == 0) {
-            block(ctr, key, out);
+            uint32_t hi[4], lo[4];
+            const uint32_t low_ctr[4] = {ctr[0] | 0x80000000u, ctr[1], ctr[2], ctr[3]};
+            block(ctr, key, hi);
+            block(low_ctr, key, lo);
+            for (int w = 0; w < 4; w++) out[w] = ((uint64_t)hi[w] << 32) | lo[w];
             ctr[0]++;
-            have = 2;
+            have = 4;
         }
-        const int i = 2 - have;
-        have--;
-        return (uint64_t)out[2 * i] | ((uint64_t)out[2 * i + 1] << 32);
+        return out[4 - have--];
     }
 };
 

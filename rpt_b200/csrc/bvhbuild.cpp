@@ -27,6 +27,7 @@ namespace {
 
 using rptb::BvhNodeDev;
 using rptb::Bvh8Node;
+using rptb::Bvh4Node;
 
 struct Box {
     float lo[3], hi[3];
@@ -232,6 +233,50 @@ int32_t emit8(const Node& n, std::vector<Bvh8Node>& out, uint32_t depth, uint32_
     return (int32_t)me;
 }
 
+// ---- the four-wide form: the same greedy collapse, stopped at four children ----------------------------------------
+int32_t emit4(const Node& n, std::vector<Bvh4Node>& out, uint32_t depth, uint32_t& max_depth) {
+    const size_t me = out.size();
+    out.emplace_back();
+    max_depth = std::max(max_depth, depth);
+    const Node* kids[4];
+    int nk = 2;
+    kids[0] = n.kid[0].get();
+    kids[1] = n.kid[1].get();
+    while (nk < 4) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int i = 0; i < nk; i++)
+            if (!kids[i]->count && kids[i]->box.half_area() > best_area) best_area = kids[i]->box.half_area(), best = i;
+        if (best < 0) break;
+        const Node* open = kids[best];
+        kids[best] = open->kid[0].get();
+        kids[nk++] = open->kid[1].get();
+    }
+    float lo[4][3], hi[4][3];
+    int32_t code[4];
+    for (int i = 0; i < 4; i++) {
+        if (i >= nk) {  // an empty slot: a box nothing can enter, and a code the traversal never follows
+            // (both planes at +inf: every slab product is +inf or -inf on BOTH planes, never NaN, and near > far)
+            for (int a = 0; a < 3; a++) lo[i][a] = INFINITY, hi[i][a] = INFINITY;
+            code[i] = rptb::BVH8_EMPTY;
+            continue;
+        }
+        pad(kids[i]->box, lo[i], hi[i]);
+        code[i] = kids[i]->count ? ~(int32_t)((kids[i]->first << 3) | (kids[i]->count - 1u)) : emit4(*kids[i], out, depth + 1, max_depth);
+    }
+    Bvh4Node node;
+    std::memset(&node, 0, sizeof(node));
+    node.lox = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
+    node.hix = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+    node.loy = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+    node.hiy = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+    node.loz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+    node.hiz = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+    node.code = make_int4(code[0], code[1], code[2], code[3]);
+    out[me] = node;
+    return (int32_t)me;
+}
+
 }  // namespace
 
 namespace rptb {
@@ -242,7 +287,7 @@ namespace rptb {
 // whose two children are the halves of that leaf (the same leaf twice for a single triangle -- the second test of a
 // triangle can never tighten the hit, `time >= h.t` rejects it).
 int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& nodes, std::vector<uint32_t>& order,
-                   uint32_t& depth, std::vector<Bvh8Node>* nodes8) {
+                   uint32_t& depth, std::vector<Bvh8Node>* nodes8, std::vector<Bvh4Node>* nodes4) {
     if (ntris == 0 || ntris >= (1ull << 28)) return -1;
     std::vector<Prim> prims(ntris);
     for (uint64_t i = 0; i < ntris; i++) {
@@ -289,6 +334,13 @@ int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& 
         nodes8->clear();
         uint32_t depth8 = 0;
         emit8(*root, *nodes8, 0, depth8);
+    }
+    if (nodes4) {
+        nodes4->clear();
+        uint32_t depth4 = 0;
+        emit4(*root, *nodes4, 0, depth4);
+        // a ray pushes at most three entries per level it descends
+        if (3 * (depth4 + 1) > (uint32_t)rptb::BVH4_STACK) nodes4->clear();
     }
     order.resize(ntris);
     for (uint64_t i = 0; i < ntris; i++) order[i] = prims[i].id;

@@ -30,7 +30,7 @@ int build_kdtree_host(const double* tris, uint64_t ntris, std::vector<rptb_kdnod
 int build_kdtree_boxes_host(const double* boxes, uint64_t nboxes, std::vector<rptb_kdnode>& nodes, std::vector<uint32_t>& refs,
                             uint32_t& depth, uint32_t& max_leaf);
 int build_bvh_host(const double* tris, uint64_t ntris, std::vector<BvhNodeDev>& nodes, std::vector<uint32_t>& order, uint32_t& depth,
-                   std::vector<Bvh8Node>* nodes8 = nullptr);
+                   std::vector<Bvh8Node>* nodes8 = nullptr, std::vector<Bvh4Node>* nodes4 = nullptr);
 
 inline int flat_fail(std::string& err, int code, const char* fmt, ...) {
     char buf[512];
@@ -160,6 +160,7 @@ struct HostMesh : FlatTree {
     std::vector<float4> leaf_planes;
     std::vector<BvhNodeDev> bvh_nodes;  // F_BVH: the f32 path's own structure over the same triangles
     std::vector<Bvh8Node> bvh8_nodes;   // ... collapsed to eight children per node
+    std::vector<Bvh4Node> bvh4_nodes;   // ... and to four
     std::vector<float4> bvh_tri48;
     std::vector<uint32_t> bvh_ids;
     std::vector<float> verts32, norms32;
@@ -531,7 +532,7 @@ inline int flatten_scene(const rptb_scene_desc* d, HostScene& hs, std::string& e
         }
         if (!leaf && want_bvh) {  // the f32 path's own BVH over the same triangles (bvhbuild.cpp)
             uint32_t bvh_depth = 0;
-            if (build_bvh_host(d->meshes[i].tris, d->meshes[i].ntris, hm.bvh_nodes, hm.bvh_ids, bvh_depth, RPTB_BUILD_BVH8 ? &hm.bvh8_nodes : nullptr) != 0)
+            if (build_bvh_host(d->meshes[i].tris, d->meshes[i].ntris, hm.bvh_nodes, hm.bvh_ids, bvh_depth, RPTB_BUILD_BVH8 ? &hm.bvh8_nodes : nullptr, RPTB_BUILD_BVH4 ? &hm.bvh4_nodes : nullptr) != 0)
                 return flat_fail(err, RPTB_ERR_UNSUPPORTED, "mesh %u: cannot build a BVH over %llu triangles", i, (unsigned long long)d->meshes[i].ntris);
             if (bvh_depth + 2 >= (uint32_t)BVH_STACK)
                 return flat_fail(err, RPTB_ERR_UNSUPPORTED, "mesh %u: BVH depth %u exceeds the traversal stack (%d)", i, bvh_depth, BVH_STACK);
@@ -635,7 +636,7 @@ bool bind_scene(HostScene& hs, Put& put, bool release, SceneView<float>& v32, Sc
         MeshRec<double>& b = hs.t64.meshes[i];
         const uint64_t before = put.bytes();
         if (!put(hm.nodes32, &a.nodes) || !put(hm.refs, &a.refs) || !put(hm.tri48, &a.tri48) || !put(hm.leaf_planes, &a.leaf_planes) ||
-            !put(hm.verts32, &a.verts) || !put(hm.norms32, &a.norms) || !put(hm.bvh_nodes, &a.bvh_nodes) || !put(hm.bvh8_nodes, &a.bvh8_nodes) ||
+            !put(hm.verts32, &a.verts) || !put(hm.norms32, &a.norms) || !put(hm.bvh_nodes, &a.bvh_nodes) || !put(hm.bvh8_nodes, &a.bvh8_nodes) || !put(hm.bvh4_nodes, &a.bvh4_nodes) ||
             !put(hm.bvh_tri48, &a.bvh_tri48) || !put(hm.bvh_ids, &a.bvh_ids))
             return false;
         f32_bytes += put.bytes() - before;
@@ -650,6 +651,7 @@ bool bind_scene(HostScene& hs, Put& put, bool release, SceneView<float>& v32, Sc
             std::vector<float4>().swap(hm.leaf_planes);
             std::vector<BvhNodeDev>().swap(hm.bvh_nodes);
             std::vector<Bvh8Node>().swap(hm.bvh8_nodes);
+            std::vector<Bvh4Node>().swap(hm.bvh4_nodes);
             std::vector<float4>().swap(hm.bvh_tri48);
             std::vector<uint32_t>().swap(hm.bvh_ids);
             std::vector<float>().swap(hm.verts32);

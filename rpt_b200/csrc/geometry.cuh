@@ -365,6 +365,128 @@ RPTB_D bool bvh_intersect(const MeshRec<double>&, Vec3<double>, Vec3<double>, do
     return false;  // the f64 gate never uses the BVH
 }
 
+// ------------------------------------------------- the four-wide BVH ---------
+// One lane per ray through Bvh4Node: all four child boxes decided from one 112-byte fetch, the hit children sorted by
+// entry distance (a five-exchange network on (t, code) pairs), the nearest followed and the others stacked farthest
+// first WITH their entry distance, so that a popped entry the ray has meanwhile found a closer hit than is dropped
+// without a fetch.  Same leaves, same triangle test and the same answer as bvh_intersect (ties in t aside).
+#define RPTB_CSWAP(i, j)                                   \
+    {                                                      \
+        const bool s_ = tn[j] < tn[i];                     \
+        const float ta_ = s_ ? tn[j] : tn[i];              \
+        const float tb_ = s_ ? tn[i] : tn[j];              \
+        const int32_t ca_ = s_ ? cd[j] : cd[i];            \
+        const int32_t cb_ = s_ ? cd[i] : cd[j];            \
+        tn[i] = ta_, tn[j] = tb_, cd[i] = ca_, cd[j] = cb_; \
+    }
+template <bool STATS>
+RPTB_D bool bvh4_intersect(const MeshRec<float>& m, Vec3<float> o, Vec3<float> d, float tmin, bool any, Hit<float>& h,
+                           TravStats& ts) {
+    const Vec3<float> inv = {slab_rcp(d.x), slab_rcp(d.y), slab_rcp(d.z)};
+    const Vec3<float> oi = {o.x * inv.x, o.y * inv.y, o.z * inv.z};
+    const float inf = M<float>::inf();
+    int32_t scode[BVH4_STACK];
+    float stn[BVH4_STACK];
+    int sp = 0;
+    int32_t cur = 0;  // the root is always an inner node
+    bool hit = false;
+    while (true) {
+        while (cur >= 0) {
+            if (STATS) ts.bvh_nodes += 2;  // counted in 64-byte units, like the binary tree's nodes
+            const float4* q = reinterpret_cast<const float4*>(m.bvh4_nodes + cur);
+            const float4 lox = ldg(q), hix = ldg(q + 1), loy = ldg(q + 2), hiy = ldg(q + 3), loz = ldg(q + 4), hiz = ldg(q + 5);
+            const int4 code = ldg(reinterpret_cast<const int4*>(q + 6));
+            const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, hx[4] = {hix.x, hix.y, hix.z, hix.w};
+            const float ly[4] = {loy.x, loy.y, loy.z, loy.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w};
+            const float lz[4] = {loz.x, loz.y, loz.z, loz.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+            float tn[4];
+            int32_t cd[4] = {code.x, code.y, code.z, code.w};
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int k = 0; k < 4; k++) {
+                const float x0 = fmaf(lx[k], inv.x, -oi.x), x1 = fmaf(hx[k], inv.x, -oi.x);
+                const float y0 = fmaf(ly[k], inv.y, -oi.y), y1 = fmaf(hy[k], inv.y, -oi.y);
+                const float z0 = fmaf(lz[k], inv.z, -oi.z), z1 = fmaf(hz[k], inv.z, -oi.z);
+                const float nr = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+                const float fr = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), h.t));
+                tn[k] = (nr <= fr && cd[k] != BVH8_EMPTY) ? nr : inf;
+            }
+            RPTB_CSWAP(0, 1)
+            RPTB_CSWAP(2, 3)
+            RPTB_CSWAP(0, 2)
+            RPTB_CSWAP(1, 3)
+            RPTB_CSWAP(1, 2)
+            if (tn[0] == inf) {  // nothing hit: back to the nearest pending entry still in range
+                cur = BVH8_EMPTY;
+                while (sp > 0) {
+                    --sp;
+                    if (stn[sp] < h.t) {
+                        cur = scode[sp];
+                        break;
+                    }
+                }
+                if (cur == BVH8_EMPTY) return hit;
+                continue;
+            }
+            if (tn[3] < inf) scode[sp] = cd[3], stn[sp] = tn[3], sp++;
+            if (tn[2] < inf) scode[sp] = cd[2], stn[sp] = tn[2], sp++;
+            if (tn[1] < inf) scode[sp] = cd[1], stn[sp] = tn[1], sp++;
+            cur = cd[0];
+        }
+        {  // leaf: ~cur = (first << 3) | (count - 1)
+            const uint32_t lcode = (uint32_t)~cur;
+            const uint32_t first = lcode >> 3, count = (lcode & 7u) + 1u;
+            for (uint32_t k = first; k < first + count; k++) {
+                if (STATS) ts.bvh_tris++;
+                const float4* q = m.bvh_tri48 + 3 * (size_t)k;
+                const float4 q0 = ldg(q);
+                const float cosine = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+                if (fabsf(cosine) < 1e-8f) continue;
+                const float time = fdividef(q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z), cosine);
+                if (time < tmin || time >= h.t) continue;
+                const float4 q1 = ldg(q + 1);
+                const float4 q2 = ldg(q + 2);
+                const float px = fmaf(time, d.x, o.x), py = fmaf(time, d.y, o.y), pz = fmaf(time, d.z, o.z);
+                const float v = fmaf(q1.x, px, fmaf(q1.y, py, fmaf(q1.z, pz, q1.w)));
+                const float w = fmaf(q2.x, px, fmaf(q2.y, py, fmaf(q2.z, pz, q2.w)));
+                const float u = 1.0f - v - w;
+                if (u >= 0.0f && v >= 0.0f && w >= 0.0f) {
+                    h.t = time;
+                    h.bv = v;
+                    h.bw = w;
+                    h.aux = ldg(m.bvh_ids + k);
+                    hit = true;
+                }
+            }
+        }
+        if (any && hit) return true;
+        cur = BVH8_EMPTY;
+        while (sp > 0) {
+            --sp;
+            if (stn[sp] < h.t) {
+                cur = scode[sp];
+                break;
+            }
+        }
+        if (cur == BVH8_EMPTY) return hit;
+    }
+}
+#undef RPTB_CSWAP
+template <bool STATS>
+RPTB_D bool bvh4_intersect(const MeshRec<double>&, Vec3<double>, Vec3<double>, double, bool, Hit<double>&, TravStats&) {
+    return false;
+}
+
+// what a mesh with a BVH is traversed through: the four-wide tree where the scene has one, else the binary tree
+template <bool STATS, typename R>
+RPTB_D bool bvh_query(const MeshRec<R>& m, Vec3<R> o, Vec3<R> d, R tmin, bool any, Hit<R>& h, TravStats& ts) {
+#if RPTB_BVH4
+    if (m.bvh4_nodes) return bvh4_intersect<STATS>(m, o, d, tmin, any, h, ts);
+#endif
+    return bvh_intersect<STATS>(m, o, d, tmin, any, h, ts);
+}
+
 // ------------------------------------------------- the eight-wide BVH --------
 // Per-lane (scalar) traversal of the collapsed tree: test infrastructure for the builder (tests/hostemu checks its hits
 // against the binary tree's) -- the product traverses Bvh8Node with groups of eight lanes, below.
@@ -624,7 +746,7 @@ RPTB_D bool kd_intersect(const SceneView<R>& sv, const MeshRec<R>& m, Vec3<R> o,
         return hit;
     }
     if constexpr (!(FEAT & F_TREE) && !M<R>::literal) return false;  // (unreachable: compiled for tree-less scenes)
-    if constexpr ((FEAT & F_BVH) != 0 && !M<R>::literal) return bvh_intersect<STATS>(m, o, d, tmin, any, h, ts);
+    if constexpr ((FEAT & F_BVH) != 0 && !M<R>::literal) return bvh_query<STATS>(m, o, d, tmin, any, h, ts);
     // root cull: BoundingBox::intersect of `bounds` (kdtree.rs:130-134)
     R lo, hi;
     Vec3<R> inv;
@@ -975,7 +1097,7 @@ __device__ __forceinline__ void closest_hit_coop(const SceneView<float>& sv, con
             const unsigned m = __ballot_sync(0xffffffffu, pred);
             if (__popc(m) > RPTB_COOP_MAX) {
                 // many rays of the warp enter the mesh (coherent camera or shadow rays): one ray per lane fills the warp
-                if (pred && bvh_intersect<STATS>(mm, o, d, tmin, any, h, ts)) h.obj = (int)i;
+                if (pred && bvh_query<STATS>(mm, o, d, tmin, any, h, ts)) h.obj = (int)i;
             } else if (m != 0u) {
                 const uint32_t pos = (uint32_t)__popc(m & ((1u << lane) - 1u));
                 if (pred) {
@@ -990,7 +1112,7 @@ __device__ __forceinline__ void closest_hit_coop(const SceneView<float>& sv, con
                 if (pred) {
                     const float4 r = cw.res[pos];
                     if (r.x == -2.0f) {  // the group's stack overflowed (a pathological tree): the binary BVH has no such limit
-                        if (bvh_intersect<STATS>(mm, o, d, tmin, any, h, ts)) h.obj = (int)i;
+                        if (bvh_query<STATS>(mm, o, d, tmin, any, h, ts)) h.obj = (int)i;
                     } else if (r.x >= 0.0f) {
                         h.t = r.x;
                         h.bv = r.y;

@@ -127,12 +127,16 @@ struct DeviceWarp {
 };
 #endif
 
-// The generator the megakernel draws from: f64 the oracle's, f32 the shared-memory ring (rng.cuh)
-template <class R>
+// The generator the megakernel draws from: f64 the oracle's; f32 the same stream buffered in registers the way that
+// suits the instantiation (rng.cuh: the 64-register F_BVH kernels take the smallest buffer), or the shared-memory ring
+template <class R, int FEAT>
 struct MegaRng { typedef Rng<R> type; };
-#if !RPTB_RNG_FIFO
-template <>
-struct MegaRng<float> { typedef RngRing type; };
+#if RPTB_RNG_FIFO
+template <int FEAT>
+struct MegaRng<float, FEAT> { typedef RngF32<(FEAT & F_BVH) ? RPTB_FIFO_MODE_BVH : RPTB_FIFO_MODE> type; };
+#else
+template <int FEAT>
+struct MegaRng<float, FEAT> { typedef RngRing type; };
 #endif
 
 // `rng_ring`: RNG_RING * RENDER_THREADS words of shared memory (f32 on the device; null otherwise).
@@ -168,7 +172,7 @@ RPTB_D void render_thread(const SceneView<R>& sv, const RenderArgs<R>& a, const 
     PathCounters pc = {0, 0, 0, 0, {0, 0, 0, 0, 0}};
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     Level<R> stack[M<R>::literal ? MAXD : 1];  // f64 gate only
-    typename MegaRng<R>::type rng;
+    typename MegaRng<R, FEAT>::type rng;
     rng.bind(rng_ring ? rng_ring + thread_x : nullptr, RENDER_THREADS);
     rng.init(a.seed, pix, a.first_sample);
 

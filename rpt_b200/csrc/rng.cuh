@@ -8,7 +8,12 @@
 //   UnitCircle        src/material.rs:251
 // The reference seeds ChaCha12 from OS entropy per row (src/renderer.rs:121); here
 // key = (seed_lo, seed_hi), counter = (block, pixel, sample_lo, sample_hi).
-// Each block yields two 64-bit draws: (x0 | x1<<32), then (x2 | x3<<32).
+// A path's stream of 64-bit draws is TWO Philox streams side by side: draw 4b + w has word w of block b as its high
+// half and word w of block (b | 2^31) as its low half.  The f32 kernels only ever look at the high half of a draw (24
+// bits of it make a float), so they compute the first stream alone and use all four words of every block; the f64
+// gate and the oracle compute both.  (Until round 2 a block was cut into two 64-bit draws and the f32 path threw the
+// low words away: half of its Philox work -- a quarter of Cornell's warp instructions, ncu -- bought nothing.)
+constexpr uint32_t PHILOX_LOW_STREAM = 0x80000000u;
 #pragma once
 #include "vec.cuh"
 
@@ -17,8 +22,8 @@ namespace rptb {
 struct Philox {
     uint32_t key0, key1;
     uint32_t block, pixel, samp_lo, samp_hi;
-    uint32_t spare_lo, spare_hi;
-    bool have_spare;
+    uint64_t d1, d2, d3;  // the draws of the current block pair not handed out yet, next first
+    uint32_t left;
 
     RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) {
         key0 = (uint32_t)seed;
@@ -27,8 +32,8 @@ struct Philox {
         pixel = pix;
         samp_lo = (uint32_t)sample;
         samp_hi = (uint32_t)(sample >> 32);
-        have_spare = false;
-        spare_lo = spare_hi = 0;
+        left = 0;
+        d1 = d2 = d3 = 0;
     }
 
     static RPTB_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
@@ -71,25 +76,29 @@ struct Philox {
 #endif
     RPTB_HD uint64_t refill() {
 #ifdef __CUDA_ARCH__
-        const uint4 v = block_call(block, pixel, samp_lo, samp_hi, key0, key1);
-        const uint32_t o[4] = {v.x, v.y, v.z, v.w};
+        const uint4 vh = block_call(block, pixel, samp_lo, samp_hi, key0, key1);
+        const uint4 vl = block_call(block | PHILOX_LOW_STREAM, pixel, samp_lo, samp_hi, key0, key1);
+        const uint32_t hi[4] = {vh.x, vh.y, vh.z, vh.w}, lo[4] = {vl.x, vl.y, vl.z, vl.w};
 #else
-        uint32_t o[4];
-        block10(block, pixel, samp_lo, samp_hi, key0, key1, o);
+        uint32_t hi[4], lo[4];
+        block10(block, pixel, samp_lo, samp_hi, key0, key1, hi);
+        block10(block | PHILOX_LOW_STREAM, pixel, samp_lo, samp_hi, key0, key1, lo);
 #endif
         block++;
-        spare_lo = o[2];
-        spare_hi = o[3];
-        have_spare = true;
-        return (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+        d1 = ((uint64_t)hi[1] << 32) | lo[1];
+        d2 = ((uint64_t)hi[2] << 32) | lo[2];
+        d3 = ((uint64_t)hi[3] << 32) | lo[3];
+        left = 3;
+        return ((uint64_t)hi[0] << 32) | lo[0];
     }
 
     RPTB_HD uint64_t next_u64() {
-        if (have_spare) {
-            have_spare = false;
-            return (uint64_t)spare_lo | ((uint64_t)spare_hi << 32);
-        }
-        return refill();
+        if (left == 0) return refill();
+        const uint64_t v = d1;
+        d1 = d2;
+        d2 = d3;
+        left--;
+        return v;
     }
 };
 
@@ -133,37 +142,73 @@ struct Rng<double> {
 };
 
 // f32: only the HIGH 32-bit word of each 64-bit draw is kept -- its top 24 bits are the f64
-// value truncated to a float in [0,1), so both precisions see the same stream.  The words
-// are produced a block (two draws) at a time into a 4-entry register FIFO by ensure(),
-// which the integrator calls where the whole warp is converged: the ~60-instruction
-// Philox block then runs once for 32 lanes instead of once per lane per call site.
+// value truncated to a float in [0,1), so both precisions see the same stream -- and the high
+// words are the first Philox stream's words in order (see the top of the file): a block is four
+// draws.  They enter a 4-entry register FIFO two at a time (the other two of a block wait in
+// s0/s1; `half` counts pairs, its low bit says a pair is waiting) from ensure(), which the
+// integrator calls where the whole warp is converged: the ~60-instruction Philox block then runs
+// once for 32 lanes instead of once per lane per call site.
 // gen_bool / Uniform(0..n) decide on the high word alone; the decision differs from the
 // 64-bit one with probability <= n * 2^-32 per draw (f32 mode only).
-template <>
-struct Rng<float> {
-    uint32_t key0, key1, block, pixel, samp_lo, samp_hi;
-    uint32_t q0, q1, q2, q3;
-    uint32_t avail;
-    RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) {
+// How the four draws of a block are buffered is a template parameter (same stream, bit for bit, whichever):
+//   BUF_PAIR  two draws enter a 4-entry FIFO, the other two wait in s0/s1           (6 words)
+//   BUF_FOUR  a 4-entry FIFO, refilled when empty                                    (4 words)
+//   BUF_EIGHT an 8-entry FIFO; a block enters whenever four entries are free          (8 words)
+//   BUF_TWO   the block being drawn from and the one after it, side by side           (8 words)
+// Measured on one B200 (gpurun r02r/r02s, Msamples/s at 64-100 spp; PAIR / FOUR / EIGHT / TWO):
+//   sphere 10 595 / 10 515 / 11 619 / 11 540, cornell 4 670 / 4 705 / 5 214 / 5 081, glass 19 620 / 20 631 / 20 359 / 20 846,
+//   teapot 17 253 / 18 802 / 17 201 / 17 119, monomial_glass 7 232 / 6 873 / 7 006 / 6 681.
+// EIGHT keeps ensure() -- the converged point -- the place where nearly every block is computed (a lane holds >= 4
+// draws after it, and few slots draw more); FOUR is the smallest in registers, which is what the 64-register kernels of
+// the mesh scenes (F_BVH, 8 CTAs per SM) want.  The megakernel picks per instantiation (integrator.cuh, MegaRng).
+enum { BUF_PAIR = 0, BUF_FOUR = 1, BUF_EIGHT = 2, BUF_TWO = 3 };
+#ifndef RPTB_FIFO_MODE
+#define RPTB_FIFO_MODE 2      // Rng<float>, and the megakernel's generator for scenes without a BVH
+#endif
+#ifndef RPTB_FIFO_MODE_BVH
+#define RPTB_FIFO_MODE_BVH 1  // the megakernel's generator in F_BVH instantiations
+#endif
+
+template <int BUF>
+struct RngBuf;  // state + push_block() / ensure() / next32() / save() / load()
+
+struct RngStream {  // which block comes next
+    uint32_t key0, key1, half, pixel, samp_lo, samp_hi;  // half: pairs of draws produced so far (block = half >> 1)
+    RPTB_HD void init_stream(uint64_t seed, uint32_t pix, uint64_t sample) {
         key0 = (uint32_t)seed;
         key1 = (uint32_t)(seed >> 32);
-        block = 0;
+        half = 0;
         pixel = pix;
         samp_lo = (uint32_t)sample;
         samp_hi = (uint32_t)(sample >> 32);
-        q0 = q1 = q2 = q3 = 0;
-        avail = 0;
     }
-    RPTB_HD void push_block() {  // requires avail <= 2
+    RPTB_HD void block4(uint32_t o[4]) {
 #ifdef __CUDA_ARCH__
-        const uint4 v = Philox::block_call(block, pixel, samp_lo, samp_hi, key0, key1);
-        const uint32_t a = v.y, b = v.w;
+        const uint4 v = Philox::block_call(half >> 1, pixel, samp_lo, samp_hi, key0, key1);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 #else
-        uint32_t o[4];
-        Philox::block10(block, pixel, samp_lo, samp_hi, key0, key1, o);
-        const uint32_t a = o[1], b = o[3];
+        Philox::block10(half >> 1, pixel, samp_lo, samp_hi, key0, key1, o);
 #endif
-        block++;
+    }
+};
+
+template <>
+struct RngBuf<BUF_PAIR> : RngStream {
+    uint32_t q0, q1, q2, q3, s0, s1, avail;
+    RPTB_HD void clear() { q0 = q1 = q2 = q3 = s0 = s1 = 0; avail = 0; }
+    RPTB_HD void save(uint32_t* w) const { w[0] = q0; w[1] = q1; w[2] = q2; w[3] = q3; w[4] = s0; w[5] = s1; }
+    RPTB_HD void load(const uint32_t* w) { q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3]; s0 = w[4]; s1 = w[5]; }
+    RPTB_HD void push_block() {  // the next two draws of the stream; requires avail <= 2
+        uint32_t a, b;
+        if (half & 1u) {
+            a = s0;
+            b = s1;
+        } else {
+            uint32_t o[4];
+            block4(o);
+            a = o[0]; b = o[1]; s0 = o[2]; s1 = o[3];
+        }
+        half++;
         if (avail == 0) { q0 = a; q1 = b; }
         else if (avail == 1) { q1 = a; q2 = b; }
         else { q2 = a; q3 = b; }
@@ -173,32 +218,129 @@ struct Rng<float> {
         if (avail <= 2) push_block();
         if (avail <= 2) push_block();
     }
-    template <class W>
-    RPTB_HD void ensure(unsigned, uint32_t) { ensure(); }  // (a 6-entry FIFO refilled to the slot's expected draws was measured too: Cornell 4 841 vs 5 673)
-    RPTB_HD void bind(uint32_t*, uint32_t) {}
     RPTB_HD uint32_t next32() {
-        if (avail == 0) push_block();  // rare: a slot consumed more than the FIFO held
+        if (avail == 0) push_block();  // a slot consumed more than the FIFO held
         const uint32_t v = q0;
         q0 = q1; q1 = q2; q2 = q3;
         avail--;
         return v;
     }
-    RPTB_HD float gen() { return (float)(next32() >> 8) * (1.0f / 16777216.0f); }
+};
+
+template <>
+struct RngBuf<BUF_FOUR> : RngStream {
+    uint32_t q0, q1, q2, q3, avail;
+    RPTB_HD void clear() { q0 = q1 = q2 = q3 = 0; avail = 0; }
+    RPTB_HD void save(uint32_t* w) const { w[0] = q0; w[1] = q1; w[2] = q2; w[3] = q3; }
+    RPTB_HD void load(const uint32_t* w) { q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3]; }
+    RPTB_HD void push_block() {  // a whole block; requires avail == 0
+        uint32_t o[4];
+        block4(o);
+        half += 2;
+        q0 = o[0]; q1 = o[1]; q2 = o[2]; q3 = o[3];
+        avail = 4;
+    }
+    RPTB_HD void ensure() {
+        if (avail == 0) push_block();
+    }
+    RPTB_HD uint32_t next32() {
+        if (avail == 0) push_block();
+        const uint32_t v = q0;
+        q0 = q1; q1 = q2; q2 = q3;
+        avail--;
+        return v;
+    }
+};
+
+template <>
+struct RngBuf<BUF_EIGHT> : RngStream {
+    uint32_t q0, q1, q2, q3, q4, q5, q6, q7, avail;
+    RPTB_HD void clear() { q0 = q1 = q2 = q3 = q4 = q5 = q6 = q7 = 0; avail = 0; }
+    RPTB_HD void save(uint32_t* w) const { w[0] = q0; w[1] = q1; w[2] = q2; w[3] = q3; w[4] = q4; w[5] = q5; w[6] = q6; w[7] = q7; }
+    RPTB_HD void load(const uint32_t* w) { q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3]; q4 = w[4]; q5 = w[5]; q6 = w[6]; q7 = w[7]; }
+    RPTB_HD void push_block() {  // a whole block; requires avail <= 4
+        uint32_t o[4];
+        block4(o);
+        half += 2;
+        switch (avail) {
+            case 0: q0 = o[0]; q1 = o[1]; q2 = o[2]; q3 = o[3]; break;
+            case 1: q1 = o[0]; q2 = o[1]; q3 = o[2]; q4 = o[3]; break;
+            case 2: q2 = o[0]; q3 = o[1]; q4 = o[2]; q5 = o[3]; break;
+            case 3: q3 = o[0]; q4 = o[1]; q5 = o[2]; q6 = o[3]; break;
+            default: q4 = o[0]; q5 = o[1]; q6 = o[2]; q7 = o[3]; break;
+        }
+        avail += 4;
+    }
+    RPTB_HD void ensure() {
+        if (avail <= 4) push_block();
+    }
+    RPTB_HD uint32_t next32() {
+        if (avail == 0) push_block();
+        const uint32_t v = q0;
+        q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5; q5 = q6; q6 = q7;
+        avail--;
+        return v;
+    }
+};
+
+template <>
+struct RngBuf<BUF_TWO> : RngStream {
+    // draws leave q0..q3 (three moves per draw, as in the 4-entry FIFO); a whole block enters either q (nothing
+    // buffered) or b (the block after: present iff avail > 4, and then q is not empty); b moves up when q runs empty
+    uint32_t q0, q1, q2, q3, b0, b1, b2, b3, avail;
+    RPTB_HD void clear() { q0 = q1 = q2 = q3 = b0 = b1 = b2 = b3 = 0; avail = 0; }
+    RPTB_HD void save(uint32_t* w) const { w[0] = q0; w[1] = q1; w[2] = q2; w[3] = q3; w[4] = b0; w[5] = b1; w[6] = b2; w[7] = b3; }
+    RPTB_HD void load(const uint32_t* w) { q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3]; b0 = w[4]; b1 = w[5]; b2 = w[6]; b3 = w[7]; }
+    RPTB_HD void push_block() {  // requires avail <= 4
+        uint32_t o[4];
+        block4(o);
+        half += 2;
+        if (avail == 0) { q0 = o[0]; q1 = o[1]; q2 = o[2]; q3 = o[3]; }
+        else { b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3]; }
+        avail += 4;
+    }
+    RPTB_HD void ensure() {
+        if (avail <= 4) push_block();
+    }
+    RPTB_HD uint32_t next32() {
+        if (avail == 0) push_block();
+        const uint32_t v = q0;
+        q0 = q1; q1 = q2; q2 = q3;
+        if (avail == 5) { q0 = b0; q1 = b1; q2 = b2; q3 = b3; }  // that was q's last draw and b is waiting
+        avail--;
+        return v;
+    }
+};
+
+template <int BUF>
+struct RngF32 : RngBuf<BUF> {
+    static constexpr int STATE_WORDS = 8;  // what save() may write
+    RPTB_HD void init(uint64_t seed, uint32_t pix, uint64_t sample) {
+        this->init_stream(seed, pix, sample);
+        this->clear();
+    }
+    template <class W>
+    RPTB_HD void ensure(unsigned, uint32_t) { RngBuf<BUF>::ensure(); }  // (topping up to the slot's expected draws instead was measured too: Cornell 4 841 vs 5 673)
+    RPTB_HD void ensure() { RngBuf<BUF>::ensure(); }
+    RPTB_HD void bind(uint32_t*, uint32_t) {}
+    RPTB_HD float gen() { return (float)(this->next32() >> 8) * (1.0f / 16777216.0f); }
     RPTB_HD float u52() { return gen(); }
     RPTB_HD bool bernoulli(float prob) {
-        const uint32_t v = next32();
+        const uint32_t v = this->next32();
         if (prob >= 1.0f) return true;
         return v < (uint32_t)((uint64_t)((double)prob * 18446744073709551616.0) >> 32);
     }
-    RPTB_HD bool coin() { return (next32() >> 31) != 0; }
+    RPTB_HD bool coin() { return (this->next32() >> 31) != 0; }
     RPTB_HD uint64_t below(uint64_t n) {
 #ifdef __CUDA_ARCH__
-        return (uint64_t)__umulhi(next32(), (uint32_t)n);
+        return (uint64_t)__umulhi(this->next32(), (uint32_t)n);
 #else
-        return ((uint64_t)next32() * (uint32_t)n) >> 32;
+        return ((uint64_t)this->next32() * (uint32_t)n) >> 32;
 #endif
     }
 };
+template <>
+struct Rng<float> : RngF32<RPTB_FIFO_MODE> {};
 
 // The megakernel's f32 generator: the same stream as Rng<float> (high word of every 64-bit draw), buffered in an
 // 8-entry ring per thread that lives in SHARED memory on the device (entry i of thread t at ring[i * stride + t]:
@@ -245,19 +387,20 @@ struct RngRing {
         avail = 0;
     }
     RPTB_HD uint32_t& at(uint32_t i) { return ring[(i & (RNG_RING - 1u)) * stride]; }
-    RPTB_HD void push_block() {  // requires avail <= RNG_RING - 2
+    RPTB_HD void push_block() {  // four draws; requires avail <= RNG_RING - 4
 #ifdef __CUDA_ARCH__
         const uint4 v = Philox::block_call(block, pixel, samp_lo, samp_hi, key0, key1);
-        const uint32_t a = v.y, b = v.w;
+        const uint32_t o[4] = {v.x, v.y, v.z, v.w};
 #else
         uint32_t o[4];
         Philox::block10(block, pixel, samp_lo, samp_hi, key0, key1, o);
-        const uint32_t a = o[1], b = o[3];
 #endif
         block++;
-        at(head + avail) = a;
-        at(head + avail + 1u) = b;
-        avail += 2;
+        at(head + avail) = o[0];
+        at(head + avail + 1u) = o[1];
+        at(head + avail + 2u) = o[2];
+        at(head + avail + 3u) = o[3];
+        avail += 4;
     }
     // W = the warp policy of integrator.cuh (real votes on the device, a single lane in host emulation).  `need` = how
     // many draws this lane expects to take before the next converged point (0 for a lane that will draw nothing): the
@@ -265,21 +408,21 @@ struct RngRing {
     // after two draws (a camera ray that leaves the scene) costs one Philox block, not a ring full.
     template <class W>
     RPTB_HD void ensure(unsigned mask, uint32_t need) {
-        // (a block is two entries: a lane can take one while avail <= RNG_RING - 2)
+        // (a block is four entries: a lane can take one while avail <= RNG_RING - 4)
 #if RPTB_RNG_FILL
         // A/B switch: top every lane up to >= 6 entries whatever it is about to draw
         (void)need;
-        while (W::any(mask, avail <= 5u)) {
-            if (avail <= RNG_RING - 2u) push_block();
+        while (W::any(mask, avail <= RNG_RING - 4u)) {
+            if (avail <= RNG_RING - 4u) push_block();
         }
 #else
-        while (W::any(mask, avail < need && avail <= RNG_RING - 2u)) {
-            if (avail < need && avail <= RNG_RING - 2u) push_block();
+        while (W::any(mask, avail < need && avail <= RNG_RING - 4u)) {
+            if (avail < need && avail <= RNG_RING - 4u) push_block();
         }
 #endif
     }
     RPTB_HD uint32_t next32() {
-        if (avail == 0) push_block();  // rare: a slot consumed more than six draws
+        if (avail == 0) push_block();  // a slot consumed more than the ring held
         const uint32_t v = at(head);
         head++;
         avail--;

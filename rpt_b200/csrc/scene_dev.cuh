@@ -108,7 +108,28 @@ struct Bvh8Node {
     Bvh8Child c[8];
 };
 constexpr int32_t BVH8_EMPTY = (int32_t)0x80000000;
+
+// The four-wide form for ONE lane per ray (geometry.cuh, bvh4_intersect): a node holds the boxes of four children as
+// six float4 (one per box plane, child k in component k), so the slab test of all four is 24 FMAs on whole vectors and a
+// ray takes half as many dependent fetches as through the binary tree -- the node loop is latency bound (ncu:
+// long_scoreboard on top at 5-6 active lanes).  Child codes as in Bvh8Node (>= 0 inner, BVH8_EMPTY none, else leaf).
+#ifndef RPTB_BUILD_BVH4
+#define RPTB_BUILD_BVH4 RPTB_BVH4  // the builder makes the four-wide tree only for a build that walks it (tests/hostemu sets it on its own)
+#endif
+struct __align__(16) Bvh4Node {
+    float4 lox, hix, loy, hiy, loz, hiz;
+    int4 code;
+    int4 _pad;
+};
+#ifndef RPTB_BVH4
+#define RPTB_BVH4 0  // 1: meshes with a BVH are traversed through the four-wide tree.  Measured (gpurun r02p, one B200, Msamples/s, binary / four-wide
+                     // at 8, 6, 5 CTAs per SM): teapot 17 002 / 12 707 / 14 153 / 14 115, dragon 1 796 / 1 439 / 1 449 / 1 408, dragon_knot
+                     // 1 002 / 850 / 794 / 760, fractal_teapots 644 / 594 / 580 / 584 -- 0.45x the dependent fetches (tests/test_hostemu.py) but
+                     // 24 slab FMAs + a sorting network per step whether one child is hit or four: the loop is bound by issue slots at 5-6
+                     // active lanes, not by the fetch latency alone, so the binary tree stays the default.
+#endif
 constexpr int BVH8_STACK = 48;     // entries of a group's traversal stack in shared memory (overflow -> the ray falls back to the binary BVH)
+constexpr int BVH4_STACK = 64;     // (code, entry t) pairs of the four-wide traversal; the builder drops the four-wide tree of a mesh too deep for it
 constexpr int BVH_STACK = 96;      // traversal stack entries; the builder keeps the depth below it (bvhbuild.cpp)
 constexpr int BVH_LEAF_MAX = 4;    // triangles per leaf (3 bits in the leaf code would allow 8)
 
@@ -120,6 +141,7 @@ struct MeshRec {
     const float4* leaf_planes;  // f32, kd-tree meshes only: tri48[3*refs[k]] for every leaf ref k (planes in leaf order)
     const BvhNodeDev* bvh_nodes;  // f32, when the scene was created with the BVH (F_BVH): node 0 is the root
     const Bvh8Node* bvh8_nodes;   // the same tree, eight children per node (node 0 = root), for the lane-group traversal
+    const Bvh4Node* bvh4_nodes;   // the same tree, four children per node: what one lane per ray traverses (RPTB_BVH4)
     const float4* bvh_tri48;      // tri48 permuted into BVH leaf order (a leaf's triangles are contiguous)
     const uint32_t* bvh_ids;      // original triangle index of each BVH-order triangle (normals, Hit::aux)
     const R* verts;       // 9 per triangle

@@ -73,7 +73,7 @@ struct __align__(16) WfPath {
     float fwdTmin2;
     uint32_t chunk_id;  // sample chunk this path is summing (scene_dev.cuh: RenderArgs::chunk)
     uint32_t rng_block, rng_avail;
-    uint32_t rng_q[4];
+    uint32_t rng_q[8];  // the generator's buffered draws (Rng<float>::save)
     double acc[3];
     double _pad1;
 };
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade_kernel(const SceneView<fl
     const uint32_t pix = y * a.width + x;
     Rng<R> rng;
     rng.init(a.seed, pix, a.first_sample + st.s);
-    rng.block = st.rng_block;
+    rng.half = st.rng_block;
     rng.avail = st.rng_avail;
-    rng.q0 = st.rng_q[0]; rng.q1 = st.rng_q[1]; rng.q2 = st.rng_q[2]; rng.q3 = st.rng_q[3];
+    rng.load(st.rng_q);
 
     uint32_t n_seg = 0, n_mesh = 0, n_env = 0, n_rays = 0;
     Vec3<R> color = {st.color[0], st.color[1], st.color[2]};
@@ -381,9 +381,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade_kernel(const SceneView<fl
         st.fwdT0 = fwdT.x; st.fwdT12[0] = fwdT.y; st.fwdT12[1] = fwdT.z;
         st.fwdTmin[0] = fwdTmin.x; st.fwdTmin[1] = fwdTmin.y; st.fwdTmin2 = fwdTmin.z;
         st.flags = (st.flags & ~8u) | (fwd_ok ? 8u : 0u);
-        st.rng_block = rng.block;
+        st.rng_block = rng.half;
         st.rng_avail = rng.avail;
-        st.rng_q[0] = rng.q0; st.rng_q[1] = rng.q1; st.rng_q[2] = rng.q2; st.rng_q[3] = rng.q3;
+        rng.save(st.rng_q);
         b.paths[p] = st;
     }
 

@@ -31,6 +31,7 @@ def lib():
         L.hostemu_occluded.argtypes = [C.c_void_p, dp, dp, C.c_uint64, C.c_double, C.c_uint32, C.c_int, capi.c_i32_p]
         L.hostemu_bvh_check.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.hostemu_bvh8_probe.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_int, dp, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+        L.hostemu_bvh4_probe.argtypes = L.hostemu_bvh8_probe.argtypes
         L.hostemu_illuminate.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_uint64, C.c_uint32, dp, dp, dp]
         _lib = L
     return _lib
@@ -96,6 +97,18 @@ class EmuScene:
                                     tri.ctypes.data_as(C.POINTER(C.c_int64)), info) != 0:
             return None
         return t, tri, dict(zip(("nodes8", "max_children", "empty_slots", "visits2", "visits8"), [int(v) for v in info]))
+
+    def bvh4_probe(self, mesh, rays, any_hit=False):
+        """Mesh-local rays through the binary BVH and through its four-wide collapse: (t[n, 2], tri[n, 2], info) or None."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        n = rays.shape[0]
+        t = np.empty((n, 2))
+        tri = np.empty((n, 2), np.int64)
+        info = (C.c_uint64 * 6)()
+        if lib().hostemu_bvh4_probe(self.handle, mesh, rays.ctypes.data_as(dp), n, 1 if any_hit else 0, t.ctypes.data_as(dp),
+                                    tri.ctypes.data_as(C.POINTER(C.c_int64)), info) != 0:
+            return None
+        return t, tri, dict(zip(("nodes4", "empty_slots", "visits2", "visits4", "tris2", "tris4"), [int(v) for v in info]))
 
     def closest_hit(self, rays, t_min=1e-12, precision=capi.PRECISION_F64):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)

@@ -358,6 +358,38 @@ int hostemu_bvh8_probe(const hostemu_scene* s, uint32_t mesh, const double* rays
     return 0;
 }
 
+// The four-wide collapse (what one lane per ray traverses: geometry.cuh, bvh4_intersect) against the binary tree, ray by
+// ray, same layout of the outputs; out_info = {4-wide nodes, empty child slots, binary node visits, 4-wide node visits,
+// binary triangle tests, 4-wide triangle tests}.
+int hostemu_bvh4_probe(const hostemu_scene* s, uint32_t mesh, const double* rays, uint64_t n, int any, double* out_t, int64_t* out_tri,
+                       uint64_t* out_info) {
+    if (mesh >= s->hs.t32.meshes.size()) return -1;
+    const MeshRec<float>& m = s->v32.meshes[mesh];
+    if (!m.bvh_nodes || !m.bvh4_nodes) return -1;
+    const HostMesh& hm = s->hs.meshes[mesh];
+    uint64_t empty = 0;
+    for (const Bvh4Node& nd : hm.bvh4_nodes)
+        empty += (nd.code.x == BVH8_EMPTY) + (nd.code.y == BVH8_EMPTY) + (nd.code.z == BVH8_EMPTY) + (nd.code.w == BVH8_EMPTY);
+    unsigned long long v2 = 0, v4 = 0, t2 = 0, t4 = 0;
+#pragma omp parallel for schedule(static) reduction(+ : v2, v4, t2, t4)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const double* r = rays + 6 * i;
+        const Vec3<float> o = {(float)r[0], (float)r[1], (float)r[2]}, d = {(float)r[3], (float)r[4], (float)r[5]};
+        for (int w = 0; w < 2; w++) {
+            TravStats ts = {0, 0, 0, 0, 0};
+            Hit<float> h;
+            h.t = INFINITY; h.obj = -1; h.aux = 0xFFFFFFFFu; h.bv = h.bw = 0.0f;
+            const bool hit = w == 0 ? bvh_intersect<true>(m, o, d, 1e-12f, any != 0, h, ts) : bvh4_intersect<true>(m, o, d, 1e-12f, any != 0, h, ts);
+            out_t[2 * i + w] = hit ? (double)h.t : (double)INFINITY;
+            out_tri[2 * i + w] = hit ? (int64_t)h.aux : -1;
+            (w == 0 ? v2 : v4) += ts.bvh_nodes;
+            (w == 0 ? t2 : t4) += ts.bvh_tris;
+        }
+    }
+    out_info[0] = hm.bvh4_nodes.size(); out_info[1] = empty; out_info[2] = v2; out_info[3] = v4 / 2; out_info[4] = t2; out_info[5] = t4;
+    return 0;
+}
+
 int hostemu_bvh_check(const hostemu_scene* s, uint32_t mesh, uint64_t* out) {
     const HostMesh& hm = s->hs.meshes[mesh];
     for (int i = 0; i < 6; i++) out[i] = 0;

@@ -138,4 +138,9 @@ def test_random_scene_renders(orc, seed):
     for ext_bvh in (False, True):
         g32, s32, _ = e.render(cam, r.precision(capi.PRECISION_F32).params(6), ext_bvh=ext_bvh)
         assert np.isfinite(g32[fin]).all()
-        assert util.rmse(cl(g32[fin]), cl(ref[fin])) <= 0.5 * noise + 1e-4, (ext_bvh, util.rmse(cl(g32[fin]), cl(ref[fin])), noise)
+        # same streams: the f32 image is the f64 image up to rounding, except where a path took another branch at a
+        # threshold (one path in thousands; it moves ONE pixel by up to the full range, so those are counted, not averaged)
+        dev = np.abs(cl(g32[fin]) - cl(ref[fin])).max(axis=1)
+        off = dev > 2e-2
+        assert off.mean() <= 0.005, (ext_bvh, off.sum())
+        assert util.rmse(cl(g32[fin][~off]), cl(ref[fin][~off])) <= 0.25 * noise + 1e-4, (ext_bvh, util.rmse(cl(g32[fin][~off]), cl(ref[fin][~off])), noise)

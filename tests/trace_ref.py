@@ -59,22 +59,21 @@ def philox_block(block, pixel, s_lo, s_hi, k0, k1):
 
 
 class Rng:
-    """Two 64-bit draws per block: (x0 | x1 << 32), then (x2 | x3 << 32); counter = (block, pixel, sample)."""
+    """64-bit draw 4b + w = (word w of Philox block b) << 32 | (word w of block b | 2^31); counter = (block, pixel, sample)."""
 
     def __init__(self, seed, pixel, sample):
         self.k0, self.k1 = seed & M32, (seed >> 32) & M32
         self.pixel, self.s_lo, self.s_hi = pixel, sample & M32, (sample >> 32) & M32
         self.block = 0
-        self.spare = None
+        self.pending = []
 
     def next_u64(self):
-        if self.spare is not None:
-            v, self.spare = self.spare, None
-            return v
-        x0, x1, x2, x3 = philox_block(self.block, self.pixel, self.s_lo, self.s_hi, self.k0, self.k1)
-        self.block += 1
-        self.spare = x2 | (x3 << 32)
-        return x0 | (x1 << 32)
+        if not self.pending:
+            hi = philox_block(self.block, self.pixel, self.s_lo, self.s_hi, self.k0, self.k1)
+            lo = philox_block(self.block | 0x80000000, self.pixel, self.s_lo, self.s_hi, self.k0, self.k1)
+            self.block += 1
+            self.pending = [(h << 32) | l for h, l in zip(hi, lo)]
+        return self.pending.pop(0)
 
     def gen(self):  # Standard f64: 53 bits
         return float(self.next_u64() >> 11) * (1.0 / 9007199254740992.0)
