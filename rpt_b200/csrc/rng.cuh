@@ -154,14 +154,16 @@ struct Rng<double> {
 //   BUF_PAIR  two draws enter a 4-entry FIFO, the other two wait in s0/s1           (6 words)
 //   BUF_FOUR  a 4-entry FIFO, refilled when empty                                    (4 words)
 //   BUF_EIGHT an 8-entry FIFO; a block enters whenever four entries are free          (8 words)
-//   BUF_TWO   the block being drawn from and the one after it, side by side           (8 words)
-// Measured on one B200 (gpurun r02r/r02s, Msamples/s at 64-100 spp; PAIR / FOUR / EIGHT / TWO):
-//   sphere 10 595 / 10 515 / 11 619 / 11 540, cornell 4 670 / 4 705 / 5 214 / 5 081, glass 19 620 / 20 631 / 20 359 / 20 846,
-//   teapot 17 253 / 18 802 / 17 201 / 17 119, monomial_glass 7 232 / 6 873 / 7 006 / 6 681.
+// Measured on one B200 (gpurun r02r/r02s, Msamples/s at 64-100 spp; PAIR / FOUR / EIGHT):
+//   sphere 10 595 / 10 515 / 11 619, cornell 4 670 / 4 705 / 5 214, glass 19 620 / 20 631 / 20 359,
+//   teapot 17 253 / 18 802 / 17 201, monomial_glass 7 232 / 6 873 / 7 006.
+// (Two more were tried and dropped -- the current block in a 4-entry FIFO plus the whole next block beside it, handed
+// over at the draw that empties the FIFO or at the next draw after: cornell 5 081 and 5 233, within 2 % of EIGHT; the
+// shared-memory ring below with four-word blocks: cornell 4 481.  profiles/r02_rng_buffering.md has the table.)
 // EIGHT keeps ensure() -- the converged point -- the place where nearly every block is computed (a lane holds >= 4
 // draws after it, and few slots draw more); FOUR is the smallest in registers, which is what the 64-register kernels of
 // the mesh scenes (F_BVH, 8 CTAs per SM) want.  The megakernel picks per instantiation (integrator.cuh, MegaRng).
-enum { BUF_PAIR = 0, BUF_FOUR = 1, BUF_EIGHT = 2, BUF_TWO = 3 };
+enum { BUF_PAIR = 0, BUF_FOUR = 1, BUF_EIGHT = 2 };
 #ifndef RPTB_FIFO_MODE
 #define RPTB_FIFO_MODE 2      // Rng<float>, and the megakernel's generator for scenes without a BVH
 #endif
@@ -274,39 +276,20 @@ struct RngBuf<BUF_EIGHT> : RngStream {
     RPTB_HD void ensure() {
         if (avail <= 4) push_block();
     }
-    RPTB_HD uint32_t next32() {
-        if (avail == 0) push_block();
-        const uint32_t v = q0;
-        q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5; q5 = q6; q6 = q7;
-        avail--;
-        return v;
-    }
-};
-
-template <>
-struct RngBuf<BUF_TWO> : RngStream {
-    // draws leave q0..q3 (three moves per draw, as in the 4-entry FIFO); a whole block enters either q (nothing
-    // buffered) or b (the block after: present iff avail > 4, and then q is not empty); b moves up when q runs empty
-    uint32_t q0, q1, q2, q3, b0, b1, b2, b3, avail;
-    RPTB_HD void clear() { q0 = q1 = q2 = q3 = b0 = b1 = b2 = b3 = 0; avail = 0; }
-    RPTB_HD void save(uint32_t* w) const { w[0] = q0; w[1] = q1; w[2] = q2; w[3] = q3; w[4] = b0; w[5] = b1; w[6] = b2; w[7] = b3; }
-    RPTB_HD void load(const uint32_t* w) { q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3]; b0 = w[4]; b1 = w[5]; b2 = w[6]; b3 = w[7]; }
-    RPTB_HD void push_block() {  // requires avail <= 4
+    // the refill at a draw site (a slot drew more than the FIFO held): the FIFO is empty, so no placement by count --
+    // next32() is inlined at ~20 sites, and with the switch above at each of them the kernel outgrew the instruction
+    // cache (ncu, Cornell: stall no_instruction 0.57 -> 2.58 warps per issue, issue-active 70.6 -> 65.6 %)
+    RPTB_HD void refill_empty() {
         uint32_t o[4];
         block4(o);
         half += 2;
-        if (avail == 0) { q0 = o[0]; q1 = o[1]; q2 = o[2]; q3 = o[3]; }
-        else { b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3]; }
-        avail += 4;
-    }
-    RPTB_HD void ensure() {
-        if (avail <= 4) push_block();
+        q0 = o[0]; q1 = o[1]; q2 = o[2]; q3 = o[3];
+        avail = 4;
     }
     RPTB_HD uint32_t next32() {
-        if (avail == 0) push_block();
+        if (avail == 0) refill_empty();
         const uint32_t v = q0;
-        q0 = q1; q1 = q2; q2 = q3;
-        if (avail == 5) { q0 = b0; q1 = b1; q2 = b2; q3 = b3; }  // that was q's last draw and b is waiting
+        q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5; q5 = q6; q6 = q7;
         avail--;
         return v;
     }
