@@ -32,9 +32,19 @@ def lib():
         L.hostemu_bvh_check.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.hostemu_bvh8_probe.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_int, dp, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
         L.hostemu_bvh4_probe.argtypes = L.hostemu_bvh8_probe.argtypes
+        L.hostemu_draws.restype = None
+        L.hostemu_draws.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.hostemu_illuminate.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_uint64, C.c_uint64, C.c_uint32, dp, dp, dp]
         _lib = L
     return _lib
+
+
+def draws(seed, pixel, sample, n, ensure_every=0):
+    """(u64[n], u32[4, n]): the stream as the f64 generator and as the four f32 buffers of rng.cuh hand it out."""
+    o64 = np.empty(n, np.uint64)
+    o32 = np.empty((4, n), np.uint32)
+    lib().hostemu_draws(seed, pixel, sample, n, ensure_every, o64.ctypes.data_as(C.POINTER(C.c_uint64)), o32.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return o64, o32
 
 
 class EmuScene:

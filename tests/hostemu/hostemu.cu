@@ -469,4 +469,35 @@ int hostemu_illuminate(const hostemu_scene* s, uint32_t light, const double* pos
     return 0;
 }
 
+// The first n draws of stream (seed, pixel, sample) as every generator of rng.cuh hands them out: out64 = the f64
+// generator's 64-bit draws; out32 = 4 x n words, row k = Rng buffering k (BUF_PAIR, BUF_FOUR, BUF_EIGHT) and row 3 the
+// shared-memory ring's host form.  `ensure_every` > 0: ensure() is called before every ensure_every-th draw, as the
+// integrator does at its converged points (the buffers must hand out the same words whenever they are refilled).
+void hostemu_draws(uint64_t seed, uint32_t pixel, uint64_t sample, uint32_t n, uint32_t ensure_every, uint64_t* out64, uint32_t* out32) {
+    Rng<double> r64;
+    r64.init(seed, pixel, sample);
+    for (uint32_t i = 0; i < n; i++) out64[i] = r64.p.next_u64();
+    RngF32<BUF_PAIR> a;
+    RngF32<BUF_FOUR> b;
+    RngF32<BUF_EIGHT> c;
+    RngRing d;
+    a.init(seed, pixel, sample);
+    b.init(seed, pixel, sample);
+    c.init(seed, pixel, sample);
+    d.bind(nullptr, 0);
+    d.init(seed, pixel, sample);
+    for (uint32_t i = 0; i < n; i++) {
+        if (ensure_every && i % ensure_every == 0) {
+            a.ensure();
+            b.ensure();
+            c.ensure();
+            d.ensure<HostLane>(1u, 1u + (i / ensure_every) % 8u);
+        }
+        out32[i] = a.next32();
+        out32[n + i] = b.next32();
+        out32[2 * n + i] = c.next32();
+        out32[3 * n + i] = d.next32();
+    }
+}
+
 }  // extern "C"

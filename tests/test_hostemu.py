@@ -520,3 +520,23 @@ def test_eight_wide_bvh_is_the_binary_bvh_collapsed(name):
     print(name, info4)
     ta4, _, _ = e.bvh4_probe(0, rays, any_hit=True)
     assert (np.isfinite(ta4[:, 1]) == hit).all()
+
+
+@pytest.mark.parametrize("ensure_every", [0, 1, 3, 7])
+def test_f32_generators_hand_out_the_high_halves_of_the_f64_draws(orc, ensure_every):
+    """rng.cuh: a path's 64-bit draws are two Philox streams side by side (draw 4b + w = word w of block b, over word w of
+    block b | 2^31), so that the f32 kernels -- which look at the high half only -- compute the first stream alone and use
+    every word of a block.  Whatever the buffering (two-and-two, four, eight, the ring) and wherever ensure() falls, the f32
+    generators hand out exactly the high halves of the f64 generator's draws, in order: that is what keeps every
+    same-stream parity test of the f32 path meaningful.  The halves themselves are pinned against the oracle's raw Philox
+    blocks (known-answer tested in test_oracle.py)."""
+    seed, pixel, sample, n = 0x0123456789ABCDEF, 4242, (7 << 32) | 9, 101
+    o64, o32 = emu.draws(seed, pixel, sample, n, ensure_every)
+    hi = (o64 >> np.uint64(32)).astype(np.uint32)
+    for k, name in enumerate(("pair", "four", "eight", "ring")):
+        np.testing.assert_array_equal(o32[k], hi, err_msg=name)
+    nb = (n + 3) // 4
+    first = orc.philox(seed, pixel, sample, nb).reshape(-1)[:n]
+    second = orc.philox(seed, pixel, sample, nb, first_block=0x80000000).reshape(-1)[:n]
+    np.testing.assert_array_equal(hi, first)
+    np.testing.assert_array_equal((o64 & np.uint64(0xFFFFFFFF)).astype(np.uint32), second)
