@@ -144,10 +144,9 @@ struct Rng<double> {
 // f32: only the HIGH 32-bit word of each 64-bit draw is kept -- its top 24 bits are the f64
 // value truncated to a float in [0,1), so both precisions see the same stream -- and the high
 // words are the first Philox stream's words in order (see the top of the file): a block is four
-// draws.  They enter a 4-entry register FIFO two at a time (the other two of a block wait in
-// s0/s1; `half` counts pairs, its low bit says a pair is waiting) from ensure(), which the
-// integrator calls where the whole warp is converged: the ~60-instruction Philox block then runs
-// once for 32 lanes instead of once per lane per call site.
+// draws.  They wait in a register FIFO (RngBuf below) that ensure() refills -- the integrator
+// calls it where the whole warp is converged: the ~60-instruction Philox block then runs once
+// for 32 lanes instead of once per lane per call site (`half` counts pairs of draws produced).
 // gen_bool / Uniform(0..n) decide on the high word alone; the decision differs from the
 // 64-bit one with probability <= n * 2^-32 per draw (f32 mode only).
 // How the four draws of a block are buffered is a template parameter (same stream, bit for bit, whichever):
@@ -325,7 +324,8 @@ struct RngF32 : RngBuf<BUF> {
 template <>
 struct Rng<float> : RngF32<RPTB_FIFO_MODE> {};
 
-// The megakernel's f32 generator: the same stream as Rng<float> (high word of every 64-bit draw), buffered in an
+// The alternative to the register FIFOs (RPTB_RNG_FIFO 0; what the vertex-at-once engine draws from): the same stream
+// as Rng<float> (high word of every 64-bit draw), buffered in an
 // 8-entry ring per thread that lives in SHARED memory on the device (entry i of thread t at ring[i * stride + t]:
 // one bank per lane, no conflicts; a ring in registers would need shuffling moves per draw and four more live
 // registers in a kernel that already spills).  What this buys (ncu, Cornell, round 2): with the 4-entry register FIFO
@@ -337,9 +337,10 @@ constexpr uint32_t RNG_RING = 8;
 #define RPTB_RNG_FILL 0
 #endif
 #ifndef RPTB_RNG_FIFO
-// 1 = the slot engine keeps the 4-entry register FIFO (Rng<float>), 0 = it draws from the ring below.  Measured on one
-// B200 with everything else equal (gpurun r02h, Msamples/s, FIFO / ring topped up to 6 / ring topped up on demand):
-// cornell 5 676 / 5 252 / 4 919, glass 20 553 / 14 676 / 15 590, sphere 9 284 / 9 638 / 8 908 -- the ring does raise the
+// 1 = the slot engine keeps a register FIFO (RngF32), 0 = it draws from the ring below.  Measured on one B200 with
+// everything else equal, Msamples/s, FIFO / ring topped up / ring topped up on demand -- while a block still was two
+// draws (gpurun r02h): cornell 5 676 / 5 252 / 4 919, glass 20 553 / 14 676 / 15 590, sphere 9 284 / 9 638 / 8 908; with
+// four-word blocks (r02r): cornell 5 214 / 4 347 / 4 481, glass 20 359 / 17 374 / 19 432 -- the ring does raise the
 // lanes per Philox instruction (7.4 -> 11.2, ncu) but its shared-memory traffic and vote loops cost more than that saves,
 // so the FIFO is the default and the ring is what the vertex-at-once engine (integrator_vx.cuh) uses.
 #define RPTB_RNG_FIFO 1
