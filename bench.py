@@ -440,6 +440,12 @@ def run_native(args):
                 ctr, _, _ = sj.counters(probe_spp)   # counters per segment at reduced spp (they scale with the sample count)
                 sj.render(spp=probe_spp)             # warm-up of the plain kernel
                 sj.assemble()
+                # ... and one un-timed render at the full size: the first full-size launch of a process is slower than the
+                # ones after it (measured, tools/gpu_fullspp_repeat.py, two processes alike: dragon 1 688 / 1 709 then 1 821 /
+                # 1 851, glass 20 787 / 20 562 then 21 233 / 21 209 Msamples/s; it is also the first launch that needs the
+                # full set of chunk sums in scratch)
+                sj.render()
+                sj.assemble()
                 stream.synchronize()
                 barrier()
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -463,7 +469,8 @@ def run_native(args):
                 ach = bytes_all / world / (t_kern / 1e3) / 1e9
                 secondary[scfg.name] = {
                     "config": "%s %dx%d, %d spp total, max_bounces %d; %s" % (scfg.name, scfg.width, scfg.height, scfg.spp, scfg.max_bounces, scfg.note),
-                    "scaling": "strong", "steps": 1, "value": segs / (t_step / 1e3) / 1e6, "unit": UNIT,
+                    "scaling": "strong", "steps": 1, "warmup": "one %d-spp render + one full-size render" % probe_spp,
+                    "value": segs / (t_step / 1e3) / 1e6, "unit": UNIT,
                     "ms_per_step": t_step, "kernel_ms_max_rank": t_kern, "segments": segs, "rays": rays,
                     "image_mean": float(sj.image.mean().item()), "device_scene_bytes": sj.r.device_scene().device_bytes(),
                     "clocks": sclocks,
