@@ -115,7 +115,7 @@ def test_random_scene_queries(orc, seed):
         assert ((occ == 1) == (o0 >= 0)).mean() >= 0.995
 
 
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(8))
 def test_random_scene_renders(orc, seed):
     scene, rng = random_scene(200 + seed)
     cam = api.Camera.look_at(api.vec3(*(util.random_unit(rng, 1)[0] * 11.0)), api.vec3(0.0, 0.0, 0.0), api.vec3(0.0, 1.0, 0.0), 0.9)
